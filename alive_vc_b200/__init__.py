@@ -1,0 +1,17 @@
+"""alive_vc_b200 - B200-native kNN voice-library matching (ALiVE-VC hot path).
+
+Public surface = the reference's own Python symbols for this path:
+    match_features(source, reference, k=4, alpha=0.0)      module/common.py:96
+    VoiceLibrary(num_tokens=512, hubert_dim=768)           module/voice_library.py:6
+plus the packed-library handles the kernels work on (pack_library, match_packed,
+match_indices, ShardedLibrary).  Everything runs through the C ABI in
+include/alive_knn.h (alive_vc_b200/libalive_knn.so, sm_100a); there is no fallback.
+"""
+from .matching import (PackedFrames, clear_pack_cache, match_features, match_indices, match_packed,
+                       pack_frames, pack_library, search_topk)
+from .voice_library import VoiceLibrary
+
+__all__ = [
+    "match_features", "VoiceLibrary", "match_indices", "match_packed", "pack_library", "pack_frames",
+    "search_topk", "PackedFrames", "clear_pack_cache",
+]

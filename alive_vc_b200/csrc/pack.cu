@@ -1,0 +1,117 @@
+// K1 - L2-normalise and pack frames (library once, queries per call).
+//
+// Reference lines replaced: module/common.py:100-104 (transpose views, torch.norm,
+// `x / norm`) - the reference redoes this for the WHOLE library on every call
+// (SURVEY §0); here it runs once per library and once per query batch.
+//
+// Input  x[i*stride_n + j*stride_d]  (reference layout [1,D,N]: stride_n=1, stride_d=N)
+// Output raw    [n,d] f32  row-major copy of the raw frames (gather + exact rescoring)
+//        norms  [n]   f32  sqrt(sum x^2), sum in fp64
+//        packed [n,d] bf16 row-major x/|x| (IEEE division, then round-to-nearest-even)
+//        err    [n]   f32  || bf16(x/|x|) - x/|x| ||_2   (screening error bound input)
+//        stats  [0] atomicMax of err bits, [1] count of non-finite normalised rows
+//
+// HBM-bound: algorithmic bytes per frame = d*(4 read + 4 raw + 2 packed) = 7,680 B at d=768.
+// A CTA owns 32 consecutive frames: the channel-major input is read as 128-byte rows
+// (32 frames x 4 B, coalesced), staged transposed in shared memory, and written back as
+// full 3 KB / 1.5 KB frame rows.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace alive {
+namespace {
+
+constexpr int kFrames = 32;        // frames per CTA
+constexpr int kPackThreads = 256;  // 8 warps
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
+            float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
+            float* __restrict__ err, unsigned int* __restrict__ stats) {
+  extern __shared__ float tile[];          // [d][kFrames + 1]
+  const int ld = kFrames + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long f0 = static_cast<long long>(blockIdx.x) * kFrames;
+  const int nf = static_cast<int>(min(static_cast<long long>(kFrames), n - f0));
+
+  if (stride_n == 1 || stride_d != 1) {
+    // frames are the fast axis (or fully strided): lane = frame, warps stride over channels
+    const bool ok = lane < nf;
+    const float* src = x + (f0 + lane) * stride_n;
+    for (int j = warp; j < d; j += kPackThreads / 32) tile[j * ld + lane] = ok ? src[j * stride_d] : 0.f;
+  } else {
+    // already row-major frames: lane = channel
+    for (int f = warp; f < kFrames; f += kPackThreads / 32) {
+      const float* src = x + (f0 + f) * stride_n;
+      for (int j = lane; j < d; j += 32) tile[j * ld + f] = (f < nf) ? src[j] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // each warp finishes whole frames: 4 frames per warp
+  for (int f = warp; f < nf; f += kPackThreads / 32) {
+    const long long row = f0 + f;
+    double ss = 0.0;
+    for (int j = lane; j < d; j += 32) {
+      const float v = tile[j * ld + f];
+      raw[row * d + j] = v;
+      ss += static_cast<double>(v) * static_cast<double>(v);
+    }
+    ss = warp_sum_f64(ss);
+    const float nrm = static_cast<float>(sqrt(ss));
+    double e2 = 0.0;
+    bool finite = true;
+    // two channels per lane so the bf16 row is written as 4-byte words
+    for (int j = 2 * lane; j < d; j += 64) {
+      const float a = __fdiv_rn(tile[j * ld + f], nrm);
+      const float b = __fdiv_rn(tile[(j + 1) * ld + f], nrm);
+      const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+      const float da = __bfloat162float(ha) - a, db = __bfloat162float(hb) - b;
+      e2 += static_cast<double>(da) * da + static_cast<double>(db) * db;
+      finite = finite && isfinite(a) && isfinite(b);
+      __nv_bfloat162 h2;
+      h2.x = ha;
+      h2.y = hb;
+      *reinterpret_cast<__nv_bfloat162*>(packed + row * d + j) = h2;
+    }
+    e2 = warp_sum_f64(e2);
+    finite = __all_sync(0xffffffffu, finite);
+    if (lane == 0) {
+      norms[row] = nrm;
+      // round the error norm UP a little: it feeds a bound that must not be under-estimated
+      float e = finite ? static_cast<float>(sqrt(e2)) * 1.0001f + 1e-9f : 0.f;
+      if (err) err[row] = e;
+      if (stats) {
+        if (finite) atomicMax(&stats[0], __float_as_uint(e));
+        else atomicAdd(&stats[1], 1u);
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace alive
+
+extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
+                              float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
+                              alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(x && raw && norms && packed, "alive_knn_pack: NULL argument");
+  ALIVE_REQUIRE(n >= 0 && n < (1ll << 31), "alive_knn_pack: n out of range (%lld)", static_cast<long long>(n));
+  ALIVE_REQUIRE(d >= 2 && d % 2 == 0 && d <= 1536, "alive_knn_pack: d must be even and <= 1536 (got %d)", d);
+  ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 3) == 0, "alive_knn_pack: packed must be 4-byte aligned");
+  if (n == 0) return 0;
+  const size_t smem = static_cast<size_t>(d) * (kFrames + 1) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * (kFrames + 1) * 4));
+    attr_done = true;
+  }
+  const unsigned grid = static_cast<unsigned>((n + kFrames - 1) / kFrames);
+  pack_kernel<<<grid, kPackThreads, smem, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw, norms,
+                                                              reinterpret_cast<__nv_bfloat16*>(packed), err, stats);
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

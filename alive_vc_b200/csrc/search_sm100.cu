@@ -1,0 +1,635 @@
+// K2 - fused cosine-similarity contraction + running top list (sm_100a).
+//
+// Replaces the `torch.bmm` of module/common.py:104 (voice_library.py:28) and the
+// scan of `torch.topk` (:105 / :29) of the reference, without ever writing the
+// [T,N] score matrix to HBM.
+//
+// Shape of the computation
+//   scores[t, n] = sum_d Q[t,d] * L[n,d]     Q [T,768] bf16, L [N,768] bf16, both
+//                                            row-major = "K-major" for the MMA.
+//   One work unit = (group of 128*kCtas queries) x (segment of whole 256-frame
+//   tiles of the library).  A persistent CTA (or CTA pair) walks its units; per
+//   tile it issues 48 tcgen05.mma (M=128*kCtas, N=256, K=16) into one of two
+//   256-column TMEM accumulators while the 8 epilogue warps drain the other one.
+//
+// Warp roles (384 threads):
+//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor, 128B swizzle, mbarrier tx
+//   warp 1      MMA issuer     (one lane, leader CTA only): tcgen05.mma + tcgen05.commit
+//   warp 2      TMEM allocator (512 columns) / deallocator
+//   warp 3      idle
+//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. (= 32 queries) and
+//               columns 128*((w-4)/4).. of every tile; each THREAD owns one query
+//               row and keeps a sorted 8-entry (score, frame) list in registers.
+//               tcgen05.ld 32x32b.x32 -> chunk max -> rare ordered insert.
+//
+// Output: per (query, list) the 8 best screened (score, frame) pairs; list id =
+// 2*segment + column half.  The list minimum is an upper bound on every score
+// the list dropped, which is what the certificate in select.cu needs.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace alive {
+namespace {
+
+constexpr int kBlockM = ALIVE_KNN_TILE_M;   // 128 queries per CTA (TMEM lanes)
+constexpr int kBlockN = ALIVE_KNN_TILE_N;   // 256 library frames per tile (TMEM columns)
+constexpr int kBlockK = 64;                 // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kListLen = ALIVE_KNN_LIST_LEN;
+constexpr int kNumEpiWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);   // 384
+constexpr int kTmemCols = 512;                                  // 2 accumulators x 256 columns
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;             // 16 KB per stage per CTA
+
+template <int kCtas> struct Cfg {
+  static constexpr int kStages = (kCtas == 1) ? 4 : 6;
+  static constexpr int kBRows = kBlockN / kCtas;                       // library rows this CTA loads per tile
+  static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;            // 32 KB or 16 KB
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTxBytes = kStageBytes * kCtas;            // bytes landing per stage, whole unit
+  static constexpr uint32_t kSmemData = kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = kSmemData + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct SearchParams {
+  int t;
+  int n;
+  int k_blocks;        // d / 64
+  int m_units;
+  int segments;
+  int tiles_per_segment;
+  int n_tiles;
+  int lists;
+  float* cand_score;
+  int* cand_idx;
+  int debug;           // diagnostics only: 1 = epilogue skips the scan, 2 = also skips the TMEM loads
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of `local_addr` (a shared::cta address) inside CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier given by a shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+      printf("alive_knn_search: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
+}
+template <int kCtas>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
+  if constexpr (kCtas == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    // data lands in THIS CTA's smem, the transaction bytes are reported to the barrier at
+    // `bar` (a shared::cluster address inside the leader CTA of the pair)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int kCtas> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (kCtas == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+template <int kCtas> __device__ __forceinline__ void tmem_relinquish() {
+  if constexpr (kCtas == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCtas> __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  if constexpr (kCtas == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major bf16 tile stored as 128-byte rows with the
+// 128B swizzle TMA applies (8-row groups of 1024 B): start>>4 | LBO(16B, unused)=1 |
+// SBO = 1024 B | version 1 (Blackwell) | layout SWIZZLE_128B (=2 in bits 61..63).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+template <int kCtas>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kCtas == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
+template <int kCtas> __device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (kCtas == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    // same barrier offset in both CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(static_cast<uint16_t>(3))
+        : "memory");
+  }
+}
+
+#define ALIVE_R32(v)                                                                               \
+  v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14],    \
+      v[15], v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27],    \
+      v[28], v[29], v[30], v[31]
+
+// 32 lanes x 32 consecutive fp32 columns: thread i receives TMEM lane (base lane + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld that also "touches" the destination registers so the compiler cannot
+// schedule their first use above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+// Ordered insert of (v, idx) into the descending list; requires v > s[kListLen-1].
+// Equal scores keep the earlier (lower) frame first.
+__device__ __forceinline__ void list_insert(float (&s)[kListLen], uint32_t (&id)[kListLen], float v, uint32_t idx) {
+#pragma unroll
+  for (int i = kListLen - 1; i >= 1; --i) {
+    const bool above = v > s[i - 1];   // v also displaces entry i-1 -> entry i-1 shifts down into i
+    const bool here = v > s[i];
+    s[i] = above ? s[i - 1] : (here ? v : s[i]);
+    id[i] = above ? id[i - 1] : (here ? idx : id[i]);
+  }
+  const bool top = v > s[0];
+  s[0] = top ? v : s[0];
+  id[0] = top ? idx : id[0];
+}
+
+// One 32-column chunk of one query row: reject with a single max tree when nothing beats the
+// list minimum (the common case), otherwise insert in column order.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_base, int n_valid,
+                                           float (&s)[kListLen], uint32_t (&id)[kListLen]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  if (col_base + 32 > n_valid) {   // ragged last tile of the library (warp-uniform branch)
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col_base + j >= n_valid) v[j] = -INFINITY;
+  }
+  float m = v[0];
+#pragma unroll
+  for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+  if (m > s[kListLen - 1]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (v[j] > s[kListLen - 1]) list_insert(s, id, v[j], static_cast<uint32_t>(col_base + j));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int kCtas>
+__global__ void __launch_bounds__(kThreads, 1)
+knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_lib,
+                  const SearchParams p) {
+  using C = Cfg<kCtas>;
+  constexpr int kStages = C::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024 B alignment
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + kStages * kABytes;
+  const uint32_t bars = smem_base + C::kSmemData;
+  const uint32_t bar_full = bars;                                // kStages x 8 B
+  const uint32_t bar_empty = bars + 8 * kStages;                 // kStages x 8 B
+  const uint32_t bar_tfull = bars + 16 * kStages;                // 2 x 8 B
+  const uint32_t bar_tempty = bars + 16 * kStages + 16;          // 2 x 8 B
+  const uint32_t tmem_slot = bars + 16 * kStages + 32;           // 4 B
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtas == 1) ? 0u : cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int unit_stride = gridDim.x / kCtas;
+  const int first_unit = blockIdx.x / kCtas;
+  const int total_units = p.m_units * p.segments;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_lib);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);    // the leader's arrive.expect_tx; bytes of both CTAs land here
+      mbar_init(bar_empty + 8 * s, 1);   // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);                        // one tcgen05.commit
+      mbar_init(bar_tempty + 8 * a, kNumEpiWarps * kCtas);    // one arrive per epilogue warp of the unit
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kCtas>(tmem_slot, kTmemCols);
+    tmem_relinquish<kCtas>();
+  }
+  tcgen05_fence_before();
+  if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      const uint32_t full0 = (kCtas == 1) ? bar_full : map_to_cta(bar_full, 0);   // barrier lives in the leader
+      uint32_t it = 0;
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        const int m_unit = unit % p.m_units;
+        const int seg = unit / p.m_units;
+        const int tile0 = seg * p.tiles_per_segment;
+        const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
+        const int q_row = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          const int lib_row = tile * kBlockN + static_cast<int>(cta_rank) * C::kBRows;
+          for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+            const uint32_t stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1u;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            if (leader) mbar_expect_tx(bar_full + 8 * stage, C::kTxBytes);
+            tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row);
+            tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN);
+      uint32_t it = 0, tile_count = 0;
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        const int seg = unit / p.m_units;
+        const int tile0 = seg * p.tiles_per_segment;
+        const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
+        for (int tile = tile0; tile < tile1; ++tile, ++tile_count) {
+          const uint32_t acc = tile_count & 1u;
+          const uint32_t acc_phase = (tile_count >> 1) & 1u;
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);   // epilogue drained this accumulator
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kBlockN;
+          for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+            const uint32_t stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1u;
+            mbar_wait(bar_full + 8 * stage, phase);
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_a + stage * kABytes);
+            const uint64_t bdesc = make_smem_desc(smem_b + stage * C::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_bf16<kCtas>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<kCtas>(bar_empty + 8 * stage);   // smem slot reusable once these MMAs retire
+          }
+          umma_commit<kCtas>(bar_tfull + 8 * acc);       // accumulator complete -> epilogue
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    // ======================================= epilogue =======================================
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - kFirstEpiWarp) >> 2;       // which 128 columns of each tile
+    const uint32_t tempty0 = (kCtas == 1) ? bar_tempty : map_to_cta(bar_tempty, 0);
+    const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+    uint32_t tile_count = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+      const int m_unit = unit % p.m_units;
+      const int seg = unit / p.m_units;
+      const int tile0 = seg * p.tiles_per_segment;
+      const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
+      const int row = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
+      const bool row_valid = row < p.t;
+
+      float s[kListLen];
+      uint32_t id[kListLen];
+#pragma unroll
+      for (int i = 0; i < kListLen; ++i) {
+        s[i] = row_valid ? -INFINITY : INFINITY;   // padded query rows never insert
+        id[i] = 0xFFFFFFFFu;
+      }
+
+      for (int tile = tile0; tile < tile1; ++tile, ++tile_count) {
+        const uint32_t acc = tile_count & 1u;
+        const uint32_t acc_phase = (tile_count >> 1) & 1u;
+        mbar_wait(bar_tfull + 8 * acc, acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = taddr_base + acc * kBlockN;
+        const int col0 = tile * kBlockN + half * 128;
+        uint32_t va[32], vb[32];
+        if (p.debug == 2) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtas == 1) mbar_arrive(bar_tempty + 8 * acc);
+            else mbar_arrive_cluster(tempty0 + 8 * acc);
+          }
+          continue;
+        }
+        tmem_ld_32x32(taddr, va);
+        tmem_ld_wait(va);
+        tmem_ld_32x32(taddr + 32, vb);
+        if (p.debug == 0) scan_chunk(va, col0, p.n, s, id);
+        else s[0] = fmaxf(s[0], __uint_as_float(va[lane]));
+        tmem_ld_wait(vb);
+        tmem_ld_32x32(taddr + 64, va);
+        if (p.debug == 0) scan_chunk(vb, col0 + 32, p.n, s, id);
+        else s[0] = fmaxf(s[0], __uint_as_float(vb[lane]));
+        tmem_ld_wait(va);
+        tmem_ld_32x32(taddr + 96, vb);
+        if (p.debug == 0) scan_chunk(va, col0 + 64, p.n, s, id);
+        else s[0] = fmaxf(s[0], __uint_as_float(va[lane]));
+        tmem_ld_wait(vb);
+        // all TMEM reads of this accumulator are done: hand it back before the last scan
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtas == 1) mbar_arrive(bar_tempty + 8 * acc);
+          else mbar_arrive_cluster(tempty0 + 8 * acc);
+        }
+        if (p.debug == 0) scan_chunk(vb, col0 + 96, p.n, s, id);
+        else s[0] = fmaxf(s[0], __uint_as_float(vb[lane]));
+      }
+
+      if (row_valid) {
+        const size_t o = (static_cast<size_t>(row) * p.lists + static_cast<size_t>(seg * 2 + half)) * kListLen;
+        float4* ps = reinterpret_cast<float4*>(p.cand_score + o);
+        int4* pi = reinterpret_cast<int4*>(p.cand_idx + o);
+        ps[0] = make_float4(s[0], s[1], s[2], s[3]);
+        ps[1] = make_float4(s[4], s[5], s[6], s[7]);
+        pi[0] = make_int4(static_cast<int>(id[0]), static_cast<int>(id[1]), static_cast<int>(id[2]), static_cast<int>(id[3]));
+        pi[1] = make_int4(static_cast<int>(id[4]), static_cast<int>(id[5]), static_cast<int>(id[6]), static_cast<int>(id[7]));
+      }
+    }
+  }
+
+  // ------------------------------------------ teardown ------------------------------------------
+  tcgen05_fence_before();
+  if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<kCtas>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// [rows, d] bf16 row-major -> 2-D map, box = 64 elements (128 B) x box_rows, 128B swizzle, OOB = 0
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t d, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return -3;
+  }
+  cuuint64_t gdim[2] = {d, rows};
+  cuuint64_t gstride[1] = {d * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu d=%llu box_rows=%u base=%p)",
+              static_cast<int>(r), static_cast<unsigned long long>(rows), static_cast<unsigned long long>(d),
+              box_rows, base);
+    return -3;
+  }
+  return 0;
+}
+
+template <int kCtas>
+int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t& plan, float* cand_score,
+                  int32_t* cand_idx, cudaStream_t stream) {
+  using C = Cfg<kCtas>;
+  CUtensorMap mq, ml;
+  int rc = make_map(&mq, q, static_cast<uint64_t>(plan.t), static_cast<uint64_t>(plan.d), kBlockM);
+  if (rc) return rc;
+  rc = make_map(&ml, lib, static_cast<uint64_t>(plan.n), static_cast<uint64_t>(plan.d), C::kBRows);
+  if (rc) return rc;
+  SearchParams p;
+  p.t = plan.t;
+  p.n = static_cast<int>(plan.n);
+  p.k_blocks = plan.d / kBlockK;
+  p.m_units = plan.m_units;
+  p.segments = plan.segments;
+  p.tiles_per_segment = plan.tiles_per_segment;
+  p.n_tiles = plan.n_tiles;
+  p.lists = plan.lists;
+  p.cand_score = cand_score;
+  p.cand_idx = cand_idx;
+  {
+    const char* dbg = getenv("ALIVE_KNN_DEBUG_EPILOGUE");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(knn_search_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(C::kSmemBytes)));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ALIVE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_search_kernel<kCtas>, mq, ml, p));
+  return 0;
+}
+
+}  // namespace
+}  // namespace alive
+
+extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
+                              alive_knn_plan_t* plan) {
+  using namespace alive;
+  ALIVE_REQUIRE(plan != nullptr, "alive_knn_plan: plan is NULL");
+  ALIVE_REQUIRE(t >= 1, "alive_knn_plan: t must be >= 1 (got %d)", t);
+  ALIVE_REQUIRE(n >= 1 && n < (1ll << 31) - 512, "alive_knn_plan: n out of range (%lld)", static_cast<long long>(n));
+  ALIVE_REQUIRE(d >= 64 && d % 64 == 0 && d <= 8192, "alive_knn_plan: d must be a multiple of 64 (got %d)", d);
+  ALIVE_REQUIRE(num_sms >= 2, "alive_knn_plan: num_sms must be >= 2");
+  if (variant == 0) variant = 1;
+  ALIVE_REQUIRE(variant == 1 || variant == 2, "alive_knn_plan: variant must be 0, 1 or 2");
+  const int ctas = variant;
+  const int slots = num_sms / ctas;   // units that run concurrently
+  plan->t = t;
+  plan->n = n;
+  plan->d = d;
+  plan->ctas_per_unit = ctas;
+  plan->m_units = (t + kBlockM * ctas - 1) / (kBlockM * ctas);
+  plan->n_tiles = static_cast<int32_t>((n + kBlockN - 1) / kBlockN);
+  // Segments: enough units to fill every SM, at least 16 per query group when the library is
+  // long (more, shorter lists make the completeness certificate easy), and as few idle
+  // tile-slots in the last wave as possible.
+  const int n_tiles = plan->n_tiles;
+  int s_lo = (slots + plan->m_units - 1) / plan->m_units;
+  if (s_lo < 16) s_lo = 16;
+  if (s_lo > n_tiles) s_lo = n_tiles;
+  int s_hi = s_lo * 4;
+  if (s_hi > n_tiles) s_hi = n_tiles;
+  long long best_cost = -1;
+  int best_tps = 1;
+  for (int s = s_lo; s <= s_hi; ++s) {
+    const int tps = (n_tiles + s - 1) / s;
+    const int s_eff = (n_tiles + tps - 1) / tps;
+    const long long units = static_cast<long long>(plan->m_units) * s_eff;
+    const long long waves = (units + slots - 1) / slots;
+    const long long cost = waves * tps;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_tps = tps;
+    }
+  }
+  plan->tiles_per_segment = best_tps;
+  plan->segments = (n_tiles + best_tps - 1) / best_tps;
+  plan->lists = plan->segments * 2;
+  const long long units = static_cast<long long>(plan->m_units) * plan->segments;
+  plan->grid = static_cast<int32_t>((units < slots ? units : slots) * ctas);
+  return 0;
+}
+
+extern "C" int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,
+                                const alive_knn_plan_t* plan, float* cand_score, int32_t* cand_idx,
+                                alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(plan && q_packed && lib_packed && cand_score && cand_idx, "alive_knn_search: NULL argument");
+  ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(q_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(lib_packed) & 15) == 0,
+                "alive_knn_search: packed operands must be 16-byte aligned");
+  ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(cand_score) & 15) == 0 && (reinterpret_cast<uintptr_t>(cand_idx) & 15) == 0,
+                "alive_knn_search: candidate buffers must be 16-byte aligned");
+  ALIVE_REQUIRE(plan->d % 64 == 0 && plan->grid > 0 && plan->grid % plan->ctas_per_unit == 0, "alive_knn_search: bad plan");
+  if (plan->ctas_per_unit == 1) return launch_search<1>(q_packed, lib_packed, *plan, cand_score, cand_idx, as_stream(stream));
+  if (plan->ctas_per_unit == 2) return launch_search<2>(q_packed, lib_packed, *plan, cand_score, cand_idx, as_stream(stream));
+  set_error("alive_knn_search: ctas_per_unit must be 1 or 2");
+  return -1;
+}

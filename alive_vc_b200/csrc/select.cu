@@ -1,0 +1,438 @@
+// K2b/K3 - certificate + prune, exact rescoring, exact scan, multi-GPU merge.
+//
+// Reference lines mirrored: module/common.py:102-105 (voice_library.py:26-29):
+//   normalise each frame first (x / |x|, float32 IEEE division), then the dot product,
+//   then torch.topk (largest, sorted, NaN first).  The dot is accumulated in fp64 and
+//   rounded once, i.e. it is the correctly rounded value the reference's fp32 sgemm
+//   approximates; ties resolve to the lowest frame index.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace alive {
+namespace {
+
+constexpr int kListLen = ALIVE_KNN_LIST_LEN;
+constexpr int kMaxK = ALIVE_KNN_MAX_K;
+constexpr int kMaxRMax = 256;
+// slack added to the screening error bound: fp32 accumulation inside the tensor core over
+// d <= 1536 terms with |partial sums| <= 1 (d * 2^-22 = 3.7e-4 worst case) + final roundings
+constexpr float kAccumSlack = 4.0e-4f;
+
+__device__ __forceinline__ float warp_max_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// prune: one warp per query
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prune_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
+             const float* __restrict__ q_err, const float* __restrict__ q_norm,
+             const unsigned int* __restrict__ lib_stats, int r_max, int* __restrict__ sel_idx,
+             int* __restrict__ sel_n, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= t) return;
+  const int entries = lists * kListLen;
+  const float* sc = cand_score + static_cast<size_t>(q) * entries;
+  const int* ix = cand_idx + static_cast<size_t>(q) * entries;
+
+  // tau: upper bound on every screened score that any list dropped (= max of list minima;
+  // a list that never filled has minimum -inf and dropped nothing)
+  float tau = -INFINITY;
+  for (int l = lane; l < lists; l += 32) tau = fmaxf(tau, sc[l * kListLen + kListLen - 1]);
+  tau = warp_max_f32(tau);
+
+  // S_k: k-th largest screened score, by k passes under the total order (score desc, pos asc)
+  float prev_s = INFINITY;
+  int prev_p = -1;
+  float sk = -INFINITY;
+  for (int r = 0; r < k; ++r) {
+    float best_s = -INFINITY;
+    int best_p = 0x7fffffff;
+    for (int e = lane; e < entries; e += 32) {
+      const float s = sc[e];
+      const bool after_prev = (s < prev_s) || (s == prev_s && e > prev_p);
+      if (after_prev && (s > best_s || (s == best_s && e < best_p))) {
+        best_s = s;
+        best_p = e;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, best_s, o);
+      const int op = __shfl_xor_sync(0xffffffffu, best_p, o);
+      if (os > best_s || (os == best_s && op < best_p)) {
+        best_s = os;
+        best_p = op;
+      }
+    }
+    prev_s = best_s;
+    prev_p = best_p;
+    sk = best_s;
+  }
+
+  const float le = __uint_as_float(lib_stats[0]);
+  const float qe = q_err[q];
+  const float eps = (le + qe + le * qe + kAccumSlack) * 1.00001f;
+  const float cut = sk - 2.0f * eps - 1e-7f;
+  const float qn = q_norm[q];
+  bool fallback = lib_stats[1] != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > tau);
+
+  int count = 0;
+  if (!fallback) {
+    for (int e0 = 0; e0 < entries; e0 += 32) {
+      const int e = e0 + lane;
+      const bool keep = e < entries && sc[e] >= cut && ix[e] >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int pos = count + __popc(m & ((1u << lane) - 1u));
+      if (keep && pos < r_max) sel_idx[static_cast<size_t>(q) * r_max + pos] = ix[e];
+      count += __popc(m);
+    }
+    if (count > r_max || count < k) fallback = true;
+  }
+  if (lane == 0) {
+    if (fallback) {
+      sel_n[q] = -1;
+      fb_list[atomicAdd(fb_count, 1)] = q;
+    } else {
+      sel_n[q] = count;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact similarity of one library frame against a normalised query held in shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dot_norm_f64(const float* __restrict__ qh, const float* __restrict__ row,
+                                               float nrm, int d, int lane) {
+  double acc = 0.0;
+  for (int j = lane * 4; j < d; j += 128) {
+    const float4 r = *reinterpret_cast<const float4*>(row + j);
+    const float4 a = *reinterpret_cast<const float4*>(qh + j);
+    acc += static_cast<double>(a.x) * static_cast<double>(__fdiv_rn(r.x, nrm));
+    acc += static_cast<double>(a.y) * static_cast<double>(__fdiv_rn(r.y, nrm));
+    acc += static_cast<double>(a.z) * static_cast<double>(__fdiv_rn(r.z, nrm));
+    acc += static_cast<double>(a.w) * static_cast<double>(__fdiv_rn(r.w, nrm));
+  }
+  return warp_sum_f64(acc);
+}
+
+// top-k of (sc[i], id[i]) i<n by k selection rounds, executed by one warp
+__device__ __forceinline__ void warp_select_topk(const float* sc, const long long* id, int n, int k,
+                                                 float* out_s, long long* out_i, long long base, int lane) {
+  float ps = 0.f;
+  long long pi = -1;
+  bool first = true;
+  for (int r = 0; r < k; ++r) {
+    float bs = 0.f;
+    long long bi = -1;
+    bool have = false;
+    for (int e = lane; e < n; e += 32) {
+      const float s = sc[e];
+      const long long i = id[e];
+      if (i < 0) continue;
+      if (!first && !score_better(ps, pi, s, i)) continue;   // not strictly after the previous winner
+      if (!have || score_better(s, i, bs, bi)) {
+        bs = s;
+        bi = i;
+        have = true;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int oh = __shfl_xor_sync(0xffffffffu, static_cast<int>(have), o);
+      if (oh && (!have || score_better(os, oi, bs, bi))) {
+        bs = os;
+        bi = oi;
+        have = true;
+      }
+    }
+    ps = bs;
+    pi = bi;
+    first = false;
+    if (lane == 0) {
+      out_s[r] = have ? bs : -INFINITY;
+      out_i[r] = have ? bi + base : -1;
+    }
+    if (!have) {   // fewer than k valid entries (caller guarantees this cannot happen)
+      for (int r2 = r + 1; r2 < k; ++r2)
+        if (lane == 0) {
+          out_s[r2] = -INFINITY;
+          out_i[r2] = -1;
+        }
+      break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// rescore: one CTA (4 warps) per query
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+rescore_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm, int t,
+               const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, int d,
+               const int* __restrict__ sel_idx, const int* __restrict__ sel_n, int r_max, int k,
+               long long idx_base, float* __restrict__ top_score, long long* __restrict__ top_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qh = reinterpret_cast<float*>(smem_raw);                         // [d]
+  long long* cid = reinterpret_cast<long long*>(qh + d);                  // [r_max]
+  float* csc = reinterpret_cast<float*>(cid + r_max);                     // [r_max]
+  const int q = blockIdx.x;
+  const int n_sel = sel_n[q];
+  if (n_sel < 0) return;   // exact scan handles it
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float qn = q_norm[q];
+  for (int j = threadIdx.x; j < d; j += blockDim.x) qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
+  __syncthreads();
+  for (int c = warp; c < n_sel; c += 4) {
+    const int idx = sel_idx[static_cast<size_t>(q) * r_max + c];
+    const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
+    if (lane == 0) {
+      csc[c] = static_cast<float>(acc);
+      cid[c] = idx;
+    }
+  }
+  __syncthreads();
+  if (warp == 0)
+    warp_select_topk(csc, cid, n_sel, k, top_score + static_cast<size_t>(q) * k,
+                     top_idx + static_cast<size_t>(q) * k, idx_base, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// exact scan: grid (query groups of 8, library splits); 8 warps per CTA
+// ------------------------------------------------------------------------------------------
+constexpr int kQB = 8;
+
+__global__ void __launch_bounds__(256)
+exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm, int t,
+                     const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
+                     int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
+                     int region0_bytes, float* __restrict__ part_score, long long* __restrict__ part_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // region 0: normalised queries [kQB][d] during the scan, merge scratch afterwards
+  float* qh = reinterpret_cast<float*>(smem_raw);
+  long long* lid = reinterpret_cast<long long*>(smem_raw + region0_bytes);   // [8 warps][kQB][k]
+  float* lsc = reinterpret_cast<float*>(lid + 8 * kQB * k);                  // [8 warps][kQB][k]
+  __shared__ int qids[kQB];
+
+  const int nq = q_count ? *q_count : t;
+  const int g0 = blockIdx.x * kQB;
+  if (g0 >= nq) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kQB) {
+    const int slot = g0 + threadIdx.x;
+    qids[threadIdx.x] = slot < nq ? (q_list ? q_list[slot] : slot) : -1;
+  }
+  __syncthreads();
+  for (int qi = 0; qi < kQB; ++qi) {
+    const int q = qids[qi];
+    const float qn = q >= 0 ? q_norm[q] : 1.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x)
+      qh[qi * d + j] = q >= 0 ? __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn) : 0.f;
+  }
+  for (int e = threadIdx.x; e < 8 * kQB * k; e += blockDim.x) {
+    lid[e] = -1;
+    lsc[e] = 0.f;
+  }
+  __syncthreads();
+
+  const long long per = (n + splits - 1) / splits;
+  const long long r0 = per * blockIdx.y;
+  const long long r1 = min(n, r0 + per);
+  // lane qi (< kQB) of every warp owns that warp's list for query qi; worst = entry to replace
+  float* my_s = lsc + (warp * kQB + (lane & (kQB - 1))) * k;
+  long long* my_i = lid + (warp * kQB + (lane & (kQB - 1))) * k;
+  int filled = 0, worst = 0;
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    const float* row = lib_raw + static_cast<size_t>(r) * d;
+    const float nrm = lib_norm[r];
+    float mine = 0.f;
+#pragma unroll
+    for (int qi = 0; qi < kQB; ++qi) {
+      const double acc = dot_norm_f64(qh + qi * d, row, nrm, d, lane);
+      if (lane == qi) mine = static_cast<float>(acc);
+    }
+    if (lane < kQB && qids[lane] >= 0) {
+      if (filled < k) {
+        my_s[filled] = mine;
+        my_i[filled] = r;
+        ++filled;
+        if (filled == k) {
+          worst = 0;
+          for (int e = 1; e < k; ++e)
+            if (score_better(my_s[worst], my_i[worst], my_s[e], my_i[e])) worst = e;
+        }
+      } else if (score_better(mine, r, my_s[worst], my_i[worst])) {
+        my_s[worst] = mine;
+        my_i[worst] = r;
+        worst = 0;
+        for (int e = 1; e < k; ++e)
+          if (score_better(my_s[worst], my_i[worst], my_s[e], my_i[e])) worst = e;
+      }
+    }
+  }
+  __syncthreads();
+  // merge the 8 per-warp lists of each query (warp w finishes query w); region 0 is free now
+  float* scratch_s = qh;                                                  // [kQB][8*k] floats
+  long long* scratch_i = reinterpret_cast<long long*>(qh + kQB * 8 * k + ((kQB * 8 * k) & 1));
+  for (int e = threadIdx.x; e < kQB * 8 * k; e += blockDim.x) {
+    const int qi = e / (8 * k), rem = e % (8 * k), w = rem / k, j = rem % k;
+    scratch_s[e] = lsc[(w * kQB + qi) * k + j];
+    scratch_i[e] = lid[(w * kQB + qi) * k + j];
+  }
+  __syncthreads();
+  {
+    const int qi = warp;
+    if (qids[qi] >= 0) {
+      const size_t o = (static_cast<size_t>(g0 + qi) * splits + blockIdx.y) * k;
+      warp_select_topk(scratch_s + qi * 8 * k, scratch_i + qi * 8 * k, 8 * k, k, part_score + o, part_idx + o, 0, lane);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+exact_final_kernel(int t, int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
+                   const float* __restrict__ part_score, const long long* __restrict__ part_idx,
+                   long long idx_base, float* __restrict__ top_score, long long* __restrict__ top_idx) {
+  const int nq = q_count ? *q_count : t;
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= nq) return;
+  const int q = q_list ? q_list[slot] : slot;
+  const size_t o = static_cast<size_t>(slot) * splits * k;
+  warp_select_topk(part_score + o, part_idx + o, splits * k, k, top_score + static_cast<size_t>(q) * k,
+                   top_idx + static_cast<size_t>(q) * k, idx_base, threadIdx.x & 31);
+}
+
+__global__ void __launch_bounds__(128)
+merge_kernel(const float* __restrict__ scores, const long long* __restrict__ idx, int ranks, int t, int k,
+             float* __restrict__ top_score, long long* __restrict__ top_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + warp;
+  long long* ci = reinterpret_cast<long long*>(smem_raw) + warp * ranks * k;
+  float* cs = reinterpret_cast<float*>(reinterpret_cast<long long*>(smem_raw) + 4 * ranks * k) + warp * ranks * k;
+  if (q >= t) return;
+  for (int e = lane; e < ranks * k; e += 32) {
+    const int r = e / k, j = e % k;
+    cs[e] = scores[(static_cast<size_t>(r) * t + q) * k + j];
+    ci[e] = idx[(static_cast<size_t>(r) * t + q) * k + j];
+  }
+  __syncwarp();
+  warp_select_topk(cs, ci, ranks * k, k, top_score + static_cast<size_t>(q) * k, top_idx + static_cast<size_t>(q) * k, 0, lane);
+}
+
+int exact_splits(int t, long long n, int k) {
+  long long s = (n + 8191) / 8192;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  while (s > 1 && static_cast<long long>(t) * s * k * 12 > (256ll << 20)) s /= 2;
+  return static_cast<int>(s);
+}
+
+}  // namespace
+}  // namespace alive
+
+extern "C" int alive_knn_prune(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists,
+                               int32_t k, const float* q_err, const float* q_norm, const uint32_t* lib_stats,
+                               int32_t r_max, int32_t* sel_idx, int32_t* sel_n, int32_t* fb_list,
+                               int32_t* fb_count, alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(cand_score && cand_idx && q_err && q_norm && lib_stats && sel_idx && sel_n && fb_list && fb_count,
+                "alive_knn_prune: NULL argument");
+  ALIVE_REQUIRE(t >= 1 && lists >= 1, "alive_knn_prune: bad sizes");
+  ALIVE_REQUIRE(k >= 1 && k <= kListLen, "alive_knn_prune: k must be in [1,%d] for the screened path (got %d)", kListLen, k);
+  ALIVE_REQUIRE(r_max >= k && r_max <= kMaxRMax, "alive_knn_prune: r_max must be in [k,%d]", kMaxRMax);
+  ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), as_stream(stream)));
+  const int wpb = 8;
+  prune_kernel<<<(t + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(
+      cand_score, cand_idx, t, lists, k, q_err, q_norm, lib_stats, r_max, sel_idx, sel_n, fb_list, fb_count);
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int alive_knn_rescore(const float* q_raw, const float* q_norm, int32_t t, const float* lib_raw,
+                                 const float* lib_norm, int32_t d, const int32_t* sel_idx, const int32_t* sel_n,
+                                 int32_t r_max, int32_t k, int64_t idx_base, float* top_score, int64_t* top_idx,
+                                 alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(q_raw && q_norm && lib_raw && lib_norm && sel_idx && sel_n && top_score && top_idx,
+                "alive_knn_rescore: NULL argument");
+  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 8192, "alive_knn_rescore: d must be a multiple of 4");
+  ALIVE_REQUIRE(k >= 1 && k <= r_max && r_max <= kMaxRMax, "alive_knn_rescore: need 1 <= k <= r_max <= %d", kMaxRMax);
+  ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw)) & 15) == 0,
+                "alive_knn_rescore: raw buffers must be 16-byte aligned");
+  if (t <= 0) return 0;
+  const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 12 + 16;
+  rescore_kernel<<<t, 128, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, d, sel_idx, sel_n, r_max, k,
+                                                      idx_base, top_score, reinterpret_cast<long long*>(top_idx));
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k) {
+  using namespace alive;
+  if (t < 1 || k < 1) return 0;
+  const int s = exact_splits(t, n, k);
+  const size_t groups = (static_cast<size_t>(t) + kQB - 1) / kQB;
+  return groups * kQB * s * k * 12 + 256;
+}
+
+extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t, const float* lib_raw,
+                               const float* lib_norm, int64_t n, int32_t d, int32_t k, const int32_t* q_list,
+                               const int32_t* q_count, int64_t idx_base, void* workspace, float* top_score,
+                               int64_t* top_idx, alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(q_raw && q_norm && lib_raw && lib_norm && workspace && top_score && top_idx,
+                "alive_knn_exact: NULL argument");
+  ALIVE_REQUIRE((q_list == nullptr) == (q_count == nullptr), "alive_knn_exact: q_list and q_count go together");
+  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 1536, "alive_knn_exact: d must be a multiple of 4, <= 1536");
+  ALIVE_REQUIRE(k >= 1 && k <= kMaxK, "alive_knn_exact: k must be in [1,%d]", kMaxK);
+  ALIVE_REQUIRE(n >= k, "selected index k out of range");
+  ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw)) & 15) == 0,
+                "alive_knn_exact: raw buffers must be 16-byte aligned");
+  if (t <= 0) return 0;
+  const int splits = exact_splits(t, n, k);
+  const size_t groups = (static_cast<size_t>(t) + kQB - 1) / kQB;
+  // workspace layout: part_idx [groups*kQB*splits*k] int64, then part_score float
+  long long* part_idx = reinterpret_cast<long long*>(workspace);
+  float* part_score = reinterpret_cast<float*>(part_idx + groups * kQB * splits * k);
+  const size_t smem_q = static_cast<size_t>(kQB) * d * 4;
+  const size_t smem_scratch = static_cast<size_t>(kQB) * 8 * k * 12 + 8;
+  const size_t region0 = ((smem_q > smem_scratch ? smem_q : smem_scratch) + 15) & ~static_cast<size_t>(15);
+  const size_t smem = region0 + static_cast<size_t>(8) * kQB * k * 12;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_done = true;
+  }
+  ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
+  dim3 grid(static_cast<unsigned>(groups), static_cast<unsigned>(splits));
+  exact_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, n, d, k, q_list,
+                                                              q_count, splits, static_cast<int>(region0), part_score, part_idx);
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  exact_final_kernel<<<(t + 3) / 4, 128, 0, as_stream(stream)>>>(t, k, q_list, q_count, splits, part_score, part_idx,
+                                                                 idx_base, top_score, reinterpret_cast<long long*>(top_idx));
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int alive_knn_merge(const float* scores, const int64_t* idx, int32_t ranks, int32_t t, int32_t k,
+                               float* top_score, int64_t* top_idx, alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(scores && idx && top_score && top_idx, "alive_knn_merge: NULL argument");
+  ALIVE_REQUIRE(ranks >= 1 && ranks <= 64 && k >= 1 && k <= kMaxK, "alive_knn_merge: bad sizes");
+  if (t <= 0) return 0;
+  const size_t smem = static_cast<size_t>(4) * ranks * k * 12;
+  ALIVE_REQUIRE(smem <= 48 * 1024, "alive_knn_merge: ranks*k too large");
+  merge_kernel<<<(t + 3) / 4, 128, smem, as_stream(stream)>>>(scores, reinterpret_cast<const long long*>(idx), ranks, t, k,
+                                                              top_score, reinterpret_cast<long long*>(top_idx));
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

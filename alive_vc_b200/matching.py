@@ -1,0 +1,389 @@
+"""Host side of the kNN voice-library matching path.
+
+Mirrors the reference's functional interface
+    module/common.py:96-109   match_features(source, reference, k=4, alpha=0.0)
+with the same argument meaning, return layout and error behaviour, and runs it
+as hand-written sm_100a kernels behind the C ABI in include/alive_knn.h:
+
+    pack (K1)  ->  fused tcgen05 similarity + running top lists (K2)
+               ->  certificate + prune (K2b)  ->  exact fp32/fp64 rescoring (K3)
+               ->  exact scan for uncertified queries  ->  gather + mean + blend (K4)
+
+PyTorch is used for device memory, streams and autograd plumbing only.  There
+is no CPU path: tensors must live on a CUDA device and the in-tree
+libalive_knn.so must be built, otherwise a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _cabi
+
+LIST_LEN = 8            # ALIVE_KNN_LIST_LEN
+MAX_K = 64              # ALIVE_KNN_MAX_K
+DEFAULT_R_MAX = 64      # survivors rescored per query before falling back to the exact scan
+EXACT_BELOW_N = 1024    # libraries this small skip the tensor-core screen
+
+_sm_count: dict = {}
+
+
+def _num_sms(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _sm_count:
+        _sm_count[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _sm_count[idx]
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"alive_vc_b200: `{name}` is on {t.device}; this implementation has no CPU path "
+            "(sm_100a CUDA kernels only) - move the tensors to a B200 device")
+
+
+@dataclass
+class PackedFrames:
+    """Frames in the layout the kernels consume (see DESIGN.md "Data layout in HBM")."""
+    n: int
+    d: int
+    raw: torch.Tensor        # [n,d] float32, raw frames, row-major
+    norms: torch.Tensor      # [n]   float32
+    packed: torch.Tensor     # [n,d] bfloat16, frames / norm
+    err: torch.Tensor        # [n]   float32, ||bf16(x/|x|) - x/|x|||_2
+    stats: torch.Tensor      # [2]   int32 (uint32 bit patterns): max err, non-finite row count
+    row_base: int = 0        # global index of frame 0 (sharded libraries)
+    _keepalive: list = field(default_factory=list, repr=False)
+
+    @property
+    def device(self):
+        return self.raw.device
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.raw, self.norms, self.packed, self.err, self.stats))
+
+
+def alloc_packed(n: int, d: int, device) -> PackedFrames:
+    return PackedFrames(
+        n=n, d=d,
+        raw=torch.empty((n, d), dtype=torch.float32, device=device),
+        norms=torch.empty((n,), dtype=torch.float32, device=device),
+        packed=torch.empty((n, d), dtype=torch.bfloat16, device=device),
+        err=torch.empty((n,), dtype=torch.float32, device=device),
+        stats=torch.zeros((2,), dtype=torch.int32, device=device),
+    )
+
+
+def pack_into(dst: PackedFrames, row0: int, frames_dn: torch.Tensor):
+    """K1 on a [D, n] float32 view (any strides) -> rows [row0, row0+n) of `dst`."""
+    lib = _cabi.load()
+    d, n = frames_dn.shape
+    if n == 0:
+        return
+    assert frames_dn.dtype == torch.float32 and frames_dn.is_cuda
+    assert d == dst.d and row0 + n <= dst.n
+    rc = lib.alive_knn_pack(
+        frames_dn.data_ptr(), n, d, frames_dn.stride(1), frames_dn.stride(0),
+        dst.raw[row0:].data_ptr(), dst.norms[row0:].data_ptr(), dst.packed[row0:].data_ptr(),
+        dst.err[row0:].data_ptr(), dst.stats.data_ptr(), _stream_ptr())
+    _cabi.check(rc, "alive_knn_pack")
+
+
+def pack_frames(frames_dn: torch.Tensor) -> PackedFrames:
+    """Normalise-and-pack a [D, N] float32 CUDA view (the reference's channel-major
+    layout, any strides).  Done ONCE per library (generate_voice_library.py / load time)
+    instead of once per call as common.py:101-104 does."""
+    _require_cuda(frames_dn, "frames")
+    if frames_dn.dtype != torch.float32:
+        frames_dn = frames_dn.float()
+    d, n = frames_dn.shape
+    out = alloc_packed(n, d, frames_dn.device)
+    pack_into(out, 0, frames_dn)
+    return out
+
+
+def pack_library(reference: torch.Tensor) -> PackedFrames:
+    """[1, D, N] (or [D, N]) library tensor -> PackedFrames."""
+    if reference.dim() == 3:
+        if reference.shape[0] != 1:
+            raise RuntimeError("pack_library expects a single library [1, D, N]")
+        reference = reference[0]
+    return pack_frames(reference)
+
+
+# ---------------------------------------------------------------------------------------
+# pack cache: invisible to callers, keyed on the tensor OBJECT and validated against its
+# storage pointer / version counter / geometry (SURVEY §8(b) "Ownership")
+# ---------------------------------------------------------------------------------------
+_pack_cache: dict = {}
+_PACK_CACHE_MAX = 16
+
+
+def _cache_key(t: torch.Tensor):
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), str(t.device), t.dtype)
+
+
+def cached_pack(owner: torch.Tensor, frames_dn: torch.Tensor, tag=0) -> PackedFrames:
+    """Pack `frames_dn` (a view of `owner`) unless `owner` was packed before and has not
+    changed since (same object, same storage pointer, same version counter)."""
+    oid = (id(owner), tag)
+    ent = _pack_cache.get(oid)
+    key = _cache_key(owner)
+    if ent is not None:
+        ref, old_key, packed = ent
+        if ref() is owner and old_key == key:
+            return packed
+        del _pack_cache[oid]
+    packed = pack_frames(frames_dn)
+    if len(_pack_cache) >= _PACK_CACHE_MAX:
+        for dead in [k for k, (r, _, _) in _pack_cache.items() if r() is None]:
+            del _pack_cache[dead]
+        while len(_pack_cache) >= _PACK_CACHE_MAX:
+            del _pack_cache[next(iter(_pack_cache))]
+
+    def _drop(_ref, oid=oid):
+        _pack_cache.pop(oid, None)
+
+    try:
+        _pack_cache[oid] = (weakref.ref(owner, _drop), key, packed)
+    except TypeError:
+        pass
+    return packed
+
+
+def clear_pack_cache():
+    _pack_cache.clear()
+
+
+# ---------------------------------------------------------------------------------------
+# top-k search
+# ---------------------------------------------------------------------------------------
+@dataclass
+class SearchInfo:
+    """Per-call bookkeeping (device tensors; reading them synchronises)."""
+    mode: str
+    plan: Optional[dict] = None
+    fb_count: Optional[torch.Tensor] = None     # [1] int32: queries sent to the exact scan
+    sel_n: Optional[torch.Tensor] = None        # [T] int32: survivors rescored per query (-1 = exact scan)
+    launches: int = 0
+
+    def fallback_queries(self) -> int:
+        return int(self.fb_count.item()) if self.fb_count is not None else 0
+
+
+last_info: Optional[SearchInfo] = None
+
+
+def make_plan(t: int, n: int, d: int, device, variant: int = 0) -> _cabi.Plan:
+    plan = _cabi.Plan()
+    rc = _cabi.load().alive_knn_plan(t, n, d, _num_sms(device), variant, ctypes.byref(plan))
+    _cabi.check(rc, "alive_knn_plan")
+    return plan
+
+
+def exact_topk(q: PackedFrames, lib: PackedFrames, k: int, top_score=None, top_idx=None,
+               q_list=None, q_count=None):
+    """common.py:102-105 by exhaustive exact scan (fp64-accumulated similarities)."""
+    c = _cabi.load()
+    dev = q.device
+    t = q.n
+    if top_score is None:
+        top_score = torch.empty((t, k), dtype=torch.float32, device=dev)
+        top_idx = torch.empty((t, k), dtype=torch.int64, device=dev)
+    ws_bytes = c.alive_knn_exact_workspace_bytes(t, lib.n, k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    rc = c.alive_knn_exact(q.raw.data_ptr(), q.norms.data_ptr(), t, lib.raw.data_ptr(), lib.norms.data_ptr(),
+                           lib.n, lib.d, k,
+                           q_list.data_ptr() if q_list is not None else None,
+                           q_count.data_ptr() if q_count is not None else None,
+                           lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), _stream_ptr())
+    _cabi.check(rc, "alive_knn_exact")
+    return top_score, top_idx
+
+
+def search_topk(q: PackedFrames, lib: PackedFrames, k: int, mode: str = "auto",
+                r_max: int = DEFAULT_R_MAX, variant: int = 0):
+    """Exact top-k (score desc, frame asc) of every query frame against the library.
+    Returns (top_score [T,k] float32, top_idx [T,k] int64 incl. lib.row_base)."""
+    global last_info
+    c = _cabi.load()
+    if q.d != lib.d:
+        raise RuntimeError(f"feature dims differ: queries {q.d}, library {lib.d}")
+    if k < 1 or k > lib.n:
+        raise RuntimeError("selected index k out of range")   # torch.topk's message (common.py:105)
+    if k > MAX_K:
+        raise RuntimeError(f"alive_vc_b200 supports k <= {MAX_K} (got {k})")
+    t, n, d = q.n, lib.n, lib.d
+    dev = q.device
+    if mode == "auto":
+        mode = "exact" if (k > LIST_LEN or n < EXACT_BELOW_N or d % 64 != 0) else "screen"
+    if mode == "exact":
+        top_score, top_idx = exact_topk(q, lib, k)
+        last_info = SearchInfo(mode="exact", launches=2)
+        return top_score, top_idx
+    if mode != "screen":
+        raise ValueError(f"unknown mode {mode!r}")
+    if k > LIST_LEN:
+        raise RuntimeError(f"the screened path needs k <= {LIST_LEN}")
+
+    plan = make_plan(t, n, d, dev, variant)
+    stream = _stream_ptr()
+    cand_score = torch.empty((t, plan.lists, LIST_LEN), dtype=torch.float32, device=dev)
+    cand_idx = torch.empty((t, plan.lists, LIST_LEN), dtype=torch.int32, device=dev)
+    rc = c.alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
+                            cand_score.data_ptr(), cand_idx.data_ptr(), stream)
+    _cabi.check(rc, "alive_knn_search")
+
+    sel_idx = torch.empty((t, r_max), dtype=torch.int32, device=dev)
+    sel_n = torch.empty((t,), dtype=torch.int32, device=dev)
+    fb_list = torch.empty((t,), dtype=torch.int32, device=dev)
+    fb_count = torch.empty((1,), dtype=torch.int32, device=dev)
+    rc = c.alive_knn_prune(cand_score.data_ptr(), cand_idx.data_ptr(), t, plan.lists, k, q.err.data_ptr(),
+                           q.norms.data_ptr(), lib.stats.data_ptr(), r_max, sel_idx.data_ptr(), sel_n.data_ptr(),
+                           fb_list.data_ptr(), fb_count.data_ptr(), stream)
+    _cabi.check(rc, "alive_knn_prune")
+
+    top_score = torch.empty((t, k), dtype=torch.float32, device=dev)
+    top_idx = torch.empty((t, k), dtype=torch.int64, device=dev)
+    rc = c.alive_knn_rescore(q.raw.data_ptr(), q.norms.data_ptr(), t, lib.raw.data_ptr(), lib.norms.data_ptr(), d,
+                             sel_idx.data_ptr(), sel_n.data_ptr(), r_max, k, lib.row_base,
+                             top_score.data_ptr(), top_idx.data_ptr(), stream)
+    _cabi.check(rc, "alive_knn_rescore")
+    # queries the certificate could not clear: exhaustive scan (device-side list, no host sync)
+    exact_topk(q, lib, k, top_score, top_idx, fb_list, fb_count)
+    last_info = SearchInfo(mode="screen", plan=plan.as_dict(), fb_count=fb_count, sel_n=sel_n, launches=7)
+    return top_score, top_idx
+
+
+def gather_mean(lib: PackedFrames, top_idx: torch.Tensor, q: PackedFrames, alpha: float, out: torch.Tensor):
+    """K4: common.py:107-109 into `out` [T,D] float32."""
+    t, k = top_idx.shape
+    rc = _cabi.load().alive_knn_gather_mean(lib.raw.data_ptr(), lib.n, lib.d, top_idx.data_ptr(), t, k,
+                                            q.raw.data_ptr(), float(alpha), out.data_ptr(), _stream_ptr())
+    _cabi.check(rc, "alive_knn_gather_mean")
+    return out
+
+
+def pack_queries(source: torch.Tensor) -> PackedFrames:
+    """[B, D, T] float32 CUDA -> PackedFrames with B*T rows (row b*T + t)."""
+    B, D, T = source.shape
+    out = alloc_packed(B * T, D, source.device)
+    for b in range(B):
+        pack_into(out, b * T, source[b])
+    return out
+
+
+def match_packed(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0,
+                 mode: str = "auto", variant: int = 0, r_max: int = DEFAULT_R_MAX):
+    """All B*T query frames of `source` [B,D,T] against ONE packed library.
+    Returns (out [B,T,D] float32 contiguous, top_idx [B,T,k] int64, top_score [B,T,k])."""
+    B, D, T = source.shape
+    q = pack_queries(source)
+    top_score, top_idx = search_topk(q, lib, k, mode=mode, variant=variant, r_max=r_max)
+    out = torch.empty((B, T, D), dtype=torch.float32, device=source.device)
+    gather_mean(lib, top_idx, q, alpha, out)
+    return out, top_idx.view(B, T, k), top_score.view(B, T, k)
+
+
+def _check_inputs(source: torch.Tensor, reference: torch.Tensor, k: int):
+    # shape / k errors first, with the reference's own messages, then the device check
+    if source.dim() != 3 or reference.dim() != 3:
+        raise RuntimeError("match_features expects source [B, D, T] and reference [B, D, N]")
+    B, D, T = source.shape
+    if reference.shape[0] != B or reference.shape[1] != D:
+        # message of torch.bmm in the reference (common.py:104)
+        raise RuntimeError(
+            f"Expected size for first two dimensions of batch2 tensor to be: [{B}, {D}] "
+            f"but got: [{reference.shape[0]}, {reference.shape[1]}].")
+    N = reference.shape[2]
+    if not isinstance(k, int) or k < 1 or k > N:
+        raise RuntimeError("selected index k out of range")   # torch.topk (common.py:105)
+    _require_cuda(source, "source")
+    _require_cuda(reference, "reference")
+    if source.device != reference.device:
+        raise RuntimeError(f"source is on {source.device} but reference is on {reference.device}")
+
+
+def match_indices(source: torch.Tensor, reference: torch.Tensor, k: int = 4, mode: str = "auto",
+                  variant: int = 0):
+    """The neighbour indices the reference computes at common.py:105 but never returns:
+    ([B,T,k] int64, [B,T,k] float32 similarities)."""
+    out = _match_impl(source, reference, k, 0.0, mode, variant, want_out=False)
+    return out[1], out[2]
+
+
+def _match_impl(source, reference, k, alpha, mode, variant, want_out=True):
+    _check_inputs(source, reference, k)
+    B, D, T = source.shape
+    src32 = source if source.dtype == torch.float32 else source.float()
+    ref32 = reference if reference.dtype == torch.float32 else reference.float()
+    dev = source.device
+    if T == 0:
+        return (torch.empty((B, 0, D), dtype=torch.float32, device=dev),
+                torch.empty((B, 0, k), dtype=torch.int64, device=dev),
+                torch.empty((B, 0, k), dtype=torch.float32, device=dev))
+    shared = B == 1 or ref32.stride(0) == 0
+    if shared:
+        # one library for every batch item (VoiceLibrary.match: tokens.expand, voice_library.py:16-19)
+        owner = reference if (reference.dtype == torch.float32) else ref32
+        lib = cached_pack(owner, ref32[0])
+        return match_packed(src32, lib, k, alpha, mode, variant)
+    outs, idxs, scs = [], [], []
+    for b in range(B):
+        owner = reference if (reference.dtype == torch.float32) else ref32
+        lib = cached_pack(owner, ref32[b], tag=b + 1)
+        o, i, s = match_packed(src32[b:b + 1], lib, k, alpha, mode, variant)
+        outs.append(o)
+        idxs.append(i)
+        scs.append(s)
+    return torch.cat(outs, 0), torch.cat(idxs, 0), torch.cat(scs, 0)
+
+
+class _BlendGrad(torch.autograd.Function):
+    """d(out)/d(source) of common.py:109: the matched term carries no gradient to `source`
+    (indices are not differentiable), the blend contributes alpha * g."""
+
+    @staticmethod
+    def forward(ctx, source, out_bdt, alpha):
+        ctx.alpha = alpha
+        return out_bdt.view_as(out_bdt)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.alpha, None, None
+
+
+def match_features(source: torch.Tensor, reference: torch.Tensor, k: int = 4, alpha: float = 0.0,
+                   *, return_indices: bool = False, mode: str = "auto", variant: int = 0):
+    """Drop-in for `module.common.match_features` (module/common.py:96-109).
+
+    source [B, D, T], reference [B, D, N] (same B; D = 768 in ALiVE-VC) -> [B, D, T],
+    returned exactly like the reference does: a transposed view of a contiguous
+    [B, T, D] block (strides (T*D, 1, D)).  Each source frame is replaced by the mean of
+    the RAW library frames of its k most cosine-similar neighbours, blended as
+    `result*(1-alpha) + source*alpha`.  `reference` never receives a gradient and
+    `source` receives `alpha * grad`, as in the reference (`torch.no_grad` at :98).
+
+    Raises RuntimeError("selected index k out of range") when k > N or the library is
+    empty, and the bmm size error on a batch mismatch, like the reference.
+    `return_indices=True` additionally returns the [B,T,k] int64 indices (extension used
+    for parity checks; the reference computes but never returns them).
+    """
+    with torch.no_grad():
+        out_btd, idx, _ = _match_impl(source, reference, k, float(alpha), mode, variant)
+    out = out_btd.transpose(1, 2)
+    if out.dtype != source.dtype:
+        out = out.to(source.dtype)
+    if torch.is_grad_enabled() and source.requires_grad:
+        out = _BlendGrad.apply(source, out, float(alpha))
+    if return_indices:
+        return out, idx
+    return out

@@ -1,0 +1,157 @@
+"""Row-sharded voice library across the GPUs of one box (BASELINE cfg4).
+
+The reference has no distributed code at all; this is the one exchange step the path
+needs when the library does not fit / should not live on one GPU:
+
+    rank r holds frames [lo_r, hi_r) packed (bf16 + raw fp32); every rank sees all queries
+    1. local exact top-k            (K2 + K2b + K3 on the shard, GLOBAL frame indices)
+    2. all-gather of (score, index) [T, k] per rank   - T*k*12 B per rank over NVLink
+    3. merge -> global top-k        (score desc, frame asc)  on every rank
+    4. each rank gathers the winning rows IT owns into a zero-initialised [T, k, D] block
+    5. all-reduce(sum) of that block - adding zeros is exact, so every rank now holds the
+       k winning raw frames of every query in descending-score order
+    6. mean + blend exactly as the single-GPU K4 -> bit-identical result on every rank
+
+One process per GPU (`torch.distributed`, backend nccl); the collectives are issued
+through torch.distributed on the current stream's NCCL communicator.  The compute steps
+go through a small backend object so the choreography can be exercised on CPU with
+`gloo` in tests (tests inject an oracle-based backend; the product backend below is
+CUDA-only and has no fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from . import matching as M
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """Frames [lo, hi) owned by `rank`: contiguous, sizes differ by at most one."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+class CudaShardBackend:
+    """The product backend: hand-written kernels through the C ABI."""
+
+    def __init__(self, local: M.PackedFrames, mode: str = "auto", variant: int = 0):
+        self.local = local
+        self.mode = mode
+        self.variant = variant
+
+    @property
+    def device(self):
+        return self.local.device
+
+    def pack_queries(self, source):
+        return M.pack_queries(source if source.dtype == torch.float32 else source.float())
+
+    def local_topk(self, q, k):
+        """([T,k] float32, [T,k] int64 global indices); k <= frames on this shard."""
+        return M.search_topk(q, self.local, k, mode=self.mode, variant=self.variant)
+
+    def merge(self, scores, idx, k):
+        r, t, kk = scores.shape
+        top_s = torch.empty((t, k), dtype=torch.float32, device=scores.device)
+        top_i = torch.empty((t, k), dtype=torch.int64, device=scores.device)
+        if kk != k:
+            raise RuntimeError("merge expects k entries per rank")
+        rc = _cabi.load().alive_knn_merge(scores.data_ptr(), idx.data_ptr(), r, t, k, top_s.data_ptr(),
+                                          top_i.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "alive_knn_merge")
+        return top_s, top_i
+
+    def gather_rows(self, top_idx):
+        t, k = top_idx.shape
+        rows = torch.empty((t, k, self.local.d), dtype=torch.float32, device=top_idx.device)
+        rc = _cabi.load().alive_knn_gather_rows(self.local.raw.data_ptr(), self.local.n, self.local.d,
+                                                self.local.row_base, top_idx.data_ptr(), t, k, rows.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "alive_knn_gather_rows")
+        return rows
+
+    def mean_blend(self, rows, q, alpha):
+        t, k, d = rows.shape
+        out = torch.empty((t, d), dtype=torch.float32, device=rows.device)
+        rc = _cabi.load().alive_knn_mean_blend(rows.data_ptr(), t, k, d, q.raw.data_ptr(), float(alpha),
+                                               out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "alive_knn_mean_blend")
+        return out
+
+
+class ShardedLibrary:
+    """A voice library whose frames are split by rows over the ranks of `group`."""
+
+    def __init__(self, backend, n_local: int, row_base: int, n_total: int, group=None):
+        self.backend = backend
+        self.n_local = n_local
+        self.row_base = row_base
+        self.n_total = n_total
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    @classmethod
+    def from_local_frames(cls, frames_dn: torch.Tensor, row_base: int, n_total: int, group=None,
+                          mode: str = "auto", variant: int = 0):
+        """`frames_dn` [D, n_local]: this rank's frames, global rows [row_base, row_base+n_local)."""
+        local = M.pack_frames(frames_dn)
+        local.row_base = row_base
+        return cls(CudaShardBackend(local, mode, variant), local.n, row_base, n_total, group)
+
+    @classmethod
+    def from_full(cls, reference: torch.Tensor, group=None, mode: str = "auto", variant: int = 0):
+        """Every rank passes the same [1, D, N] library; each keeps only its row range."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ref = reference[0] if reference.dim() == 3 else reference
+        lo, hi = shard_bounds(ref.shape[1], world, rank)
+        return cls.from_local_frames(ref[:, lo:hi], lo, ref.shape[1], group, mode, variant)
+
+    def match(self, source: torch.Tensor, k: int = 4, alpha: float = 0.0, return_indices: bool = False):
+        """Same contract as match_features(source, whole_library): source [B, D, T] replicated
+        on every rank -> [B, D, T] on every rank (transposed view of a contiguous [B,T,D])."""
+        if source.dim() != 3:
+            raise RuntimeError("ShardedLibrary.match expects source [B, D, T]")
+        if not isinstance(k, int) or k < 1 or k > self.n_total:
+            raise RuntimeError("selected index k out of range")
+        B, D, T = source.shape
+        be = self.backend
+        q = be.pack_queries(source)
+        t = B * T
+        dev = source.device
+        # 1. local exact top-k (pad with -inf / -1 when the shard holds fewer than k frames)
+        k_loc = min(k, self.n_local)
+        loc_s = torch.full((t, k), float("-inf"), dtype=torch.float32, device=dev)
+        loc_i = torch.full((t, k), -1, dtype=torch.int64, device=dev)
+        if k_loc > 0:
+            s, i = be.local_topk(q, k_loc)
+            loc_s[:, :k_loc] = s
+            loc_i[:, :k_loc] = i
+        if self.world == 1:
+            top_s, top_i = loc_s, loc_i
+        else:
+            # 2. all-gather candidates
+            all_s = torch.empty((self.world, t, k), dtype=torch.float32, device=dev)
+            all_i = torch.empty((self.world, t, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_s, loc_s, group=self.group)
+            dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
+            # 3. merge
+            top_s, top_i = be.merge(all_s, all_i, k)
+        # 4. owned rows, zeros elsewhere;  5. exact sum over ranks
+        rows = be.gather_rows(top_i)
+        if self.world > 1:
+            dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=self.group)
+        # 6. mean + blend
+        out = be.mean_blend(rows, q, alpha).view(B, T, D).transpose(1, 2)
+        if out.dtype != source.dtype:
+            out = out.to(source.dtype)
+        if return_indices:
+            return out, top_i.view(B, T, k)
+        return out

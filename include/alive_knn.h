@@ -1,0 +1,163 @@
+/*
+ * alive_knn.h - C ABI of the B200-native kNN voice-library matching path.
+ *
+ * This is the drop-in boundary for ONE hot path of uthree/ALiVE-VC:
+ *   module/common.py:96-109         match_features(source, reference, k, alpha)
+ *   module/voice_library.py:15-33   VoiceLibrary.match(source, k, alpha)
+ * The reference has no FFI/plugin layer (it is pure Python calling torch ops),
+ * so each entry point below cites the reference LINES whose torch ops it
+ * replaces.  The Python host side (alive_vc_b200/) binds these with ctypes and
+ * keeps the reference's Python signatures; INTEGRATION.md shows the stub a
+ * maintainer adds to module/common.py / module/voice_library.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises
+ *     the host unless stated;
+ *   - return value: 0 on success, negative on error; the message is available
+ *     from alive_knn_last_error() (thread-local);
+ *   - "rows" are frames: a library of N frames is N rows of D floats.
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ *
+ * Built for sm_100a only (tcgen05 / TMEM / TMA).
+ */
+#ifndef ALIVE_KNN_H_
+#define ALIVE_KNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* alive_stream_t; /* cudaStream_t */
+
+#define ALIVE_KNN_ABI_VERSION 1
+#define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
+#define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
+#define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
+#define ALIVE_KNN_MAX_K 64        /* largest k supported by the exact selectors */
+
+/* Work decomposition of one alive_knn_search launch (filled by alive_knn_plan). */
+typedef struct alive_knn_plan {
+  int32_t t;                 /* query frames */
+  int64_t n;                 /* library frames */
+  int32_t d;                 /* feature dim (multiple of 64) */
+  int32_t ctas_per_unit;     /* 1: cta_group::1 (128-query units), 2: CTA pair (256-query units) */
+  int32_t m_units;           /* ceil(t / (128*ctas_per_unit)) */
+  int32_t n_tiles;           /* ceil(n / 256) */
+  int32_t segments;          /* library is cut into this many runs of whole tiles */
+  int32_t tiles_per_segment;
+  int32_t lists;             /* running lists per query = 2 * segments */
+  int32_t grid;              /* CTAs launched (multiple of ctas_per_unit) */
+} alive_knn_plan_t;
+
+/* Library statistics produced by alive_knn_pack (2 x uint32 on the device):
+ *   [0] bit pattern of max over rows of || bf16(x/|x|) - x/|x| ||_2   (float >= 0)
+ *   [1] number of rows whose normalised form is not finite (zero or inf/nan rows) */
+#define ALIVE_KNN_STATS_WORDS 2
+
+const char* alive_knn_last_error(void);
+int alive_knn_abi_version(void);
+
+/* K1 - normalise and pack.  Replaces, ONCE per library instead of once per
+ * call, common.py:101,103 and the `reference / reference_norm` of :104
+ * (voice_library.py:25,27,28): reads frames x[i*stride_n + j*stride_d]
+ * (i < n, j < d; the reference's [1,D,N] layout is stride_n=1, stride_d=N),
+ * writes
+ *   raw    [n,d] float32 row-major copy of the UN-normalised frames (gather + rescoring)
+ *   norms  [n]   float32 L2 norms (fp64 accumulation, rounded once)
+ *   packed [n,d] bf16 row-major, frames divided by their norm (tensor-core operand, TMA friendly)
+ *   err    [n]   float32 || bf16(x/|x|) - x/|x| ||_2 per row (may be NULL)
+ *   stats  [2]   see above; must be zeroed by the caller before the FIRST pack
+ *                of a library (several packs may accumulate into one stats).
+ * Also used per call for the query frames (common.py:100,102,104 lhs). */
+int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
+                   float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
+                   alive_stream_t stream);
+
+/* Fill `plan` for t queries against n library frames on a device with
+ * `num_sms` SMs.  variant: 1 or 2 CTAs per unit (0 = library default). Host only. */
+int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
+                   alive_knn_plan_t* plan_host);
+
+/* K2 - fused similarity + running top list.  Replaces the bmm of
+ * common.py:104 and the first pass of torch.topk :105 WITHOUT materialising
+ * the [T,N] score matrix: TMA-fed tcgen05 bf16 MMAs accumulate 128x256 score
+ * tiles in TMEM; epilogue warps keep, per query and per list, the
+ * ALIVE_KNN_LIST_LEN best (score, frame) pairs.
+ *   q_packed [t,d] bf16, lib_packed [n,d] bf16 (from alive_knn_pack)
+ *   cand_score [t, plan.lists, 8] float32 (descending, -inf padded)
+ *   cand_idx   [t, plan.lists, 8] int32   (-1 padded) */
+int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,
+                     const alive_knn_plan_t* plan_host,
+                     float* cand_score, int32_t* cand_idx, alive_stream_t stream);
+
+/* K2b - certificate + prune.  From the screened lists pick, per query, every
+ * frame that can still belong to the exact top-k given the bf16 screening
+ * error bound eps = lib_err + q_err[t] + lib_err*q_err[t] + slack; a query whose
+ * lists cannot prove completeness (or that needs more than r_max survivors,
+ * or whose own norm is not finite, or when the library holds non-finite rows)
+ * is appended to fb_list for the exact scan.
+ *   sel_idx [t,r_max] int32, sel_n [t] int32, fb_list [t] int32, fb_count [1] int32 (zeroed here) */
+int alive_knn_prune(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists,
+                    int32_t k, const float* q_err, const float* q_norm, const uint32_t* lib_stats,
+                    int32_t r_max, int32_t* sel_idx, int32_t* sel_n, int32_t* fb_list,
+                    int32_t* fb_count, alive_stream_t stream);
+
+/* K3 - exact rescoring of the survivors.  Mirrors common.py:102-105 on the
+ * candidate set: each frame is normalised first (x / |x|, float32), then the
+ * dot product is accumulated (in fp64, rounded once to float32); top-k by
+ * (score desc, frame asc).  Queries with sel_n < 0 are skipped (fallback).
+ *   top_score [t,k] float32, top_idx [t,k] int64 (= frame + idx_base) */
+int alive_knn_rescore(const float* q_raw, const float* q_norm, int32_t t,
+                      const float* lib_raw, const float* lib_norm, int32_t d,
+                      const int32_t* sel_idx, const int32_t* sel_n, int32_t r_max, int32_t k,
+                      int64_t idx_base, float* top_score, int64_t* top_idx, alive_stream_t stream);
+
+/* Exact scan (no screen): common.py:102-105 for the queries listed in
+ * q_list[0..*q_count) (both device; NULL/NULL = all t queries) against all n
+ * frames, same arithmetic and tie rule as alive_knn_rescore; NaN similarities
+ * rank first like torch.topk.  workspace: alive_knn_exact_workspace_bytes(). */
+size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k);
+int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t,
+                    const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, int32_t k,
+                    const int32_t* q_list, const int32_t* q_count, int64_t idx_base,
+                    void* workspace, float* top_score, int64_t* top_idx, alive_stream_t stream);
+
+/* Multi-GPU merge: after an all-gather of every rank's exact local top-k,
+ * scores/idx are [ranks,t,k]; writes the global top-k (score desc, frame asc). */
+int alive_knn_merge(const float* scores, const int64_t* idx, int32_t ranks, int32_t t, int32_t k,
+                    float* top_score, int64_t* top_idx, alive_stream_t stream);
+
+/* K4 - gather + mean + blend.  Replaces common.py:107-109
+ * (voice_library.py:31-33): out[t,:] = mean_j raw[top_idx[t,j],:] summed
+ * sequentially in descending-score order then divided by k, blended as
+ * out*(1-alpha) + q_raw*alpha with separately rounded products.
+ *   out [t,d] float32 row-major (the reference returns exactly this block
+ *   viewed as [D,T]). */
+int alive_knn_gather_mean(const float* lib_raw, int64_t n, int32_t d, const int64_t* top_idx,
+                          int32_t t, int32_t k, const float* q_raw, float alpha,
+                          float* out, alive_stream_t stream);
+
+/* Sharded variant, step 1: rows[t,k,d] = raw[top_idx - row_lo] where
+ * row_lo <= top_idx < row_lo + n, else 0 (so a sum over ranks is exact). */
+int alive_knn_gather_rows(const float* lib_raw, int64_t n, int32_t d, int64_t row_lo,
+                          const int64_t* top_idx, int32_t t, int32_t k, float* rows,
+                          alive_stream_t stream);
+/* Sharded variant, step 2: same mean + blend as alive_knn_gather_mean on gathered rows. */
+int alive_knn_mean_blend(const float* rows, int32_t t, int32_t k, int32_t d, const float* q_raw,
+                         float alpha, float* out, alive_stream_t stream);
+
+/* Backward of VoiceLibrary.match w.r.t. tokens (voice_library.py:31-33 under
+ * autograd): grad_rows[top_idx[t,j],:] += scale * grad_out[t,:], scale=(1-alpha)/k.
+ * grad_rows [n,d] float32 must be zeroed by the caller. */
+int alive_knn_scatter_grad(const float* grad_out, const int64_t* top_idx, int32_t t, int32_t k,
+                           int32_t d, float scale, float* grad_rows, int64_t n,
+                           alive_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIVE_KNN_H_ */

@@ -1,0 +1,65 @@
+"""Host-side behaviour that must hold without a GPU: the reference's error behaviour, the
+loud failure when no CUDA device backs the call (there is no CPU fallback), checkpoint
+compatibility of VoiceLibrary, shard arithmetic."""
+import os
+
+import pytest
+import torch
+
+import alive_vc_b200 as A
+from alive_vc_b200.sharded import shard_bounds
+from oracle.gen_golden import GOLDEN_DIR
+
+ERRS = dict(l.rstrip("\n").split("\t") for l in open(os.path.join(GOLDEN_DIR, "errors.txt")))
+
+
+def test_k_larger_than_library_raises_like_reference():
+    with pytest.raises(RuntimeError) as e:
+        A.match_features(torch.randn(1, 768, 3), torch.randn(1, 768, 2), k=4)
+    assert str(e.value) == ERRS["k_gt_n"]
+
+
+def test_empty_library_raises_like_reference():
+    with pytest.raises(RuntimeError) as e:
+        A.match_features(torch.randn(1, 768, 3), torch.zeros(1, 768, 0), k=4)
+    assert str(e.value) == ERRS["empty_library"]
+
+
+def test_batch_mismatch_raises_like_reference():
+    with pytest.raises(RuntimeError) as e:
+        A.match_features(torch.randn(2, 768, 3), torch.randn(1, 768, 20), k=4)
+    assert str(e.value) == ERRS["batch_mismatch"]
+
+
+def test_cpu_tensors_fail_loudly_no_fallback():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        A.match_features(torch.randn(1, 768, 3), torch.randn(1, 768, 20), k=4)
+    vl = A.VoiceLibrary()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vl(torch.randn(1, 768, 5))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        A.pack_library(torch.randn(1, 768, 20))
+
+
+def test_voice_library_checkpoint_layout():
+    vl = A.VoiceLibrary()
+    sd = vl.state_dict()
+    assert list(sd.keys()) == ["tokens"] and tuple(sd["tokens"].shape) == (1, 768, 512)
+    assert sd["tokens"].dtype == torch.float32 and vl.hubert_dim == 768
+    # a reference-format checkpoint ({"tokens": [1,768,N]}) loads into a same-sized module
+    other = A.VoiceLibrary(num_tokens=100)
+    other.load_state_dict({"tokens": torch.zeros(1, 768, 100)})
+    with pytest.raises(RuntimeError):        # size mismatch, like the reference module
+        other.load_state_dict({"tokens": torch.zeros(1, 768, 512)})
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        A.VoiceLibrary(num_tokens=2).match(torch.randn(1, 768, 5), k=4)
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 2), (10, 3), (7, 8), (10_000_000, 8), (0, 4)])
+def test_shard_bounds_partition(n, world):
+    prev = 0
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        assert lo == prev and hi >= lo and hi - lo in (n // world, n // world + 1)
+        prev = hi
+    assert prev == n
