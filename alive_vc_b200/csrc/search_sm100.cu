@@ -53,7 +53,8 @@ template <int kCtas> struct Cfg {
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTxBytes = kStageBytes * kCtas;            // bytes landing per stage, whole unit
   static constexpr uint32_t kSmemData = kStages * kStageBytes;
-  static constexpr uint32_t kSmemBytes = kSmemData + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kScratchBytes = 32 * kNumEpiWarps * 32 * 4;  // epilogue chunk scratch, 32 KB
+  static constexpr uint32_t kSmemBytes = kSmemData + kScratchBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct SearchParams {
@@ -258,10 +259,14 @@ __device__ __forceinline__ void list_insert(float (&s)[kListLen], uint32_t (&id)
   id[0] = top ? idx : id[0];
 }
 
-// One 32-column chunk of one query row: reject with a single max tree when nothing beats the
-// list minimum (the common case), otherwise insert in column order.
+// One 32-column chunk of one query row.  Fast path (the common case once the list has warmed
+// up): one 3-input max tree, nothing beats the list minimum, done.  Slow path: a bit mask of
+// the columns that beat it, the chunk parked in this thread's shared-memory scratch column,
+// and a loop over the set bits with ONE copy of the ordered insert - the code stays small
+// enough to live in the instruction cache (the fully unrolled variant was fetch-bound).
 __device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_base, int n_valid,
-                                           float (&s)[kListLen], uint32_t (&id)[kListLen]) {
+                                           float (&s)[kListLen], uint32_t (&id)[kListLen],
+                                           float* __restrict__ scratch /* [32][256], this thread's column */) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -274,9 +279,18 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_ba
 #pragma unroll
   for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
   if (m > s[kListLen - 1]) {
+    const float thr = s[kListLen - 1];
+    uint32_t mask = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      if (v[j] > s[kListLen - 1]) list_insert(s, id, v[j], static_cast<uint32_t>(col_base + j));
+      scratch[j * (kNumEpiWarps * 32)] = v[j];
+      mask |= (v[j] > thr) ? (1u << j) : 0u;
+    }
+    while (mask) {
+      const int j = __ffs(static_cast<int>(mask)) - 1;
+      mask &= mask - 1;
+      const float x = scratch[j * (kNumEpiWarps * 32)];
+      if (x > s[kListLen - 1]) list_insert(s, id, x, static_cast<uint32_t>(col_base + j));
     }
   }
 }
@@ -295,7 +309,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024 B alignment
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + kStages * kABytes;
-  const uint32_t bars = smem_base + C::kSmemData;
+  const uint32_t scratch_off = C::kSmemData;                     // [32][256] floats
+  const uint32_t bars = smem_base + C::kSmemData + C::kScratchBytes;
   const uint32_t bar_full = bars;                                // kStages x 8 B
   const uint32_t bar_empty = bars + 8 * kStages;                 // kStages x 8 B
   const uint32_t bar_tfull = bars + 16 * kStages;                // 2 x 8 B
@@ -400,6 +415,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int half = (warp - kFirstEpiWarp) >> 2;       // which 128 columns of each tile
     const uint32_t tempty0 = (kCtas == 1) ? bar_tempty : map_to_cta(bar_tempty, 0);
     const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+    float* scratch = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + scratch_off) +
+                     (threadIdx.x - kFirstEpiWarp * 32);
     uint32_t tile_count = 0;
     for (int unit = first_unit; unit < total_units; unit += unit_stride) {
       const int m_unit = unit % p.m_units;
@@ -424,7 +441,6 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         tcgen05_fence_after();
         const uint32_t taddr = taddr_base + acc * kBlockN;
         const int col0 = tile * kBlockN + half * 128;
-        uint32_t va[32], vb[32];
         if (p.debug == 2) {
           tcgen05_fence_before();
           __syncwarp();
@@ -434,29 +450,23 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
           continue;
         }
-        tmem_ld_32x32(taddr, va);
-        tmem_ld_wait(va);
-        tmem_ld_32x32(taddr + 32, vb);
-        if (p.debug == 0) scan_chunk(va, col0, p.n, s, id);
-        else s[0] = fmaxf(s[0], __uint_as_float(va[lane]));
-        tmem_ld_wait(vb);
-        tmem_ld_32x32(taddr + 64, va);
-        if (p.debug == 0) scan_chunk(vb, col0 + 32, p.n, s, id);
-        else s[0] = fmaxf(s[0], __uint_as_float(vb[lane]));
-        tmem_ld_wait(va);
-        tmem_ld_32x32(taddr + 96, vb);
-        if (p.debug == 0) scan_chunk(va, col0 + 64, p.n, s, id);
-        else s[0] = fmaxf(s[0], __uint_as_float(va[lane]));
-        tmem_ld_wait(vb);
-        // all TMEM reads of this accumulator are done: hand it back before the last scan
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kCtas == 1) mbar_arrive(bar_tempty + 8 * acc);
-          else mbar_arrive_cluster(tempty0 + 8 * acc);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + 32 * c, v);
+          tmem_ld_wait(v);
+          if (c == 3) {
+            // every TMEM read of this accumulator is done: hand it back before the last scan
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCtas == 1) mbar_arrive(bar_tempty + 8 * acc);
+              else mbar_arrive_cluster(tempty0 + 8 * acc);
+            }
+          }
+          if (p.debug == 0) scan_chunk(v, col0 + 32 * c, p.n, s, id, scratch);
+          else s[0] = fmaxf(s[0], __uint_as_float(v[0] ^ v[13] ^ v[31]));
         }
-        if (p.debug == 0) scan_chunk(vb, col0 + 96, p.n, s, id);
-        else s[0] = fmaxf(s[0], __uint_as_float(vb[lane]));
       }
 
       if (row_valid) {

@@ -95,6 +95,7 @@ def pack_into(dst: PackedFrames, row0: int, frames_dn: torch.Tensor):
         dst.raw[row0:].data_ptr(), dst.norms[row0:].data_ptr(), dst.packed[row0:].data_ptr(),
         dst.err[row0:].data_ptr(), dst.stats.data_ptr(), _stream_ptr())
     _cabi.check(rc, "alive_knn_pack")
+    _count(1)
 
 
 def pack_frames(frames_dn: torch.Tensor) -> PackedFrames:
@@ -181,6 +182,16 @@ class SearchInfo:
 
 last_info: Optional[SearchInfo] = None
 
+# bookkeeping used by bench.py: kernels launched through the C ABI, and an optional list that
+# receives (start_event, end_event) pairs bracketing every alive_knn_search launch
+launch_count: int = 0
+search_events: Optional[list] = None
+
+
+def _count(n: int):
+    global launch_count
+    launch_count += n
+
 
 def make_plan(t: int, n: int, d: int, device, variant: int = 0) -> _cabi.Plan:
     plan = _cabi.Plan()
@@ -206,6 +217,7 @@ def exact_topk(q: PackedFrames, lib: PackedFrames, k: int, top_score=None, top_i
                            q_count.data_ptr() if q_count is not None else None,
                            lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), _stream_ptr())
     _cabi.check(rc, "alive_knn_exact")
+    _count(2)
     return top_score, top_idx
 
 
@@ -238,9 +250,16 @@ def search_topk(q: PackedFrames, lib: PackedFrames, k: int, mode: str = "auto",
     stream = _stream_ptr()
     cand_score = torch.empty((t, plan.lists, LIST_LEN), dtype=torch.float32, device=dev)
     cand_idx = torch.empty((t, plan.lists, LIST_LEN), dtype=torch.int32, device=dev)
+    if search_events is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = c.alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
                             cand_score.data_ptr(), cand_idx.data_ptr(), stream)
     _cabi.check(rc, "alive_knn_search")
+    if search_events is not None:
+        ev1.record()
+        search_events.append((ev0, ev1))
 
     sel_idx = torch.empty((t, r_max), dtype=torch.int32, device=dev)
     sel_n = torch.empty((t,), dtype=torch.int32, device=dev)
@@ -257,6 +276,7 @@ def search_topk(q: PackedFrames, lib: PackedFrames, k: int, mode: str = "auto",
                              sel_idx.data_ptr(), sel_n.data_ptr(), r_max, k, lib.row_base,
                              top_score.data_ptr(), top_idx.data_ptr(), stream)
     _cabi.check(rc, "alive_knn_rescore")
+    _count(3)   # search + prune + rescore
     # queries the certificate could not clear: exhaustive scan (device-side list, no host sync)
     exact_topk(q, lib, k, top_score, top_idx, fb_list, fb_count)
     last_info = SearchInfo(mode="screen", plan=plan.as_dict(), fb_count=fb_count, sel_n=sel_n, launches=7)
@@ -269,6 +289,7 @@ def gather_mean(lib: PackedFrames, top_idx: torch.Tensor, q: PackedFrames, alpha
     rc = _cabi.load().alive_knn_gather_mean(lib.raw.data_ptr(), lib.n, lib.d, top_idx.data_ptr(), t, k,
                                             q.raw.data_ptr(), float(alpha), out.data_ptr(), _stream_ptr())
     _cabi.check(rc, "alive_knn_gather_mean")
+    _count(1)
     return out
 
 

@@ -65,6 +65,7 @@ class CudaShardBackend:
         rc = _cabi.load().alive_knn_merge(scores.data_ptr(), idx.data_ptr(), r, t, k, top_s.data_ptr(),
                                           top_i.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "alive_knn_merge")
+        M._count(1)
         return top_s, top_i
 
     def gather_rows(self, top_idx):
@@ -74,6 +75,7 @@ class CudaShardBackend:
                                                 self.local.row_base, top_idx.data_ptr(), t, k, rows.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "alive_knn_gather_rows")
+        M._count(1)
         return rows
 
     def mean_blend(self, rows, q, alpha):
@@ -82,6 +84,7 @@ class CudaShardBackend:
         rc = _cabi.load().alive_knn_mean_blend(rows.data_ptr(), t, k, d, q.raw.data_ptr(), float(alpha),
                                                out.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "alive_knn_mean_blend")
+        M._count(1)
         return out
 
 
@@ -138,12 +141,12 @@ class ShardedLibrary:
             top_s, top_i = loc_s, loc_i
         else:
             # 2. all-gather candidates
-            all_s = torch.empty((self.world, t, k), dtype=torch.float32, device=dev)
-            all_i = torch.empty((self.world, t, k), dtype=torch.int64, device=dev)
+            all_s = torch.empty((self.world * t, k), dtype=torch.float32, device=dev)
+            all_i = torch.empty((self.world * t, k), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(all_s, loc_s, group=self.group)
             dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
             # 3. merge
-            top_s, top_i = be.merge(all_s, all_i, k)
+            top_s, top_i = be.merge(all_s.view(self.world, t, k), all_i.view(self.world, t, k), k)
         # 4. owned rows, zeros elsewhere;  5. exact sum over ranks
         rows = be.gather_rows(top_i)
         if self.world > 1:

@@ -1,0 +1,253 @@
+"""Parity tests proper: the CUDA path (through the C ABI / the drop-in Python API) against the
+oracle and against golden vectors produced by the unmodified reference.
+
+Bars (north_star): neighbour indices bit-exact except where fp32 similarities tie within
+1e-6; features within 1e-5 relative - and bit-exact wherever the index rows agree, because
+the gather/mean/blend arithmetic is modelled exactly.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import alive_vc_b200 as A                                   # noqa: E402
+from alive_vc_b200 import _cabi, matching as M               # noqa: E402
+from oracle import knn_oracle as O                           # noqa: E402
+from oracle.gen_golden import CASES, GOLDEN_DIR, make_case_inputs   # noqa: E402
+
+TIE_TOL = 1e-6       # north_star: indices may differ only where fp32 similarities tie within 1e-6
+FEAT_RTOL = 1e-5     # north_star: features within 1e-5 relative
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _assert_parity(out, idx, src, ref_b, k, alpha, want_idx=None, want_out=None):
+    scores = O.cosine_scores_np(src, ref_b)
+    if want_idx is None:
+        want_out, want_idx, _ = O.match_features_np(src, ref_b, k, alpha, True)
+    idx_np = idx.cpu().numpy()
+    ok, n_exact, n_tie, bad = O.indices_match_mod_ties(idx_np, want_idx.astype(np.int64), scores, TIE_TOL)
+    assert ok, f"index parity broken: {bad}"
+    o = out.detach().cpu().numpy()
+    same = (idx_np == want_idx).all(axis=2)
+    assert np.array_equal(np.swapaxes(o, 1, 2)[same], np.swapaxes(want_out, 1, 2)[same]), \
+        "features not bit-exact on rows with identical indices"
+    # rows excused by a similarity tie: the features must still be the exact mean of OUR indices
+    if (~same).any():
+        mine = np.swapaxes(O.gather_mean_np(ref_b, idx_np), 1, 2)
+        mine = ((mine * np.float32(1 - alpha)).astype(np.float32) + (src * np.float32(alpha)).astype(np.float32))
+        np.testing.assert_allclose(o, mine.astype(np.float32), rtol=FEAT_RTOL, atol=1e-6)
+    else:
+        np.testing.assert_allclose(o, want_out, rtol=FEAT_RTOL, atol=1e-6)
+    return n_exact, n_tie
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_vectors_from_reference(name):
+    """Replays every fixture generated from the unmodified reference (tests/golden)."""
+    spec = CASES[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    src, ref = make_case_inputs(spec)
+    s = _cuda(src)
+    if spec["kind"] == "vl":
+        vl = A.VoiceLibrary(num_tokens=spec["N"]).cuda()
+        with torch.no_grad():
+            vl.tokens.copy_(_cuda(ref))
+        s.requires_grad_(True)
+        out, idx = vl.match(s, k=spec["k"], alpha=spec["alpha"], return_indices=True)
+        gout = _cuda(np.random.default_rng(spec["seed"] + 1000).standard_normal(g["out"].shape, dtype=np.float32))
+        out.backward(gout)
+        np.testing.assert_allclose(vl.tokens.grad.cpu().numpy(), g["grad_tokens"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(s.grad.cpu().numpy(), g["grad_source"], rtol=1e-6, atol=1e-7)
+        ref_b = np.broadcast_to(ref, (src.shape[0],) + ref.shape[1:])
+    else:
+        r = _cuda(ref)
+        if spec["kind"] == "mf_strided":           # non-contiguous library view, realtime_inference.py:88
+            big = torch.zeros((ref.shape[0], ref.shape[1], ref.shape[2] * 4), device="cuda")
+            big[:, :, ::4] = r
+            r = big[:, :, ::4]
+            assert not r.is_contiguous()
+        out, idx = A.match_features(s, r, spec["k"], spec["alpha"], return_indices=True)
+        ref_b = ref
+    _assert_parity(out, idx, src, ref_b, spec["k"], spec["alpha"], g["indices"], g["out"])
+    B, D, T = g["out"].shape
+    assert tuple(out.shape) == (B, D, T)
+    if T > 1:
+        assert tuple(out.stride()) == tuple(g["out_strides"])      # transposed view of [B,T,D]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,T,N,k,alpha", [
+    (1, 50, 3000, 4, 0.0), (1, 200, 20000, 4, 0.0), (2, 33, 1517, 4, 0.25), (1, 96, 50000, 8, 0.0),
+    (1, 1, 2049, 1, 0.0), (1, 129, 4097, 4, 0.0), (1, 300, 257, 4, 0.0), (3, 7, 256, 2, 1.0),
+])
+def test_screened_path_against_oracle(variant, B, T, N, k, alpha):
+    """tensor-core screen + certificate + exact rescoring == oracle, both kernel variants"""
+    rng = np.random.default_rng(1000 * T + N + k)
+    src = rng.standard_normal((B, 768, T), dtype=np.float32)
+    ref = rng.standard_normal((B, 768, N), dtype=np.float32)
+    out, idx = A.match_features(_cuda(src), _cuda(ref), k, alpha, return_indices=True, mode="screen", variant=variant)
+    assert M.last_info.mode == "screen"
+    _assert_parity(out, idx, src, ref, k, alpha)
+
+
+@pytest.mark.parametrize("T,N,k", [(50, 300, 4), (7, 64, 4), (40, 1000, 8), (10, 700, 16), (5, 4, 4), (33, 20000, 4),
+                                   (3, 70, 64)])
+def test_exact_scan_against_oracle(T, N, k):
+    rng = np.random.default_rng(T * N + k)
+    src = rng.standard_normal((1, 768, T), dtype=np.float32)
+    ref = rng.standard_normal((1, 768, N), dtype=np.float32)
+    out, idx = A.match_features(_cuda(src), _cuda(ref), k, 0.0, return_indices=True, mode="exact")
+    _assert_parity(out, idx, src, ref, k, 0.0)
+
+
+def test_full_size_cfg1_against_oracle():
+    """BASELINE configs[0] at full size: T=1000 vs N=100k (the oracle needs ~1 s on CPU)."""
+    rng = np.random.default_rng(11)
+    src = rng.standard_normal((1, 768, 1000), dtype=np.float32)
+    ref = rng.standard_normal((1, 768, 100_000), dtype=np.float32)
+    out, idx = A.match_features(_cuda(src), _cuda(ref), 4, 0.0, return_indices=True)
+    n_exact, n_tie = _assert_parity(out, idx, src, ref, 4, 0.0)
+    assert M.last_info.mode == "screen" and n_exact >= 990
+    assert M.last_info.fallback_queries() <= 10
+
+
+def test_full_size_cfg2_against_oracle():
+    """BASELINE configs[1] at full size: streaming chunk T=32 vs N=200k."""
+    rng = np.random.default_rng(12)
+    src = rng.standard_normal((1, 768, 32), dtype=np.float32)
+    ref = rng.standard_normal((1, 768, 200_000), dtype=np.float32)
+    out, idx = A.match_features(_cuda(src), _cuda(ref), 4, 0.0, return_indices=True)
+    _assert_parity(out, idx, src, ref, 4, 0.0)
+
+
+def test_pack_kernel_layout_and_stats():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for n in (1, 31, 300, 4097):
+        x = torch.randn(768, n, device="cuda", generator=g)
+        p = M.pack_frames(x)
+        assert torch.equal(p.raw, x.t().contiguous())
+        nrm = torch.linalg.vector_norm(x.double(), dim=0).float()
+        assert torch.allclose(p.norms, nrm, rtol=2e-7, atol=0)
+        xn = (x / p.norms[None, :]).t()
+        assert torch.equal(p.packed, xn.bfloat16())
+        err = (xn.bfloat16().float() - xn).double().norm(dim=1).float()
+        assert torch.allclose(p.err, err, rtol=1e-3, atol=1e-8)
+        st = p.stats.cpu().numpy().view(np.uint32)
+        assert st[1] == 0
+        assert abs(np.array([st[0]], np.uint32).view(np.float32)[0] - float(p.err.max())) < 1e-9
+    x = torch.randn(500, 768, device="cuda", generator=g)      # already row-major frames
+    assert torch.equal(M.pack_frames(x.t()).raw, x)
+    x = torch.randn(768, 40, device="cuda", generator=g)
+    x[:, 17] = 0                                               # zero frame -> NaN similarities in the reference
+    assert M.pack_frames(x).stats.cpu().numpy().view(np.uint32)[1] == 1
+
+
+def test_zero_library_frame_ranks_first_like_torch_topk():
+    rng = np.random.default_rng(5)
+    src = rng.standard_normal((1, 768, 6), dtype=np.float32)
+    ref = rng.standard_normal((1, 768, 3000), dtype=np.float32)
+    ref[:, :, 17] = 0
+    out, idx = A.match_features(_cuda(src), _cuda(ref), 4, 0.0, return_indices=True, mode="screen")
+    assert (idx[0, :, 0] == 17).all()
+    assert M.last_info.fallback_queries() == 6            # non-finite library rows force the exact scan
+    _, idx_o, _ = O.match_features_np(src, ref, 4, 0.0, True)
+    assert np.array_equal(idx.cpu().numpy(), idx_o)
+
+
+def test_duplicate_frames_and_certificate_fallback():
+    """exact ties (duplicated frames) cannot be certified by the screen -> exact scan, lowest index wins"""
+    rng = np.random.default_rng(15)
+    base = rng.standard_normal((1, 768, 700), dtype=np.float32)
+    ref = np.concatenate([base] * 4, axis=2)                   # N = 2800, every frame 4 times
+    src = base[:, :, :40].copy()
+    out, idx = A.match_features(_cuda(src), _cuda(ref), 4, 0.0, return_indices=True, mode="screen")
+    idx_np = idx.cpu().numpy()[0]
+    want = np.stack([np.arange(40) + 700 * j for j in range(4)], axis=1)
+    assert np.array_equal(np.sort(idx_np, axis=1), want)        # the four copies of the query frame itself
+    np.testing.assert_allclose(out.cpu().numpy(), src, rtol=1e-6, atol=1e-6)
+
+
+def test_search_lists_match_bf16_matmul():
+    """K2 alone: the screened lists equal a torch matmul of the same bf16 operands, per list."""
+    for variant, T, N in [(1, 200, 5000), (2, 200, 5000), (1, 129, 4097), (2, 300, 70000)]:
+        g = torch.Generator(device="cuda").manual_seed(T + N)
+        q = M.pack_frames(torch.randn(768, T, device="cuda", generator=g))
+        lib = M.pack_frames(torch.randn(768, N, device="cuda", generator=g))
+        plan = M.make_plan(T, N, 768, q.device, variant)
+        cs = torch.full((T, plan.lists, 8), float("nan"), device="cuda")
+        ci = torch.full((T, plan.lists, 8), -7, dtype=torch.int32, device="cuda")
+        rc = _cabi.load().alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
+                                           cs.data_ptr(), ci.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "search")
+        ref = q.packed.float() @ lib.packed.float().t()
+        for seg in range(plan.segments):
+            t0, t1 = seg * plan.tiles_per_segment, min((seg + 1) * plan.tiles_per_segment, plan.n_tiles)
+            for half in range(2):
+                cols = [torch.arange(t * 256 + half * 128, min(t * 256 + half * 128 + 128, N), device="cuda")
+                        for t in range(t0, t1) if t * 256 + half * 128 < N]
+                lst = seg * 2 + half
+                if not cols:
+                    assert (ci[:, lst] == -1).all()
+                    continue
+                cols = torch.cat(cols)
+                kk = min(8, cols.numel())
+                want_s, _ = ref[:, cols].topk(kk, dim=1)
+                assert (cs[:, lst, :kk] - want_s).abs().max().item() < 2e-4
+                got_at = ref.gather(1, ci[:, lst, :kk].long())
+                assert (got_at - cs[:, lst, :kk]).abs().max().item() < 2e-4
+                assert (ci[:, lst, kk:] == -1).all()
+
+
+def test_pack_cache_invalidation_on_inplace_update():
+    """fine_tune.py:170 updates VL.tokens in place every step: the packed copy must follow."""
+    vl = A.VoiceLibrary(num_tokens=600).cuda()
+    src = torch.randn(1, 768, 20, device="cuda")
+    out1, idx1 = vl.match(src, return_indices=True)
+    p1 = vl.packed()
+    assert vl.packed() is p1                                   # cached while unchanged
+    with torch.no_grad():
+        vl.tokens.mul_(-1.0)                                   # in-place: bumps the version counter
+    out2, idx2 = vl.match(src, return_indices=True)
+    assert vl.packed() is not p1
+    ref = vl.tokens.detach().cpu().numpy()
+    _assert_parity(out2, idx2, src.cpu().numpy(), ref, 4, 0.0)
+    assert not torch.equal(idx1, idx2)
+
+
+def test_idempotence_and_self_match_property():
+    """size-independent properties at a larger size: every library frame's best match is itself
+    (similarity 1), and matching twice gives identical bits."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    ref = torch.randn(1, 768, 300_000, device="cuda", generator=g)
+    src = ref[:, :, 1000:1000 + 2048].contiguous()
+    out, idx = A.match_features(src, ref, 4, 0.0, return_indices=True)
+    assert torch.equal(idx[0, :, 0], torch.arange(1000, 1000 + 2048, device="cuda"))
+    out_b, idx_b = A.match_features(src, ref, 4, 0.0, return_indices=True)
+    assert torch.equal(idx, idx_b) and torch.equal(out, out_b)
+    # k=1 returns the frames themselves bit-exactly
+    out1 = A.match_features(src, ref, 1, 0.0)
+    assert torch.equal(out1, src)
+    # the two kernel variants agree bit for bit
+    o1, i1 = A.match_features(src, ref, 4, 0.0, return_indices=True, variant=1)
+    o2, i2 = A.match_features(src, ref, 4, 0.0, return_indices=True, variant=2)
+    assert torch.equal(i1, i2) and torch.equal(o1, o2)
+
+
+def test_dtype_passthrough_and_autograd_of_match_features():
+    src = torch.randn(1, 768, 12, device="cuda", dtype=torch.float16)
+    ref = torch.randn(1, 768, 2000, device="cuda")
+    out = A.match_features(src, ref, 4, 0.0)
+    assert out.dtype == torch.float16 and tuple(out.shape) == (1, 768, 12)
+    s = torch.randn(1, 768, 12, device="cuda", requires_grad=True)
+    r = torch.randn(1, 768, 2000, device="cuda", requires_grad=True)
+    out = A.match_features(s, r, 4, 0.3)
+    out.sum().backward()
+    assert r.grad is None                                         # common.py:98 no_grad
+    torch.testing.assert_close(s.grad, torch.full_like(s, 0.3))
