@@ -26,7 +26,7 @@ EXPORTS = [
     "alive_knn_last_error", "alive_knn_abi_version", "alive_knn_pack", "alive_knn_plan",
     "alive_knn_search", "alive_knn_prune", "alive_knn_rescore", "alive_knn_exact_workspace_bytes",
     "alive_knn_exact", "alive_knn_merge", "alive_knn_gather_mean", "alive_knn_gather_rows",
-    "alive_knn_mean_blend", "alive_knn_scatter_grad",
+    "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
 ]
 
 
@@ -41,6 +41,14 @@ class Plan(ctypes.Structure):
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class Library(ctypes.Structure):
+    """mirror of alive_knn_library_t"""
+    _fields_ = [
+        ("packed", ctypes.c_void_p), ("raw", ctypes.c_void_p), ("norms", ctypes.c_void_p),
+        ("stats", ctypes.c_void_p), ("n", ctypes.c_int64), ("d", ctypes.c_int32), ("row_base", ctypes.c_int64),
+    ]
 
 
 def nvcc_path() -> str:
@@ -114,6 +122,11 @@ def _declare(lib):
     lib.alive_knn_mean_blend.argtypes = [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp]
     lib.alive_knn_scatter_grad.restype = ctypes.c_int
     lib.alive_knn_scatter_grad.argtypes = [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _i64, _vp]
+    lib.alive_knn_match_layout.restype = ctypes.c_int
+    lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
+    lib.alive_knn_match.restype = ctypes.c_int
+    lib.alive_knn_match.argtypes = [_vp, _i32, _i32, _i64, _i64, _i64, ctypes.POINTER(Library), _i32, _f32, _i32,
+                                    _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]
 
 
 def load():

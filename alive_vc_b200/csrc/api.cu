@@ -17,3 +17,131 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* alive_knn_last_error(void) { return alive::g_error; }
 extern "C" int alive_knn_abi_version(void) { return ALIVE_KNN_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------
+// One-call pipeline: pack queries -> search -> prune -> rescore -> exact (uncertified) -> gather.
+// All launches go to `stream`, all scratch lives in one caller-provided workspace; nothing
+// synchronises the host, so the whole call is CUDA-graph capturable.
+// ---------------------------------------------------------------------------------------------
+namespace alive {
+namespace {
+
+constexpr int kOffQRaw = 0, kOffQNorm = 1, kOffQPacked = 2, kOffQErr = 3, kOffCandScore = 4, kOffCandIdx = 5,
+              kOffSelIdx = 6, kOffSelN = 7, kOffFbList = 8, kOffFbCount = 9, kOffExact = 10, kOffTotal = 11;
+
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+int resolve_mode(int mode, int64_t n, int d, int k) {
+  if (mode == 0) return (k > ALIVE_KNN_LIST_LEN || n < 1024 || d % 64 != 0) ? 2 : 1;
+  return mode;
+}
+
+int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t num_sms, int32_t variant, int mode,
+           alive_knn_plan_t* plan, int64_t* off) {
+  size_t cur = 0;
+  auto take = [&](int slot, size_t bytes) {
+    off[slot] = static_cast<int64_t>(cur);
+    cur += align256(bytes);
+  };
+  take(kOffQRaw, static_cast<size_t>(rows) * d * 4);
+  take(kOffQNorm, static_cast<size_t>(rows) * 4);
+  take(kOffQPacked, static_cast<size_t>(rows) * d * 2);
+  take(kOffQErr, static_cast<size_t>(rows) * 4);
+  size_t lists = 0;
+  if (mode == 1) {
+    int rc = alive_knn_plan(rows, n, d, num_sms, variant, plan);
+    if (rc) return rc;
+    lists = static_cast<size_t>(plan->lists);
+  }
+  take(kOffCandScore, static_cast<size_t>(rows) * lists * ALIVE_KNN_LIST_LEN * 4);
+  take(kOffCandIdx, static_cast<size_t>(rows) * lists * ALIVE_KNN_LIST_LEN * 4);
+  take(kOffSelIdx, mode == 1 ? static_cast<size_t>(rows) * r_max * 4 : 0);
+  take(kOffSelN, static_cast<size_t>(rows) * 4);
+  take(kOffFbList, static_cast<size_t>(rows) * 4);
+  take(kOffFbCount, 4);
+  take(kOffExact, alive_knn_exact_workspace_bytes(rows, n, k));
+  off[kOffTotal] = static_cast<int64_t>(cur);
+  return 0;
+}
+
+}  // namespace
+}  // namespace alive
+
+extern "C" int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
+                                      int32_t num_sms, int32_t variant, int64_t* offsets12) {
+  using namespace alive;
+  ALIVE_REQUIRE(offsets12 != nullptr, "alive_knn_match_layout: offsets is NULL");
+  ALIVE_REQUIRE(rows >= 1 && n >= 1 && k >= 1 && k <= ALIVE_KNN_MAX_K, "alive_knn_match_layout: bad sizes");
+  alive_knn_plan_t plan;
+  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), &plan, offsets12);
+}
+
+extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
+                               int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha,
+                               int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
+                               size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
+                               void* ev_search_start, void* ev_search_stop, alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(source && lib && workspace && top_idx && top_score, "alive_knn_match: NULL argument");
+  ALIVE_REQUIRE(batch >= 1 && t >= 1, "alive_knn_match: empty query batch");
+  ALIVE_REQUIRE(static_cast<int64_t>(batch) * t < (1ll << 31), "alive_knn_match: too many query frames");
+  ALIVE_REQUIRE(k >= 1 && k <= lib->n, "selected index k out of range");
+  ALIVE_REQUIRE(k <= ALIVE_KNN_MAX_K, "alive_knn_match: k must be <= %d", ALIVE_KNN_MAX_K);
+  const int32_t rows = batch * t;
+  const int32_t d = lib->d;
+  mode = resolve_mode(mode, lib->n, d, k);
+  ALIVE_REQUIRE(mode == 1 || mode == 2, "alive_knn_match: mode must be 0 (auto), 1 (screen) or 2 (exact)");
+  ALIVE_REQUIRE(mode == 2 || k <= ALIVE_KNN_LIST_LEN, "alive_knn_match: the screened path needs k <= %d", ALIVE_KNN_LIST_LEN);
+  alive_knn_plan_t plan;
+  int64_t off[12];
+  int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, &plan, off);
+  if (rc) return rc;
+  ALIVE_REQUIRE(static_cast<size_t>(off[kOffTotal]) <= workspace_bytes,
+                "alive_knn_match: workspace too small (%zu < %lld)", workspace_bytes, static_cast<long long>(off[kOffTotal]));
+  ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "alive_knn_match: workspace must be 256-byte aligned");
+  char* ws = static_cast<char*>(workspace);
+  float* q_raw = reinterpret_cast<float*>(ws + off[kOffQRaw]);
+  float* q_norm = reinterpret_cast<float*>(ws + off[kOffQNorm]);
+  uint16_t* q_packed = reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]);
+  float* q_err = reinterpret_cast<float*>(ws + off[kOffQErr]);
+  float* cand_score = reinterpret_cast<float*>(ws + off[kOffCandScore]);
+  int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + off[kOffCandIdx]);
+  int32_t* sel_idx = reinterpret_cast<int32_t*>(ws + off[kOffSelIdx]);
+  int32_t* sel_n = reinterpret_cast<int32_t*>(ws + off[kOffSelN]);
+  int32_t* fb_list = reinterpret_cast<int32_t*>(ws + off[kOffFbList]);
+  int32_t* fb_count = reinterpret_cast<int32_t*>(ws + off[kOffFbCount]);
+  void* exact_ws = ws + off[kOffExact];
+
+  for (int32_t b = 0; b < batch; ++b) {
+    const size_t r0 = static_cast<size_t>(b) * t;
+    rc = alive_knn_pack(source + static_cast<int64_t>(b) * stride_b, t, d, stride_t, stride_d, q_raw + r0 * d,
+                        q_norm + r0, q_packed + r0 * d, q_err + r0, nullptr, stream);
+    if (rc) return rc;
+  }
+  if (mode == 1) {
+    if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
+    rc = alive_knn_search(q_packed, lib->packed, &plan, cand_score, cand_idx, stream);
+    if (rc) return rc;
+    if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
+    rc = alive_knn_prune(cand_score, cand_idx, rows, plan.lists, k, q_err, q_norm, lib->stats, r_max, sel_idx, sel_n,
+                         fb_list, fb_count, stream);
+    if (rc) return rc;
+    rc = alive_knn_rescore(q_raw, q_norm, rows, lib->raw, lib->norms, d, sel_idx, sel_n, r_max, k, lib->row_base,
+                           top_score, top_idx, stream);
+    if (rc) return rc;
+    rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, fb_list, fb_count, lib->row_base,
+                         exact_ws, top_score, top_idx, stream);
+    if (rc) return rc;
+  } else {
+    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, 4, as_stream(stream)));
+    rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
+                         exact_ws, top_score, top_idx, stream);
+    if (rc) return rc;
+  }
+  if (out) {
+    ALIVE_REQUIRE(lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
+    rc = alive_knn_gather_mean(lib->raw, lib->n, d, top_idx, rows, k, q_raw, alpha, out, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -23,9 +23,11 @@
 namespace alive {
 namespace {
 
-constexpr int kFrames = 32;        // frames per CTA
 constexpr int kPackThreads = 256;  // 8 warps
 
+// kFrames = frames per CTA: 32 for libraries (128-byte coalesced reads of the channel-major
+// input), 8 for small query batches (more CTAs; 32-byte sectors are still fully used).
+template <int kFrames>
 __global__ void __launch_bounds__(kPackThreads)
 pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
             float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
@@ -37,10 +39,13 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
   const int nf = static_cast<int>(min(static_cast<long long>(kFrames), n - f0));
 
   if (stride_n == 1 || stride_d != 1) {
-    // frames are the fast axis (or fully strided): lane = frame, warps stride over channels
-    const bool ok = lane < nf;
-    const float* src = x + (f0 + lane) * stride_n;
-    for (int j = warp; j < d; j += kPackThreads / 32) tile[j * ld + lane] = ok ? src[j * stride_d] : 0.f;
+    // frames are the fast axis (or fully strided): lane -> (frame, channel sub-row)
+    constexpr int kRowsPerWarp = 32 / kFrames;
+    const int f = lane % kFrames, jsub = lane / kFrames;
+    const bool ok = f < nf;
+    const float* src = x + (f0 + f) * stride_n;
+    for (int j = warp * kRowsPerWarp + jsub; j < d; j += (kPackThreads / 32) * kRowsPerWarp)
+      tile[j * ld + f] = ok ? src[j * stride_d] : 0.f;
   } else {
     // already row-major frames: lane = channel
     for (int f = warp; f < kFrames; f += kPackThreads / 32) {
@@ -103,15 +108,22 @@ extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stri
   ALIVE_REQUIRE(d >= 2 && d % 2 == 0 && d <= 1536, "alive_knn_pack: d must be even and <= 1536 (got %d)", d);
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 3) == 0, "alive_knn_pack: packed must be 4-byte aligned");
   if (n == 0) return 0;
-  const size_t smem = static_cast<size_t>(d) * (kFrames + 1) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * (kFrames + 1) * 4));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4));
     attr_done = true;
   }
-  const unsigned grid = static_cast<unsigned>((n + kFrames - 1) / kFrames);
-  pack_kernel<<<grid, kPackThreads, smem, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw, norms,
-                                                              reinterpret_cast<__nv_bfloat16*>(packed), err, stats);
+  __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
+  if (n <= 8192) {
+    const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
+    pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
+        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats);
+  } else {
+    const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
+    pack_kernel<32><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
+        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats);
+  }
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

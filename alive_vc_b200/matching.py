@@ -61,7 +61,16 @@ class PackedFrames:
     err: torch.Tensor        # [n]   float32, ||bf16(x/|x|) - x/|x|||_2
     stats: torch.Tensor      # [2]   int32 (uint32 bit patterns): max err, non-finite row count
     row_base: int = 0        # global index of frame 0 (sharded libraries)
-    _keepalive: list = field(default_factory=list, repr=False)
+    _handle: object = field(default=None, repr=False)
+
+    def handle(self) -> "_cabi.Library":
+        """alive_knn_library_t view of these buffers (rebuilt if row_base changed)."""
+        h = self._handle
+        if h is None or h.row_base != self.row_base:
+            h = _cabi.Library(self.packed.data_ptr(), self.raw.data_ptr(), self.norms.data_ptr(),
+                              self.stats.data_ptr(), self.n, self.d, self.row_base)
+            self._handle = h
+        return h
 
     @property
     def device(self):
@@ -302,16 +311,125 @@ def pack_queries(source: torch.Tensor) -> PackedFrames:
     return out
 
 
+_MODES = {"auto": 0, "screen": 1, "exact": 2}
+
+
+def _layout(rows: int, lib: PackedFrames, k: int, r_max: int, mode: int, variant: int, device):
+    off = (ctypes.c_int64 * 12)()
+    rc = _cabi.load().alive_knn_match_layout(rows, lib.n, lib.d, k, r_max, mode, _num_sms(device), variant, off)
+    _cabi.check(rc, "alive_knn_match_layout")
+    return list(off)
+
+
+def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0, mode: str = "auto",
+              variant: int = 0, r_max: int = DEFAULT_R_MAX, want_out: bool = True, workspace=None,
+              out=None, top_idx=None, top_score=None):
+    """The whole path in ONE C call (alive_knn_match): pack the B*T query frames of `source`
+    [B,D,T] (any strides, float32, CUDA), search, certify, rescore, exact-scan the uncertified,
+    gather+mean+blend.  Returns (out [B,T,D] or None, top_idx [B,T,k] int64, top_score [B,T,k])."""
+    global last_info
+    c = _cabi.load()
+    B, D, T = source.shape
+    if D != lib.d:
+        raise RuntimeError(f"feature dims differ: queries {D}, library {lib.d}")
+    if not isinstance(k, int) or k < 1 or k > lib.n:
+        raise RuntimeError("selected index k out of range")   # torch.topk's message (common.py:105)
+    if k > MAX_K:
+        raise RuntimeError(f"alive_vc_b200 supports k <= {MAX_K} (got {k})")
+    _require_cuda(source, "source")
+    assert source.dtype == torch.float32
+    dev = source.device
+    rows = B * T
+    m = _MODES[mode]
+    if m == 0:
+        m = 2 if (k > LIST_LEN or lib.n < EXACT_BELOW_N or lib.d % 64 != 0) else 1
+    off = _layout(rows, lib, k, r_max, m, variant, dev)
+    if workspace is None:
+        workspace = torch.empty((off[11],), dtype=torch.uint8, device=dev)
+    if want_out and out is None:
+        out = torch.empty((B, T, D), dtype=torch.float32, device=dev)
+    if top_idx is None:
+        top_idx = torch.empty((B, T, k), dtype=torch.int64, device=dev)
+        top_score = torch.empty((B, T, k), dtype=torch.float32, device=dev)
+    ev0 = ev1 = None
+    if search_events is not None and m == 1:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()      # forces creation of the cudaEvent_t handles; re-recorded inside the C call
+        ev1.record()
+        search_events.append((ev0, ev1))
+    rc = c.alive_knn_match(source.data_ptr(), B, T, source.stride(0), source.stride(2), source.stride(1),
+                           ctypes.byref(lib.handle()), k, float(alpha), r_max, m, _num_sms(dev), variant,
+                           workspace.data_ptr(), workspace.numel(), out.data_ptr() if want_out else None,
+                           top_idx.data_ptr(), top_score.data_ptr(),
+                           ev0.cuda_event if ev0 is not None else None,
+                           ev1.cuda_event if ev1 is not None else None, _stream_ptr())
+    _cabi.check(rc, "alive_knn_match")
+    _count(B + (5 if m == 1 else 2) + (1 if want_out else 0))
+    last_info = SearchInfo(mode="screen" if m == 1 else "exact",
+                           fb_count=workspace[off[9]:off[9] + 4].view(torch.int32),
+                           sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
+                           launches=B + (5 if m == 1 else 2) + (1 if want_out else 0))
+    last_info._workspace = workspace
+    return (out if want_out else None), top_idx, top_score
+
+
 def match_packed(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0,
                  mode: str = "auto", variant: int = 0, r_max: int = DEFAULT_R_MAX):
     """All B*T query frames of `source` [B,D,T] against ONE packed library.
     Returns (out [B,T,D] float32 contiguous, top_idx [B,T,k] int64, top_score [B,T,k])."""
-    B, D, T = source.shape
-    q = pack_queries(source)
-    top_score, top_idx = search_topk(q, lib, k, mode=mode, variant=variant, r_max=r_max)
-    out = torch.empty((B, T, D), dtype=torch.float32, device=source.device)
-    gather_mean(lib, top_idx, q, alpha, out)
-    return out, top_idx.view(B, T, k), top_score.view(B, T, k)
+    return run_match(source, lib, k, alpha, mode, variant, r_max)
+
+
+class StreamingMatcher:
+    """Fixed-shape matcher for the realtime loop (realtime_inference.py:130-191): the library
+    is packed once, every buffer is pre-allocated, and the whole pipeline (pack queries ->
+    search -> prune -> rescore -> exact -> gather) is captured in ONE CUDA graph that is
+    replayed per chunk - no allocation, no host synchronisation, one graph launch.
+
+        sm = StreamingMatcher(pack_library(tgt), T=32)
+        out = sm(chunk)          # chunk [B, D, T] float32 CUDA -> [B, D, T] (static buffer, reused)
+    """
+
+    def __init__(self, lib: PackedFrames, T: int, k: int = 4, alpha: float = 0.0, batch: int = 1,
+                 mode: str = "auto", variant: int = 0, r_max: int = DEFAULT_R_MAX, use_graph: bool = True):
+        dev = lib.device
+        self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max = lib, k, float(alpha), mode, variant, r_max
+        self.src = torch.zeros((batch, lib.d, T), dtype=torch.float32, device=dev)
+        self.out = torch.empty((batch, T, lib.d), dtype=torch.float32, device=dev)
+        self.top_idx = torch.empty((batch, T, k), dtype=torch.int64, device=dev)
+        self.top_score = torch.empty((batch, T, k), dtype=torch.float32, device=dev)
+        m = _MODES[mode]
+        if m == 0:
+            m = 2 if (k > LIST_LEN or lib.n < EXACT_BELOW_N or lib.d % 64 != 0) else 1
+        off = _layout(batch * T, lib, k, r_max, m, variant, dev)
+        self.workspace = torch.empty((off[11],), dtype=torch.uint8, device=dev)
+        self.graph = None
+        self._run()                                   # eager warm-up (one-time attribute setup)
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._run()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run()
+            self.graph = g
+
+    def _run(self):
+        run_match(self.src, self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max,
+                  workspace=self.workspace, out=self.out, top_idx=self.top_idx, top_score=self.top_score)
+
+    def __call__(self, source: torch.Tensor) -> torch.Tensor:
+        self.src.copy_(source, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+            _count(self.src.shape[0] + 6)
+        else:
+            self._run()
+        return self.out.transpose(1, 2)
 
 
 def _check_inputs(source: torch.Tensor, reference: torch.Tensor, k: int):

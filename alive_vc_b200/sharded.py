@@ -50,11 +50,23 @@ class CudaShardBackend:
         return self.local.device
 
     def pack_queries(self, source):
-        return M.pack_queries(source if source.dtype == torch.float32 else source.float())
+        """Queries are packed inside alive_knn_match; keep the fp32 source and (after local_topk)
+        the workspace that holds the row-major raw query frames needed by the blend."""
+        return _Queries(source if source.dtype == torch.float32 else source.float())
 
     def local_topk(self, q, k):
         """([T,k] float32, [T,k] int64 global indices); k <= frames on this shard."""
-        return M.search_topk(q, self.local, k, mode=self.mode, variant=self.variant)
+        B, D, T = q.source.shape
+        _, idx, score = M.run_match(q.source, self.local, k, 0.0, self.mode, self.variant, want_out=False)
+        ws = M.last_info._workspace
+        q.raw = ws[: B * T * D * 4].view(torch.float32).view(B * T, D)     # offset 0 of the layout = q_raw
+        q.workspace = ws
+        return score.view(B * T, k), idx.view(B * T, k)
+
+    def match_single(self, source, k, alpha):
+        """world == 1: the plain one-call pipeline (no exchange step needed)."""
+        return M.run_match(source if source.dtype == torch.float32 else source.float(), self.local, k, alpha,
+                           self.mode, self.variant)
 
     def merge(self, scores, idx, k):
         r, t, kk = scores.shape
@@ -80,12 +92,21 @@ class CudaShardBackend:
 
     def mean_blend(self, rows, q, alpha):
         t, k, d = rows.shape
+        if q.raw is None:       # this shard held no frames, so alive_knn_match never packed the queries
+            q.raw = M.pack_queries(q.source).raw
         out = torch.empty((t, d), dtype=torch.float32, device=rows.device)
         rc = _cabi.load().alive_knn_mean_blend(rows.data_ptr(), t, k, d, q.raw.data_ptr(), float(alpha),
                                                out.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "alive_knn_mean_blend")
         M._count(1)
         return out
+
+
+class _Queries:
+    def __init__(self, source):
+        self.source = source
+        self.raw = None
+        self.workspace = None
 
 
 class ShardedLibrary:
@@ -126,6 +147,12 @@ class ShardedLibrary:
             raise RuntimeError("selected index k out of range")
         B, D, T = source.shape
         be = self.backend
+        if self.world == 1 and hasattr(be, "match_single") and self.n_local >= k:
+            out_btd, idx, _ = be.match_single(source, k, alpha)
+            out = out_btd.transpose(1, 2)
+            if out.dtype != source.dtype:
+                out = out.to(source.dtype)
+            return (out, idx) if return_indices else out
         q = be.pack_queries(source)
         t = B * T
         dev = source.device

@@ -259,6 +259,12 @@ def gpu_arm(args):
 
         def step(src):
             return sharded.match(src, K, 0.0)
+        if args.workload == "cfg2" and world == 1 and not args.no_graph:
+            # streaming chunk: fixed shape, pre-allocated, the whole pipeline replayed as one CUDA graph
+            streamer = M.StreamingMatcher(lib, T, K, 0.0, batch=B, mode="screen", variant=variant)
+
+            def step(src):                                             # noqa: F811
+                return streamer(src)
         units_per_step = B * T
         n_local = hi - lo
         scaling = "strong"
@@ -296,6 +302,13 @@ def gpu_arm(args):
     ms_total = e0.elapsed_time(e1)
     launches = M.launch_count - launches0
     search_ms = [a.elapsed_time(b) for a, b in M.search_events]
+    if not search_ms:
+        # graph-replayed path: the kernel cannot be bracketed inside the graph, so time the same
+        # launches eagerly right after the timed region (same buffers, same clocks)
+        for _ in range(min(args.steps, 50)):
+            sharded.match(src_dev, K, 0.0)
+        torch.cuda.synchronize()
+        search_ms = [a.elapsed_time(b) for a, b in M.search_events]
     M.search_events = None
     if args.workload == "cfg2":
         lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
@@ -344,13 +357,17 @@ def gpu_arm(args):
                     "kernel": "knn_search_kernel", "avg_kernel_ms": avg_search_ms, "peak_source": peaks["source"]}
         else:
             achieved = flops_per_launch / (avg_search_ms * 1e-3) / 1e12
-            sustained = ms_total > 1000.0
-            peak = peaks["bf16_sustained"] if sustained else peaks["bf16_burst"]
+            # conservative denominator: the burst cuBLAS figure, even though the kernel runs
+            # back-to-back under the power cap (frac_of_sustained is reported beside it)
+            sustained = False
+            peak = peaks["bf16_burst"]
             roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None, "kernel": "knn_search_kernel",
-                    "avg_kernel_ms": avg_search_ms, "kernel_share_of_step": avg_search_ms * len(search_ms) / ms_total,
+                    "avg_kernel_ms": avg_search_ms,
+                    "kernel_share_of_step": avg_search_ms * (len(libs) if args.workload == "cfg5" else 1) / ms_per_step,
                     "peak_kind": "sustained" if sustained else "burst", "peak_source": peaks["source"],
-                    "frac_of_burst": achieved / peaks["bf16_burst"]}
+                    "frac_of_burst": achieved / peaks["bf16_burst"],
+                    "frac_of_sustained": achieved / peaks["bf16_sustained"]}
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = run_cpu_arm(args.workload, 3, 1)
@@ -390,6 +407,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="0 default, 1 = cta_group::1, 2 = CTA pair")
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="cfg2: do not use the CUDA-graph streaming matcher")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -157,6 +157,39 @@ int alive_knn_scatter_grad(const float* grad_out, const int64_t* top_idx, int32_
                            int32_t d, float scale, float* grad_rows, int64_t n,
                            alive_stream_t stream);
 
+/* A packed library as produced by alive_knn_pack (all device pointers). */
+typedef struct alive_knn_library {
+  const uint16_t* packed;   /* [n,d] bf16 */
+  const float* raw;         /* [n,d] f32  */
+  const float* norms;       /* [n]   f32  */
+  const uint32_t* stats;    /* [2]   u32  */
+  int64_t n;
+  int32_t d;
+  int64_t row_base;         /* global index of frame 0 (row-sharded libraries), else 0 */
+} alive_knn_library_t;
+
+/* One-call pipeline = module/common.py:96-109 for `batch` x `t` query frames against one
+ * packed library: pack queries -> search -> prune -> rescore -> exact scan of uncertified
+ * queries -> gather+mean+blend.  source[b*stride_b + i*stride_t + j*stride_d] (the
+ * reference's [B,D,T] layout: stride_b=D*T, stride_t=1, stride_d=T).
+ *   mode: 0 auto (exact scan when n < 1024 or k > 8), 1 screen, 2 exact scan
+ *   workspace: 256-byte aligned, at least offsets[11] bytes of alive_knn_match_layout
+ *   out [batch*t, d] f32 (NULL = skip the gather, e.g. for a sharded library),
+ *   top_idx [batch*t, k] int64 (global frame indices), top_score [batch*t, k] f32.
+ *   ev_search_start/stop: optional cudaEvent_t recorded around the alive_knn_search launch
+ *   (used by bench.py to time the dominant kernel inside the timed region), else NULL.
+ * Everything is enqueued on `stream`; no host synchronisation (CUDA-graph capturable).
+ * alive_knn_match_layout fills 12 byte offsets into the workspace:
+ *   0 q_raw 1 q_norm 2 q_packed 3 q_err 4 cand_score 5 cand_idx 6 sel_idx 7 sel_n
+ *   8 fb_list 9 fb_count 10 exact scratch 11 TOTAL bytes. */
+int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
+                           int32_t num_sms, int32_t variant, int64_t* offsets12_host);
+int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
+                    int64_t stride_d, const alive_knn_library_t* lib_host, int32_t k, float alpha,
+                    int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
+                    size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
+                    void* ev_search_start, void* ev_search_stop, alive_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,3 +251,35 @@ def test_dtype_passthrough_and_autograd_of_match_features():
     out.sum().backward()
     assert r.grad is None                                         # common.py:98 no_grad
     torch.testing.assert_close(s.grad, torch.full_like(s, 0.3))
+
+
+def test_streaming_matcher_graph_replay_equals_functional_api():
+    """realtime loop (realtime_inference.py:130-191): graph-replayed fixed-shape matcher"""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    ref = torch.randn(1, 768, 60_000, device="cuda", generator=g)
+    lib = A.pack_library(ref)
+    sm = A.StreamingMatcher(lib, T=24, k=4, alpha=0.0)
+    assert sm.graph is not None
+    for i in range(3):
+        chunk = torch.randn(1, 768, 24, device="cuda", generator=g)
+        out = sm(chunk).clone()
+        want, widx = A.match_features(chunk, ref, 4, 0.0, return_indices=True)
+        assert torch.equal(out, want) and torch.equal(sm.top_idx, widx)
+        assert tuple(out.shape) == (1, 768, 24)
+    sm2 = A.StreamingMatcher(lib, T=24, k=4, alpha=0.5, use_graph=False)
+    chunk = torch.randn(1, 768, 24, device="cuda", generator=g)
+    assert torch.equal(sm2(chunk), A.match_features(chunk, ref, 4, 0.5))
+
+
+def test_one_call_pipeline_equals_step_by_step_kernels():
+    """alive_knn_match == pack + search + prune + rescore + exact + gather called one by one"""
+    g = torch.Generator(device="cuda").manual_seed(22)
+    src = torch.randn(2, 768, 77, device="cuda", generator=g)
+    ref = torch.randn(1, 768, 30_000, device="cuda", generator=g)
+    lib = A.pack_library(ref)
+    out, idx, sc = M.run_match(src, lib, 4, 0.25, mode="screen")
+    q = M.pack_queries(src)
+    sc2, idx2 = M.search_topk(q, lib, 4, mode="screen")
+    out2 = torch.empty((2, 77, 768), device="cuda")
+    M.gather_mean(lib, idx2, q, 0.25, out2)
+    assert torch.equal(idx.view(-1, 4), idx2) and torch.equal(sc.view(-1, 4), sc2) and torch.equal(out, out2)
