@@ -1,0 +1,49 @@
+"""Run under torchrun on N GPUs: the row-sharded library (NCCL all-gather + merge +
+all-reduce of zero-padded rows) must give bit-identical results to the single-GPU path.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/gpu_sharded_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import alive_vc_b200 as A                         # noqa: E402
+from alive_vc_b200.sharded import ShardedLibrary  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for (B, T, N, k, alpha) in [(1, 500, 200_003, 4, 0.0), (2, 64, 50_000, 4, 0.25), (1, 33, 5, 4, 0.0),
+                                (1, 2000, 1_000_000, 4, 0.0)]:
+        g = torch.Generator(device=dev).manual_seed(123)
+        src = torch.randn(B, 768, T, device=dev, generator=g)
+        ref = torch.randn(1, 768, N, device=dev, generator=g)
+        lib = ShardedLibrary.from_full(ref, mode="auto")
+        out, idx = lib.match(src, k, alpha, return_indices=True)
+        want, widx = A.match_features(src, ref.expand(B, -1, -1), k, alpha, return_indices=True)
+        same = torch.equal(out, want) and torch.equal(idx, widx)
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"sharded x{dist.get_world_size()} B={B} T={T} N={N} k={k} alpha={alpha}: bit-identical={bool(flag.item())}",
+                  flush=True)
+        ok &= bool(flag.item())
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
