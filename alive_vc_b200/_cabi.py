@@ -27,6 +27,7 @@ EXPORTS = [
     "alive_knn_search", "alive_knn_prune", "alive_knn_rescore", "alive_knn_exact_workspace_bytes",
     "alive_knn_exact", "alive_knn_merge", "alive_knn_gather_mean", "alive_knn_gather_rows",
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
+    "alive_knn_finish",
 ]
 
 
@@ -111,7 +112,11 @@ def _declare(lib):
     lib.alive_knn_exact_workspace_bytes.restype = ctypes.c_size_t
     lib.alive_knn_exact_workspace_bytes.argtypes = [_i32, _i64, _i32]
     lib.alive_knn_exact.restype = ctypes.c_int
-    lib.alive_knn_exact.argtypes = [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]
+    lib.alive_knn_exact.argtypes = [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _f32,
+                                    _vp, _vp]
+    lib.alive_knn_finish.restype = ctypes.c_int
+    lib.alive_knn_finish.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64,
+                                     _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.alive_knn_merge.restype = ctypes.c_int
     lib.alive_knn_merge.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]
     lib.alive_knn_gather_mean.restype = ctypes.c_int

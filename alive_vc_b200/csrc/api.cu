@@ -123,24 +123,19 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
     rc = alive_knn_search(q_packed, lib->packed, &plan, cand_score, cand_idx, stream);
     if (rc) return rc;
     if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
-    rc = alive_knn_prune(cand_score, cand_idx, rows, plan.lists, k, q_err, q_norm, lib->stats, r_max, sel_idx, sel_n,
-                         fb_list, fb_count, stream);
-    if (rc) return rc;
-    rc = alive_knn_rescore(q_raw, q_norm, rows, lib->raw, lib->norms, d, sel_idx, sel_n, r_max, k, lib->row_base,
-                           top_score, top_idx, stream);
+    ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
+    rc = alive_knn_finish(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
+                          lib->stats, lib->n, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
+                          fb_count, stream);
     if (rc) return rc;
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, fb_list, fb_count, lib->row_base,
-                         exact_ws, top_score, top_idx, stream);
+                         exact_ws, top_score, top_idx, alpha, out, stream);
     if (rc) return rc;
   } else {
+    ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
     ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, 4, as_stream(stream)));
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
-                         exact_ws, top_score, top_idx, stream);
-    if (rc) return rc;
-  }
-  if (out) {
-    ALIVE_REQUIRE(lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
-    rc = alive_knn_gather_mean(lib->raw, lib->n, d, top_idx, rows, k, q_raw, alpha, out, stream);
+                         exact_ws, top_score, top_idx, alpha, out, stream);
     if (rc) return rc;
   }
   return 0;

@@ -27,20 +27,13 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// prune: one warp per query
+// prune (one warp per query): certificate + survivor compaction.  Returns the survivor count,
+// or -1 when the query must go to the exact scan.  `sel` may point to global or shared memory.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-prune_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
-             const float* __restrict__ q_err, const float* __restrict__ q_norm,
-             const unsigned int* __restrict__ lib_stats, int r_max, int* __restrict__ sel_idx,
-             int* __restrict__ sel_n, int* __restrict__ fb_list, int* __restrict__ fb_count) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (q >= t) return;
+__device__ __forceinline__ int prune_query(const float* __restrict__ sc, const int* __restrict__ ix, int lists,
+                                           int k, float qe, float qn, const unsigned int* __restrict__ lib_stats,
+                                           int r_max, int* sel, int lane) {
   const int entries = lists * kListLen;
-  const float* sc = cand_score + static_cast<size_t>(q) * entries;
-  const int* ix = cand_idx + static_cast<size_t>(q) * entries;
-
   // tau: upper bound on every screened score that any list dropped (= max of list minima;
   // a list that never filled has minimum -inf and dropped nothing)
   float tau = -INFINITY;
@@ -77,31 +70,37 @@ prune_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_
   }
 
   const float le = __uint_as_float(lib_stats[0]);
-  const float qe = q_err[q];
   const float eps = (le + qe + le * qe + kAccumSlack) * 1.00001f;
   const float cut = sk - 2.0f * eps - 1e-7f;
-  const float qn = q_norm[q];
-  bool fallback = lib_stats[1] != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > tau);
+  if (lib_stats[1] != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > tau)) return -1;
 
   int count = 0;
-  if (!fallback) {
-    for (int e0 = 0; e0 < entries; e0 += 32) {
-      const int e = e0 + lane;
-      const bool keep = e < entries && sc[e] >= cut && ix[e] >= 0;
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      const int pos = count + __popc(m & ((1u << lane) - 1u));
-      if (keep && pos < r_max) sel_idx[static_cast<size_t>(q) * r_max + pos] = ix[e];
-      count += __popc(m);
-    }
-    if (count > r_max || count < k) fallback = true;
+  for (int e0 = 0; e0 < entries; e0 += 32) {
+    const int e = e0 + lane;
+    const bool keep = e < entries && sc[e] >= cut && ix[e] >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int pos = count + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < r_max) sel[pos] = ix[e];
+    count += __popc(m);
   }
+  if (count > r_max || count < k) return -1;
+  return count;
+}
+
+__global__ void __launch_bounds__(256)
+prune_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
+             const float* __restrict__ q_err, const float* __restrict__ q_norm,
+             const unsigned int* __restrict__ lib_stats, int r_max, int* __restrict__ sel_idx,
+             int* __restrict__ sel_n, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= t) return;
+  const size_t entries = static_cast<size_t>(lists) * kListLen;
+  const int count = prune_query(cand_score + q * entries, cand_idx + q * entries, lists, k, q_err[q], q_norm[q],
+                                lib_stats, r_max, sel_idx + static_cast<size_t>(q) * r_max, lane);
   if (lane == 0) {
-    if (fallback) {
-      sel_n[q] = -1;
-      fb_list[atomicAdd(fb_count, 1)] = q;
-    } else {
-      sel_n[q] = count;
-    }
+    sel_n[q] = count;
+    if (count < 0) fb_list[atomicAdd(fb_count, 1)] = q;
   }
 }
 
@@ -206,6 +205,105 @@ rescore_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm
 }
 
 // ------------------------------------------------------------------------------------------
+// finish: prune + exact rescoring + top-k + (optional) gather-mean-blend, one CTA per query.
+// Replaces three launches (prune, rescore, gather) and the survivor list round trip.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float blend_exact(float acc, float kf, float a1, float q, float a0) {
+  return __fadd_rn(__fmul_rn(__fdiv_rn(acc, kf), a1), __fmul_rn(q, a0));
+}
+
+// out[j..j+3] = mean of the k raw rows (sequential fp32 sum, true division) blended with q
+__device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_raw, long long n, int d,
+                                                const long long* idx, long long idx_base, int k,
+                                                const float* __restrict__ q_row, float a1, float a0,
+                                                float* __restrict__ out_row, int tid, int nthreads) {
+  for (int j = tid * 4; j < d; j += nthreads * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < k; ++r) {
+      long long i = idx[r] - idx_base;
+      i = i < 0 ? 0 : (i >= n ? n - 1 : i);
+      const float4 v = *reinterpret_cast<const float4*>(lib_raw + static_cast<size_t>(i) * d + j);
+      if (r == 0) acc = v;
+      else acc = make_float4(__fadd_rn(acc.x, v.x), __fadd_rn(acc.y, v.y), __fadd_rn(acc.z, v.z), __fadd_rn(acc.w, v.w));
+    }
+    const float4 qv = *reinterpret_cast<const float4*>(q_row + j);
+    const float kf = static_cast<float>(k);
+    *reinterpret_cast<float4*>(out_row + j) =
+        make_float4(blend_exact(acc.x, kf, a1, qv.x, a0), blend_exact(acc.y, kf, a1, qv.y, a0),
+                    blend_exact(acc.z, kf, a1, qv.z, a0), blend_exact(acc.w, kf, a1, qv.w, a0));
+  }
+}
+
+constexpr int kFinishThreads = 256;
+constexpr int kFinishMaxStagedEntries = 6144;   // lists*8 entries staged in shared memory (48 KB) when they fit
+
+__global__ void __launch_bounds__(kFinishThreads)
+finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
+              const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
+              const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
+              const unsigned int* __restrict__ lib_stats, long long n, int d, int r_max, long long idx_base,
+              float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
+              long long* __restrict__ top_idx, int* __restrict__ sel_n, int* __restrict__ fb_list,
+              int* __restrict__ fb_count, int staged) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qh = reinterpret_cast<float*>(smem_raw);                         // [d]
+  long long* cid = reinterpret_cast<long long*>(qh + d);                  // [r_max]
+  float* csc = reinterpret_cast<float*>(cid + r_max);                     // [r_max]
+  int* sel = reinterpret_cast<int*>(csc + r_max);                         // [r_max]
+  float* st_sc = reinterpret_cast<float*>(sel + r_max);                   // [entries] (staged only)
+  int* st_ix = reinterpret_cast<int*>(st_sc + (staged ? lists * kListLen : 0));
+  __shared__ int s_count;
+  __shared__ long long s_top[kMaxK];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float qn = q_norm[q];
+  const size_t entries = static_cast<size_t>(lists) * kListLen;
+  const float* g_sc = cand_score + q * entries;
+  const int* g_ix = cand_idx + q * entries;
+  // stage the screened lists (coalesced) and normalise the query frame (x / |x|, IEEE division)
+  if (staged) {
+    for (int e = threadIdx.x * 4; e < static_cast<int>(entries); e += kFinishThreads * 4) {
+      *reinterpret_cast<float4*>(st_sc + e) = *reinterpret_cast<const float4*>(g_sc + e);
+      *reinterpret_cast<int4*>(st_ix + e) = *reinterpret_cast<const int4*>(g_ix + e);
+    }
+  }
+  for (int j = threadIdx.x; j < d; j += kFinishThreads)
+    qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
+  __syncthreads();
+  if (warp == 0) {
+    const int count = prune_query(staged ? st_sc : g_sc, staged ? st_ix : g_ix, lists, k, q_err[q], qn, lib_stats,
+                                  r_max, sel, lane);
+    if (lane == 0) {
+      s_count = count;
+      sel_n[q] = count;
+      if (count < 0) fb_list[atomicAdd(fb_count, 1)] = q;
+    }
+  }
+  __syncthreads();
+  const int n_sel = s_count;
+  if (n_sel < 0) return;   // the exact scan (and its gather) handle this query
+  for (int c = warp; c < n_sel; c += kFinishThreads / 32) {
+    const int idx = sel[c];
+    const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
+    if (lane == 0) {
+      csc[c] = static_cast<float>(acc);
+      cid[c] = idx;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    warp_select_topk(csc, cid, n_sel, k, top_score + static_cast<size_t>(q) * k, top_idx + static_cast<size_t>(q) * k,
+                     idx_base, lane);
+  }
+  if (out == nullptr) return;
+  __syncthreads();   // top_idx of this query was written by warp 0: stage it for the whole CTA
+  if (threadIdx.x < k) s_top[threadIdx.x] = top_idx[static_cast<size_t>(q) * k + threadIdx.x];
+  __syncthreads();
+  gather_mean_row(lib_raw, n, d, s_top, idx_base, k, q_raw + static_cast<size_t>(q) * d, a1, a0,
+                  out + static_cast<size_t>(q) * d, threadIdx.x, kFinishThreads);
+}
+
+// ------------------------------------------------------------------------------------------
 // exact scan: grid (query groups of 8, library splits); 8 warps per CTA
 // ------------------------------------------------------------------------------------------
 constexpr int kQB = 8;
@@ -300,14 +398,23 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
 __global__ void __launch_bounds__(128)
 exact_final_kernel(int t, int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
                    const float* __restrict__ part_score, const long long* __restrict__ part_idx,
-                   long long idx_base, float* __restrict__ top_score, long long* __restrict__ top_idx) {
+                   long long idx_base, float* __restrict__ top_score, long long* __restrict__ top_idx,
+                   const float* __restrict__ lib_raw, long long n, int d, const float* __restrict__ q_raw,
+                   float a1, float a0, float* __restrict__ out) {
   const int nq = q_count ? *q_count : t;
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (slot >= nq) return;
+  const int lane = threadIdx.x & 31;
   const int q = q_list ? q_list[slot] : slot;
   const size_t o = static_cast<size_t>(slot) * splits * k;
   warp_select_topk(part_score + o, part_idx + o, splits * k, k, top_score + static_cast<size_t>(q) * k,
-                   top_idx + static_cast<size_t>(q) * k, idx_base, threadIdx.x & 31);
+                   top_idx + static_cast<size_t>(q) * k, idx_base, lane);
+  if (out == nullptr) return;
+  __syncwarp();
+  __threadfence_block();
+  // the warp that selected the top-k of this query also gathers it (top_idx written by lane 0)
+  gather_mean_row(lib_raw, n, d, top_idx + static_cast<size_t>(q) * k, idx_base, k, q_raw + static_cast<size_t>(q) * d,
+                  a1, a0, out + static_cast<size_t>(q) * d, lane, 32);
 }
 
 __global__ void __launch_bounds__(128)
@@ -387,7 +494,7 @@ extern "C" size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t 
 extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t, const float* lib_raw,
                                const float* lib_norm, int64_t n, int32_t d, int32_t k, const int32_t* q_list,
                                const int32_t* q_count, int64_t idx_base, void* workspace, float* top_score,
-                               int64_t* top_idx, alive_stream_t stream) {
+                               int64_t* top_idx, float alpha, float* out, alive_stream_t stream) {
   using namespace alive;
   ALIVE_REQUIRE(q_raw && q_norm && lib_raw && lib_norm && workspace && top_score && top_idx,
                 "alive_knn_exact: NULL argument");
@@ -417,8 +524,12 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
   exact_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, n, d, k, q_list,
                                                               q_count, splits, static_cast<int>(region0), part_score, part_idx);
   ALIVE_CHECK_CUDA(cudaGetLastError());
+  ALIVE_REQUIRE(out == nullptr || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && idx_base == 0),
+                "alive_knn_exact: gather needs a 16-byte aligned `out` and an unsharded library");
+  const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
   exact_final_kernel<<<(t + 3) / 4, 128, 0, as_stream(stream)>>>(t, k, q_list, q_count, splits, part_score, part_idx,
-                                                                 idx_base, top_score, reinterpret_cast<long long*>(top_idx));
+                                                                 idx_base, top_score, reinterpret_cast<long long*>(top_idx),
+                                                                 lib_raw, n, d, q_raw, a1, alpha, out);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -433,6 +544,41 @@ extern "C" int alive_knn_merge(const float* scores, const int64_t* idx, int32_t 
   ALIVE_REQUIRE(smem <= 48 * 1024, "alive_knn_merge: ranks*k too large");
   merge_kernel<<<(t + 3) / 4, 128, smem, as_stream(stream)>>>(scores, reinterpret_cast<const long long*>(idx), ranks, t, k,
                                                               top_score, reinterpret_cast<long long*>(top_idx));
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
+                                const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
+                                const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
+                                int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx,
+                                int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(cand_score && cand_idx && q_raw && q_norm && q_err && lib_raw && lib_norm && lib_stats && top_score &&
+                    top_idx && sel_n && fb_list && fb_count,
+                "alive_knn_finish: NULL argument");
+  ALIVE_REQUIRE(t >= 1 && lists >= 1, "alive_knn_finish: bad sizes");
+  ALIVE_REQUIRE(k >= 1 && k <= kListLen, "alive_knn_finish: k must be in [1,%d] for the screened path (got %d)", kListLen, k);
+  ALIVE_REQUIRE(r_max >= k && r_max <= kMaxRMax, "alive_knn_finish: r_max must be in [k,%d]", kMaxRMax);
+  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 8192, "alive_knn_finish: d must be a multiple of 4");
+  ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "alive_knn_finish: raw/out buffers must be 16-byte aligned");
+  ALIVE_REQUIRE(out == nullptr || idx_base == 0, "alive_knn_finish: gather needs an unsharded library");
+  ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), as_stream(stream)));
+  const int entries = lists * kListLen;
+  const int staged = entries <= kFinishMaxStagedEntries ? 1 : 0;
+  const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
+                      (staged ? static_cast<size_t>(entries) * 8 : 0);
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
+  const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
+  finish_kernel<<<t, kFinishThreads, smem, as_stream(stream)>>>(
+      cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1,
+      alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -130,6 +130,46 @@ def pack_library(reference: torch.Tensor) -> PackedFrames:
 
 
 # ---------------------------------------------------------------------------------------
+# library lifecycle: the packed layout stored next to the legacy pickle
+# ---------------------------------------------------------------------------------------
+PACKED_FORMAT_VERSION = 1
+
+
+def save_packed_library(lib: PackedFrames, path: str, include_legacy_tokens: bool = True):
+    """torch.save the packed library.  With `include_legacy_tokens` the file also carries the
+    reference's own checkpoint key `tokens` ([1, D, N] float32, generate_voice_library.py:42 /
+    module/voice_library.py:9), so `VoiceLibrary(num_tokens=N).load_state_dict(..., strict=False)`
+    of the REFERENCE still reads it."""
+    blob = {
+        "alive_knn_packed_version": PACKED_FORMAT_VERSION,
+        "n": lib.n, "d": lib.d, "row_base": lib.row_base,
+        "raw": lib.raw.cpu(), "norms": lib.norms.cpu(), "packed": lib.packed.cpu(), "err": lib.err.cpu(),
+        "stats": lib.stats.cpu(),
+    }
+    if include_legacy_tokens:
+        blob["tokens"] = lib.raw.t().unsqueeze(0).contiguous().cpu()
+    torch.save(blob, path)
+
+
+def load_packed_library(path: str, device="cuda") -> PackedFrames:
+    """Inverse of save_packed_library.  A legacy reference checkpoint ({"tokens": [1,D,N]}) is
+    accepted too and packed on the fly (K1)."""
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("alive_vc_b200: packed libraries live on a CUDA device (no CPU path)")
+    if "alive_knn_packed_version" not in blob:
+        if "tokens" not in blob:
+            raise RuntimeError(f"{path}: neither a packed library nor a reference voice-library checkpoint")
+        return pack_library(blob["tokens"].to(dev))
+    if blob["alive_knn_packed_version"] != PACKED_FORMAT_VERSION:
+        raise RuntimeError(f"{path}: unsupported packed format version {blob['alive_knn_packed_version']}")
+    return PackedFrames(n=int(blob["n"]), d=int(blob["d"]), raw=blob["raw"].to(dev), norms=blob["norms"].to(dev),
+                        packed=blob["packed"].to(dev), err=blob["err"].to(dev), stats=blob["stats"].to(dev),
+                        row_base=int(blob["row_base"]))
+
+
+# ---------------------------------------------------------------------------------------
 # pack cache: invisible to callers, keyed on the tensor OBJECT and validated against its
 # storage pointer / version counter / geometry (SURVEY §8(b) "Ownership")
 # ---------------------------------------------------------------------------------------
@@ -224,7 +264,8 @@ def exact_topk(q: PackedFrames, lib: PackedFrames, k: int, top_score=None, top_i
                            lib.n, lib.d, k,
                            q_list.data_ptr() if q_list is not None else None,
                            q_count.data_ptr() if q_count is not None else None,
-                           lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), _stream_ptr())
+                           lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), 0.0, None,
+                           _stream_ptr())
     _cabi.check(rc, "alive_knn_exact")
     _count(2)
     return top_score, top_idx
@@ -365,11 +406,11 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
                            ev0.cuda_event if ev0 is not None else None,
                            ev1.cuda_event if ev1 is not None else None, _stream_ptr())
     _cabi.check(rc, "alive_knn_match")
-    _count(B + (5 if m == 1 else 2) + (1 if want_out else 0))
+    _count(B + (4 if m == 1 else 2))
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
                            fb_count=workspace[off[9]:off[9] + 4].view(torch.int32),
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
-                           launches=B + (5 if m == 1 else 2) + (1 if want_out else 0))
+                           launches=B + (4 if m == 1 else 2))
     last_info._workspace = workspace
     return (out if want_out else None), top_idx, top_score
 
@@ -426,7 +467,7 @@ class StreamingMatcher:
         self.src.copy_(source, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
-            _count(self.src.shape[0] + 6)
+            _count(self.src.shape[0] + 4)
         else:
             self._run()
         return self.out.transpose(1, 2)

@@ -159,8 +159,8 @@ def reference_arm(args):
     if rank != 0:
         return
     B, T, N, desc = WORKLOADS[args.workload]
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 100))      # each step is a bounded sample (about 1 s of CPU work)
+    warmup = max(1, min(args.warmup, 10))
     cb = run_cpu_arm(args.workload, steps, warmup)
     line = {
         "impl": "reference", "metric": "query_frames_per_sec_matched_k4", "value": cb["value"],

@@ -116,15 +116,27 @@ int alive_knn_rescore(const float* q_raw, const float* q_norm, int32_t t,
                       const int32_t* sel_idx, const int32_t* sel_n, int32_t r_max, int32_t k,
                       int64_t idx_base, float* top_score, int64_t* top_idx, alive_stream_t stream);
 
+/* K2b+K3+K4 fused, one CTA per query: alive_knn_prune + alive_knn_rescore (+ the
+ * gather+mean+blend of alive_knn_gather_mean when out != NULL) in one launch.  Uncertified
+ * queries are appended to fb_list (sel_n = -1) and left to alive_knn_exact. */
+int alive_knn_finish(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
+                     const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
+                     const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
+                     int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx,
+                     int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, alive_stream_t stream);
+
 /* Exact scan (no screen): common.py:102-105 for the queries listed in
  * q_list[0..*q_count) (both device; NULL/NULL = all t queries) against all n
  * frames, same arithmetic and tie rule as alive_knn_rescore; NaN similarities
- * rank first like torch.topk.  workspace: alive_knn_exact_workspace_bytes(). */
+ * rank first like torch.topk.  workspace: alive_knn_exact_workspace_bytes().
+ * out (nullable, [t,d] f32): when given, the scanned queries are also gathered
+ * (common.py:107-109, same arithmetic as alive_knn_gather_mean with `alpha`). */
 size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k);
 int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t,
                     const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, int32_t k,
                     const int32_t* q_list, const int32_t* q_count, int64_t idx_base,
-                    void* workspace, float* top_score, int64_t* top_idx, alive_stream_t stream);
+                    void* workspace, float* top_score, int64_t* top_idx, float alpha, float* out,
+                    alive_stream_t stream);
 
 /* Multi-GPU merge: after an all-gather of every rank's exact local top-k,
  * scores/idx are [ranks,t,k]; writes the global top-k (score desc, frame asc). */

@@ -283,3 +283,29 @@ def test_one_call_pipeline_equals_step_by_step_kernels():
     out2 = torch.empty((2, 77, 768), device="cuda")
     M.gather_mean(lib, idx2, q, 0.25, out2)
     assert torch.equal(idx.view(-1, 4), idx2) and torch.equal(sc.view(-1, 4), sc2) and torch.equal(out, out2)
+
+
+def test_packed_library_save_load_roundtrip(tmp_path):
+    """library lifecycle (generate_voice_library.py:42 / inference.py:78-82): the packed layout is
+    stored next to the legacy `tokens` key; a reference-format checkpoint loads (and is packed) too"""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    ref = torch.randn(1, 768, 5000, device="cuda", generator=g)
+    src = torch.randn(1, 768, 40, device="cuda", generator=g)
+    lib = A.pack_library(ref)
+    p = str(tmp_path / "voice_library_packed.pt")
+    A.save_packed_library(lib, p)
+    lib2 = A.load_packed_library(p)
+    for a, b in ((lib.raw, lib2.raw), (lib.norms, lib2.norms), (lib.packed, lib2.packed), (lib.stats, lib2.stats)):
+        assert torch.equal(a, b)
+    want = A.match_features(src, ref)
+    out, _, _ = A.match_packed(src, lib2)
+    assert torch.equal(out.transpose(1, 2), want)
+    blob = torch.load(p, weights_only=True)
+    assert torch.equal(blob["tokens"], ref.cpu())                 # the reference's own key, [1,768,N]
+    legacy = str(tmp_path / "voice_library.pt")
+    vl = A.VoiceLibrary(num_tokens=5000)
+    with torch.no_grad():
+        vl.tokens.copy_(ref.cpu())
+    torch.save(vl.state_dict(), legacy)                           # what generate_voice_library.py:42 writes
+    lib3 = A.load_packed_library(legacy)
+    assert torch.equal(lib3.packed, lib.packed) and torch.equal(lib3.raw, lib.raw)
