@@ -127,6 +127,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// one lane of the (converged) warp; lets ptxas keep descriptors/addresses in uniform registers and
+// issue UTMALDG / UTCHMMA / UTCBAR directly instead of wrapping each one in an ELECT+BRA.U.ANY loop
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
 }
@@ -352,7 +363,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // the whole warp walks the loop (warp-uniform control flow), one elected lane issues
+    {
       const uint32_t full0 = (kCtas == 1) ? bar_full : map_to_cta(bar_full, 0);   // barrier lives in the leader
       uint32_t it = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
@@ -367,17 +379,20 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t stage = it % kStages;
             const uint32_t phase = (it / kStages) & 1u;
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            if (leader) mbar_expect_tx(bar_full + 8 * stage, C::kTxBytes);
-            tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row);
-            tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row);
+            if (elect_one_sync()) {
+              if (leader) mbar_expect_tx(bar_full + 8 * stage, C::kTxBytes);
+              tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row);
+              tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row);
+            }
+            __syncwarp();
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (leader && lane == 0) {
+    // leader CTA only; warp-uniform loop, one elected lane issues the tcgen05 instructions
+    if (leader) {
       constexpr uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN);
       uint32_t it = 0, tile_count = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
@@ -395,20 +410,22 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t phase = (it / kStages) & 1u;
             mbar_wait(bar_full + 8 * stage, phase);
             tcgen05_fence_after();
-            const uint64_t adesc = make_smem_desc(smem_a + stage * kABytes);
-            const uint64_t bdesc = make_smem_desc(smem_b + stage * C::kBBytes);
+            if (elect_one_sync()) {
+              const uint64_t adesc = make_smem_desc(smem_a + stage * kABytes);
+              const uint64_t bdesc = make_smem_desc(smem_b + stage * C::kBBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-              umma_bf16<kCtas>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                umma_bf16<kCtas>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit<kCtas>(bar_empty + 8 * stage);   // smem slot reusable once these MMAs retire
+              if (kb == p.k_blocks - 1) umma_commit<kCtas>(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
             }
-            umma_commit<kCtas>(bar_empty + 8 * stage);   // smem slot reusable once these MMAs retire
+            __syncwarp();
           }
-          umma_commit<kCtas>(bar_tfull + 8 * acc);       // accumulator complete -> epilogue
         }
       }
     }
-    __syncwarp();
   } else if (warp >= kFirstEpiWarp) {
     // ======================================= epilogue =======================================
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
@@ -588,7 +605,10 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
   ALIVE_REQUIRE(n >= 1 && n < (1ll << 31) - 512, "alive_knn_plan: n out of range (%lld)", static_cast<long long>(n));
   ALIVE_REQUIRE(d >= 64 && d % 64 == 0 && d <= 8192, "alive_knn_plan: d must be a multiple of 64 (got %d)", d);
   ALIVE_REQUIRE(num_sms >= 2, "alive_knn_plan: num_sms must be >= 2");
-  if (variant == 0) variant = 1;
+  // default: the CTA-pair kernel (cta_group::2) once there is more than one 128-query tile - it
+  // moves a third less operand data per flop and is ~10% faster under the power cap; a single
+  // tile (streaming chunks) runs on one CTA per unit
+  if (variant == 0) variant = (t > kBlockM) ? 2 : 1;
   ALIVE_REQUIRE(variant == 1 || variant == 2, "alive_knn_plan: variant must be 0, 1 or 2");
   const int ctas = variant;
   const int slots = num_sms / ctas;   // units that run concurrently

@@ -309,3 +309,52 @@ def test_packed_library_save_load_roundtrip(tmp_path):
     torch.save(vl.state_dict(), legacy)                           # what generate_voice_library.py:42 writes
     lib3 = A.load_packed_library(legacy)
     assert torch.equal(lib3.packed, lib.packed) and torch.equal(lib3.raw, lib.raw)
+
+
+def test_planted_neighbours_at_large_n():
+    """size-independent property at a BASELINE-scale library (N = 2M frames, T = 4096): for every
+    query four noisy copies with strictly decreasing similarity are planted at random library
+    positions; the match must return exactly those positions in that order, and the features
+    must be the sequential mean of those raw rows."""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(77)
+    N, T, D = 2_000_000, 4096, 768
+    lib = M.alloc_packed(N, D, dev)
+    src = torch.randn(1, D, T, device=dev, generator=g)
+    pos = torch.randperm(N, device=dev, generator=g)[: 4 * T].view(T, 4)
+    raw_rows = torch.empty((T, 4, D), device=dev)
+    for c0 in range(0, N, 250_000):
+        c1 = min(N, c0 + 250_000)
+        x = torch.randn(D, c1 - c0, device=dev, generator=g)
+        # plant: copy j of query t = q_t * scale_j + noise_j  (noise grows with j -> similarity drops)
+        inside = (pos >= c0) & (pos < c1)
+        tt, jj = inside.nonzero(as_tuple=True)
+        if tt.numel():
+            noise = torch.randn(D, tt.numel(), device=dev, generator=g) * (0.05 + 0.1 * jj.float())[None, :]
+            planted = src[0][:, tt] * (1.0 + 0.5 * jj.float())[None, :] + noise
+            x[:, pos[tt, jj] - c0] = planted
+            raw_rows[tt, jj] = planted.t()
+        M.pack_into(lib, c0, x)
+        del x
+    out, idx, score = A.match_packed(src, lib, 4, 0.0)
+    assert M.last_info.mode == "screen" and M.last_info.fallback_queries() == 0
+    assert torch.equal(idx[0], pos), "planted neighbours not recovered exactly"
+    assert (score[0, :, :-1] > score[0, :, 1:]).all()
+    want = ((raw_rows[:, 0] + raw_rows[:, 1]) + raw_rows[:, 2] + raw_rows[:, 3]) / 4.0
+    assert torch.equal(out[0], want)
+    # sharded-by-rows view of the same library gives the same answer (2 shards on one device)
+    half = N // 2
+    tops = []
+    for lo, hi in ((0, half), (half, N)):
+        shard = M.PackedFrames(n=hi - lo, d=D, raw=lib.raw[lo:hi], norms=lib.norms[lo:hi], packed=lib.packed[lo:hi],
+                               err=lib.err[lo:hi], stats=lib.stats, row_base=lo)
+        _, i, s = M.run_match(src, shard, 4, 0.0, want_out=False)
+        tops.append((s.view(T, 4), i.view(T, 4)))
+    sc = torch.stack([t[0] for t in tops]).contiguous()
+    ix = torch.stack([t[1] for t in tops]).contiguous()
+    top_s = torch.empty((T, 4), device=dev)
+    top_i = torch.empty((T, 4), dtype=torch.int64, device=dev)
+    rc = _cabi.load().alive_knn_merge(sc.data_ptr(), ix.data_ptr(), 2, T, 4, top_s.data_ptr(), top_i.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "merge")
+    assert torch.equal(top_i, pos) and torch.equal(top_s, score[0])
