@@ -82,6 +82,8 @@ class CudaShardBackend:
 
     def gather_rows(self, top_idx):
         t, k = top_idx.shape
+        if self.local.n == 0:      # a shard without frames contributes zeros
+            return torch.zeros((t, k, self.local.d), dtype=torch.float32, device=top_idx.device)
         rows = torch.empty((t, k, self.local.d), dtype=torch.float32, device=top_idx.device)
         rc = _cabi.load().alive_knn_gather_rows(self.local.raw.data_ptr(), self.local.n, self.local.d,
                                                 self.local.row_base, top_idx.data_ptr(), t, k, rows.data_ptr(),
@@ -90,15 +92,18 @@ class CudaShardBackend:
         M._count(1)
         return rows
 
-    def mean_blend(self, rows, q, alpha):
+    def mean_blend(self, rows, q, alpha, row0=0, out=None):
+        """mean + blend of rows [t,k,d] for query rows [row0, row0+t) -> out [t,d]"""
         t, k, d = rows.shape
         if q.raw is None:       # this shard held no frames, so alive_knn_match never packed the queries
             q.raw = M.pack_queries(q.source).raw
-        out = torch.empty((t, d), dtype=torch.float32, device=rows.device)
-        rc = _cabi.load().alive_knn_mean_blend(rows.data_ptr(), t, k, d, q.raw.data_ptr(), float(alpha),
-                                               out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        _cabi.check(rc, "alive_knn_mean_blend")
-        M._count(1)
+        if out is None:
+            out = torch.empty((t, d), dtype=torch.float32, device=rows.device)
+        if t > 0:
+            rc = _cabi.load().alive_knn_mean_blend(rows.data_ptr(), t, k, d, q.raw[row0:].data_ptr(), float(alpha),
+                                                   out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            _cabi.check(rc, "alive_knn_mean_blend")
+            M._count(1)
         return out
 
 
@@ -120,6 +125,13 @@ class ShardedLibrary:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def _reduce_scatter_ok(self) -> bool:
+        """reduce_scatter_tensor exists on NCCL; gloo (CPU tests) keeps the all-reduce form."""
+        try:
+            return dist.get_backend(self.group) == "nccl"
+        except Exception:
+            return False
 
     @classmethod
     def from_local_frames(cls, frames_dn: torch.Tensor, row_base: int, n_total: int, group=None,
@@ -174,12 +186,30 @@ class ShardedLibrary:
             dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
             # 3. merge
             top_s, top_i = be.merge(all_s.view(self.world, t, k), all_i.view(self.world, t, k), k)
-        # 4. owned rows, zeros elsewhere;  5. exact sum over ranks
+        # 4. owned rows, zeros elsewhere;  5. exact sum over ranks;  6. mean + blend
         rows = be.gather_rows(top_i)
-        if self.world > 1:
-            dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=self.group)
-        # 6. mean + blend
-        out = be.mean_blend(rows, q, alpha).view(B, T, D).transpose(1, 2)
+        if self.world > 1 and self._reduce_scatter_ok():
+            # NCCL: reduce-scatter the zero-padded rows over the QUERY axis (half the traffic of an
+            # all-reduce), finish T/R queries per rank, all-gather the [T, D] result
+            R = self.world
+            per = (t + R - 1) // R
+            if per * R != t:
+                rows = torch.cat([rows, rows.new_zeros((per * R - t, k, D))], 0)
+            mine = torch.empty((per, k, D), dtype=torch.float32, device=dev)
+            dist.reduce_scatter_tensor(mine, rows, op=dist.ReduceOp.SUM, group=self.group)
+            row0 = self.rank * per
+            valid = max(0, min(per, t - row0))
+            out_slice = torch.zeros((per, D), dtype=torch.float32, device=dev) if valid < per else \
+                torch.empty((per, D), dtype=torch.float32, device=dev)
+            be.mean_blend(mine[:valid], q, alpha, row0=row0, out=out_slice)
+            out_full = torch.empty((per * R, D), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(out_full, out_slice, group=self.group)
+            out_rows = out_full[:t]
+        else:
+            if self.world > 1:
+                dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=self.group)
+            out_rows = be.mean_blend(rows, q, alpha)
+        out = out_rows.view(B, T, D).transpose(1, 2)
         if out.dtype != source.dtype:
             out = out.to(source.dtype)
         if return_indices:

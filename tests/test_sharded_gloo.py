@@ -54,7 +54,7 @@ class OracleBackend:
         rows[own] = self.ref.T[loc[own]]
         return torch.from_numpy(rows)
 
-    def mean_blend(self, rows, q, alpha):
+    def mean_blend(self, rows, q, alpha, row0=0, out=None):
         r = rows.numpy()
         acc = r[:, 0].copy()
         for j in range(1, r.shape[1]):
@@ -99,6 +99,7 @@ def _free_port():
     (2, 1001, 37, 4, 0.0, 1),
     (2, 300, 16, 4, 0.25, 2),
     (3, 10, 5, 4, 0.0, 1),        # shards of 4/3/3 frames: some ranks hold fewer than k frames
+    (3, 2, 4, 2, 0.5, 1),         # shards of 1/1/0 frames: one rank holds nothing
 ])
 def test_sharded_match_equals_single_library(world, n_total, T, k, alpha, B):
     mp.spawn(_worker, args=(world, _free_port(), n_total, T, k, alpha, B), nprocs=world, join=True)
