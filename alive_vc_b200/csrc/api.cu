@@ -32,7 +32,8 @@ constexpr int kOffQRaw = 0, kOffQNorm = 1, kOffQPacked = 2, kOffQErr = 3, kOffCa
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 int resolve_mode(int mode, int64_t n, int d, int k) {
-  if (mode == 0) return (k > ALIVE_KNN_LIST_LEN || n < 1024 || d % 64 != 0) ? 2 : 1;
+  (void)n;   // the screen handles any library size; the exact scan is for k > 8 or odd feature dims
+  if (mode == 0) return (k > ALIVE_KNN_LIST_LEN || d % 64 != 0) ? 2 : 1;
   return mode;
 }
 

@@ -351,10 +351,36 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
   for (long long r = r0 + warp; r < r1; r += 8) {
     const float* row = lib_raw + static_cast<size_t>(r) * d;
     const float nrm = lib_norm[r];
+    // normalise the frame once (x / |x|, IEEE division), then one fp64 dot per query
+    constexpr int kMaxVec = 12;                       // d <= 1536 -> at most 12 float4 per lane
+    float4 rn[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int j = lane * 4 + i * 128;
+      if (j < d) {
+        const float4 v = *reinterpret_cast<const float4*>(row + j);
+        rn[i] = make_float4(__fdiv_rn(v.x, nrm), __fdiv_rn(v.y, nrm), __fdiv_rn(v.z, nrm), __fdiv_rn(v.w, nrm));
+      } else {
+        rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float mine = 0.f;
 #pragma unroll
     for (int qi = 0; qi < kQB; ++qi) {
-      const double acc = dot_norm_f64(qh + qi * d, row, nrm, d, lane);
+      const float* qv = qh + qi * d;
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i) {
+        const int j = lane * 4 + i * 128;
+        if (j < d) {
+          const float4 a = *reinterpret_cast<const float4*>(qv + j);
+          acc += static_cast<double>(a.x) * static_cast<double>(rn[i].x);
+          acc += static_cast<double>(a.y) * static_cast<double>(rn[i].y);
+          acc += static_cast<double>(a.z) * static_cast<double>(rn[i].z);
+          acc += static_cast<double>(a.w) * static_cast<double>(rn[i].w);
+        }
+      }
+      acc = warp_sum_f64(acc);
       if (lane == qi) mine = static_cast<float>(acc);
     }
     if (lane < kQB && qids[lane] >= 0) {
@@ -436,7 +462,14 @@ merge_kernel(const float* __restrict__ scores, const long long* __restrict__ idx
 }
 
 int exact_splits(int t, long long n, int k) {
-  long long s = (n + 8191) / 8192;
+  // enough (query group, split) CTAs to fill the GPU, at least 256 frames per split
+  const long long groups = (static_cast<long long>(t) + kQB - 1) / kQB;
+  long long s = (2 * 148 + groups - 1) / groups;
+  // long libraries are always split (a handful of uncertified queries must not serialise on one CTA)
+  const long long s_long = (n + 8191) / 8192;
+  if (s < s_long) s = s_long;
+  const long long s_max = (n + 255) / 256;
+  if (s > s_max) s = s_max;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
   while (s > 1 && static_cast<long long>(t) * s * k * 12 > (256ll << 20)) s /= 2;

@@ -47,6 +47,10 @@ WORKLOADS = {
 }
 
 
+# cfg2 is a latency config: SURVEY §8(d) asks for >= 1000 timed calls
+DEFAULT_STEPS = {"cfg1": 50, "cfg2": 1000, "cfg3": 5, "cfg4": 5, "cfg5": 3}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -152,6 +156,35 @@ def run_cpu_arm(workload: str, steps: int, warmup: int):
     qps = t_s / mean * scale
     return {"value": qps, "unit": "query_frames/s", "cores": cores, "kind": "port",
             "sample": what, "sample_seconds_per_step": mean, "steps": len(times)}
+
+
+def run_torch_eager_gpu(workload: str, dev):
+    """Secondary line: the reference's own torch ops (norm, div, bmm, topk, gather,
+    mean = oracle port of common.py:96-109) run eagerly on the same B200 - i.e. what `-d cuda` gives
+    a user of the reference today.  Same bounded samples as the CPU arm (the [T,N] fp32 score
+    matrix of the full cfg3/cfg4/cfg5 shapes does not fit)."""
+    import torch
+    from oracle.knn_oracle import match_features_torch
+
+    t_s, n_s, scale, what = cpu_sample_shape(workload)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    src = torch.randn(1, D, t_s, device=dev, generator=g)
+    ref = torch.randn(1, D, n_s, device=dev, generator=g)
+    for _ in range(3):
+        match_features_torch(src, ref, K, 0.0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        match_features_torch(src, ref, K, 0.0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del src, ref
+    torch.cuda.empty_cache()
+    return {"value": t_s / (ms * 1e-3) * scale, "unit": "query_frames/s", "ms_per_call": ms, "sample": what,
+            "note": "torch eager fp32 (cuBLAS sgemm, TF32 off) incl. per-call library normalisation"}
 
 
 def reference_arm(args):
@@ -268,7 +301,7 @@ def gpu_arm(args):
         units_per_step = B * T
         n_local = hi - lo
         scaling = "strong"
-        parallelism = f"library rows sharded x{world}" + (", all-gather top-k + all-reduce rows" if world > 1 else "")
+        parallelism = f"library rows sharded x{world}" + (", all-gather top-k + reduce-scatter rows + all-gather result" if world > 1 else "")
     src_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
     src_host.copy_(src_dev)
     out_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
@@ -371,6 +404,9 @@ def gpu_arm(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = run_cpu_arm(args.workload, 3, 1)
+        eager = None
+        if world == 1 and args.torch_eager:
+            eager = run_torch_eager_gpu(args.workload, dev)
         line = {
             "metric": "query_frames_per_sec_matched_k4", "value": value, "unit": "query_frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -388,6 +424,8 @@ def gpu_arm(args):
             "roofline": roof,
             "cpu_baseline": cpu,
         }
+        if eager is not None:
+            line["torch_eager_gpu"] = eager
         if lat:
             line["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                                   "min": lat[0]}
@@ -400,7 +438,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: per workload, see DEFAULT_STEPS)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
@@ -408,7 +446,11 @@ def main():
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="cfg2: do not use the CUDA-graph streaming matcher")
+    ap.add_argument("--torch-eager", action="store_true",
+                    help="also time the reference's torch ops on the GPU (secondary line, where it fits)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = DEFAULT_STEPS[args.workload]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -184,7 +184,7 @@ typedef struct alive_knn_library {
  * packed library: pack queries -> search -> prune -> rescore -> exact scan of uncertified
  * queries -> gather+mean+blend.  source[b*stride_b + i*stride_t + j*stride_d] (the
  * reference's [B,D,T] layout: stride_b=D*T, stride_t=1, stride_d=T).
- *   mode: 0 auto (exact scan when n < 1024 or k > 8), 1 screen, 2 exact scan
+ *   mode: 0 auto (screen; exact scan when k > 8 or d % 64 != 0), 1 screen, 2 exact scan
  *   workspace: 256-byte aligned, at least offsets[11] bytes of alive_knn_match_layout
  *   out [batch*t, d] f32 (NULL = skip the gather, e.g. for a sharded library),
  *   top_idx [batch*t, k] int64 (global frame indices), top_score [batch*t, k] f32.

@@ -330,8 +330,10 @@ def test_planted_neighbours_at_large_n():
         inside = (pos >= c0) & (pos < c1)
         tt, jj = inside.nonzero(as_tuple=True)
         if tt.numel():
-            noise = torch.randn(D, tt.numel(), device=dev, generator=g) * (0.05 + 0.1 * jj.float())[None, :]
-            planted = src[0][:, tt] * (1.0 + 0.5 * jj.float())[None, :] + noise
+            # relative noise 0.05 / 0.15 / 0.3 / 0.5 -> cosines ~0.999 / 0.989 / 0.958 / 0.894 (> 10 sigma apart)
+            rel = torch.tensor([0.05, 0.15, 0.3, 0.5], device=dev)[jj]
+            noise = torch.randn(D, tt.numel(), device=dev, generator=g) * rel[None, :]
+            planted = (src[0][:, tt] + noise) * (1.0 + 0.5 * jj.float())[None, :]
             x[:, pos[tt, jj] - c0] = planted
             raw_rows[tt, jj] = planted.t()
         M.pack_into(lib, c0, x)

@@ -67,6 +67,24 @@ def main():
                                     str(T), str(N)], cwd=ROOT)
     elif what == "one":
         one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif what == "pipeline":
+        # the whole one-call pipeline a few times (for an ncu launch list / per-kernel breakdown)
+        import torch
+        import bench
+        from alive_vc_b200 import matching as M
+        T, N = int(sys.argv[2]), int(sys.argv[3])
+        lib = bench.build_library(0, N, 7, torch.device("cuda", 0))
+        src = torch.randn(1, 768, T, device="cuda")
+        for _ in range(3):
+            M.run_match(src, lib, 4, 0.0, mode="screen")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            M.run_match(src, lib, 4, 0.0, mode="screen")
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"pipeline T={T} N={N}: {e0.elapsed_time(e1) / 5:.3f} ms per call")
     elif what == "prof":
         import torch
         variant = int(sys.argv[2])
