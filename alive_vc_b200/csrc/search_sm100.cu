@@ -69,6 +69,8 @@ struct SearchParams {
   float* cand_score;
   int* cand_idx;
   int debug;           // diagnostics only: 1 = epilogue skips the scan, 2 = also skips the TMEM loads
+  unsigned long long hint_q;     // L2 eviction policy of the query-tile loads
+  unsigned long long hint_lib;   // L2 eviction policy of the library-tile loads
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -99,7 +101,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // arrive on a barrier given by a shared::cluster address (own or peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default (.release.cta) semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): what is being
+  // ordered are TMEM reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync), not global
+  // memory - an explicit .release.cluster here costs a MEMBAR.ALL.GPU per tile per warp
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -141,19 +146,28 @@ __device__ __forceinline__ bool elect_one_sync() {
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
 }
+// L2 eviction-priority policies accepted by the .L2::cache_hint operand of cp.async.bulk.tensor
+// (the encodings CUTLASS uses for TMA::CacheHintSm90)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+
 template <int kCtas>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1,
+                                            uint64_t policy) {
   if constexpr (kCtas == 1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
   } else {
     // data lands in THIS CTA's smem, the transaction bytes are reported to the barrier at
     // `bar` (a shared::cluster address inside the leader CTA of the pair)
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
   }
 }
@@ -381,8 +395,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             if (elect_one_sync()) {
               if (leader) mbar_expect_tx(bar_full + 8 * stage, C::kTxBytes);
-              tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row);
-              tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row);
+              tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row, p.hint_q);
+              tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row, p.hint_lib);
             }
             __syncwarp();
           }
@@ -570,6 +584,18 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   {
     const char* dbg = getenv("ALIVE_KNN_DEBUG_EPILOGUE");
     p.debug = dbg ? atoi(dbg) : 0;
+    // defaults: query tiles are re-read for every library tile (keep), library tiles stream
+    auto pick = [](const char* name, unsigned long long dflt) -> unsigned long long {
+      const char* v = getenv(name);
+      if (!v) return dflt;
+      switch (atoi(v)) {
+        case 1: return kL2EvictFirst;
+        case 2: return kL2EvictLast;
+        default: return kL2EvictNormal;
+      }
+    };
+    p.hint_q = pick("ALIVE_KNN_HINT_Q", kL2EvictNormal);
+    p.hint_lib = pick("ALIVE_KNN_HINT_LIB", kL2EvictNormal);
   }
 
   static bool attr_done = false;

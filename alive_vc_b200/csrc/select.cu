@@ -219,12 +219,25 @@ __device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_ra
                                                 float* __restrict__ out_row, int tid, int nthreads) {
   for (int j = tid * 4; j < d; j += nthreads * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < k; ++r) {
-      long long i = idx[r] - idx_base;
-      i = i < 0 ? 0 : (i >= n ? n - 1 : i);
-      const float4 v = *reinterpret_cast<const float4*>(lib_raw + static_cast<size_t>(i) * d + j);
-      if (r == 0) acc = v;
-      else acc = make_float4(__fadd_rn(acc.x, v.x), __fadd_rn(acc.y, v.y), __fadd_rn(acc.z, v.z), __fadd_rn(acc.w, v.w));
+    for (int r0 = 0; r0 < k; r0 += 8) {
+      // issue up to 8 row loads before the (order-preserving) sequential sum
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r0 + u < k) {
+          long long i = idx[r0 + u] - idx_base;
+          i = i < 0 ? 0 : (i >= n ? n - 1 : i);
+          v[u] = *reinterpret_cast<const float4*>(lib_raw + static_cast<size_t>(i) * d + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r0 + u < k) {
+          if (r0 + u == 0) acc = v[u];
+          else acc = make_float4(__fadd_rn(acc.x, v[u].x), __fadd_rn(acc.y, v[u].y), __fadd_rn(acc.z, v[u].z),
+                                 __fadd_rn(acc.w, v[u].w));
+        }
+      }
     }
     const float4 qv = *reinterpret_cast<const float4*>(q_row + j);
     const float kf = static_cast<float>(k);
@@ -321,9 +334,9 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
   __shared__ int qids[kQB];
 
   const int nq = q_count ? *q_count : t;
-  const int g0 = blockIdx.x * kQB;
-  if (g0 >= nq) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g0 = blockIdx.x * kQB; g0 < nq; g0 += gridDim.x * kQB) {   // grid-stride over query groups
+  __syncthreads();
   if (threadIdx.x < kQB) {
     const int slot = g0 + threadIdx.x;
     qids[threadIdx.x] = slot < nq ? (q_list ? q_list[slot] : slot) : -1;
@@ -419,6 +432,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
       warp_select_topk(scratch_s + qi * 8 * k, scratch_i + qi * 8 * k, 8 * k, k, part_score + o, part_idx + o, 0, lane);
     }
   }
+  }   // grid-stride loop over query groups
 }
 
 __global__ void __launch_bounds__(128)
@@ -553,7 +567,9 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
     attr_done = true;
   }
   ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
-  dim3 grid(static_cast<unsigned>(groups), static_cast<unsigned>(splits));
+  // at most ~4 waves of CTAs; groups beyond that are reached by the grid-stride loop
+  const size_t gx_cap = (4 * 148 + splits - 1) / splits;
+  dim3 grid(static_cast<unsigned>(groups < gx_cap ? groups : gx_cap), static_cast<unsigned>(splits));
   exact_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, n, d, k, q_list,
                                                               q_count, splits, static_cast<int>(region0), part_score, part_idx);
   ALIVE_CHECK_CUDA(cudaGetLastError());

@@ -51,6 +51,18 @@ WORKLOADS = {
 DEFAULT_STEPS = {"cfg1": 50, "cfg2": 1000, "cfg3": 5, "cfg4": 5, "cfg5": 3}
 
 
+def load_traffic(workload: str, world: int):
+    """DRAM bytes per launch of the dominant kernel from a committed ncu --set full capture
+    (profiles/traffic_r01.json), or None when this (workload, n_gpus) has not been captured."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        with open(p) as f:
+            ent = json.load(f).get(f"{workload}@{world}")
+        return ent["dram_bytes_per_launch"] if ent else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -386,7 +398,7 @@ def gpu_arm(args):
             bytes_per_launch = float(n_local) * D * 2
             achieved = bytes_per_launch / (avg_search_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(args.workload, world),
                     "kernel": "knn_search_kernel", "avg_kernel_ms": avg_search_ms, "peak_source": peaks["source"]}
         else:
             achieved = flops_per_launch / (avg_search_ms * 1e-3) / 1e12
@@ -395,7 +407,7 @@ def gpu_arm(args):
             sustained = False
             peak = peaks["bf16_burst"]
             roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "kernel": "knn_search_kernel",
+                    "frac": achieved / peak, "traffic": load_traffic(args.workload, world), "kernel": "knn_search_kernel",
                     "avg_kernel_ms": avg_search_ms,
                     "kernel_share_of_step": avg_search_ms * (len(libs) if args.workload == "cfg5" else 1) / ms_per_step,
                     "peak_kind": "sustained" if sustained else "burst", "peak_source": peaks["source"],
