@@ -317,122 +317,192 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
 }
 
 // ------------------------------------------------------------------------------------------
-// exact scan: grid (query groups of 8, library splits); 8 warps per CTA
+// exact scan: fp64-accumulated similarities of kEQ queries x all frames of one library split,
+// tiled like a GEMM on the CUDA cores: a CTA holds a [kEK][kEQ] query chunk and a [kEK][kER]
+// frame chunk in shared memory as doubles (frames normalised x/|x| with IEEE division while
+// staging), every thread owns a 4 query x 8 frame block of accumulators, and after the K loop
+// each warp folds the tile's scores into its queries' running top-k lists.
+// grid = (query groups [grid-stride], library splits); partial lists go to part_score/part_idx.
 // ------------------------------------------------------------------------------------------
-constexpr int kQB = 8;
+constexpr int kEQ = 64;         // queries per CTA
+constexpr int kER = 128;        // frames per tile
+constexpr int kEK = 32;         // channels per staged chunk
+constexpr int kEThreads = 256;
+constexpr int kEScPitch = kER + 1;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kEThreads)
 exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm, int t,
                      const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
                      int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
-                     int region0_bytes, float* __restrict__ part_score, long long* __restrict__ part_idx) {
+                     float* __restrict__ part_score, long long* __restrict__ part_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // region 0: normalised queries [kQB][d] during the scan, merge scratch afterwards
-  float* qh = reinterpret_cast<float*>(smem_raw);
-  long long* lid = reinterpret_cast<long long*>(smem_raw + region0_bytes);   // [8 warps][kQB][k]
-  float* lsc = reinterpret_cast<float*>(lid + 8 * kQB * k);                  // [8 warps][kQB][k]
-  __shared__ int qids[kQB];
+  double* Qd = reinterpret_cast<double*>(smem_raw);                       // [kEK][kEQ]
+  double* Rd = Qd + kEK * kEQ;                                            // [kEK][kER]
+  float* sc = reinterpret_cast<float*>(Rd + kEK * kER);                   // [kEQ][kEScPitch]
+  long long* li = reinterpret_cast<long long*>(sc + kEQ * kEScPitch + ((kEQ * kEScPitch) & 1));   // [kEQ][k]
+  float* ls = reinterpret_cast<float*>(li + kEQ * k);                     // [kEQ][k]
+  __shared__ int qids[kEQ];
+  __shared__ float qnrm[kEQ];
+  __shared__ int lcount[kEQ];
+  __shared__ int lworst[kEQ];
 
   const int nq = q_count ? *q_count : t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int g0 = blockIdx.x * kQB; g0 < nq; g0 += gridDim.x * kQB) {   // grid-stride over query groups
-  __syncthreads();
-  if (threadIdx.x < kQB) {
-    const int slot = g0 + threadIdx.x;
-    qids[threadIdx.x] = slot < nq ? (q_list ? q_list[slot] : slot) : -1;
-  }
-  __syncthreads();
-  for (int qi = 0; qi < kQB; ++qi) {
-    const int q = qids[qi];
-    const float qn = q >= 0 ? q_norm[q] : 1.f;
-    for (int j = threadIdx.x; j < d; j += blockDim.x)
-      qh[qi * d + j] = q >= 0 ? __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn) : 0.f;
-  }
-  for (int e = threadIdx.x; e < 8 * kQB * k; e += blockDim.x) {
-    lid[e] = -1;
-    lsc[e] = 0.f;
-  }
-  __syncthreads();
-
+  const int tq = threadIdx.x & 15;          // queries 4*tq .. 4*tq+3
+  const int tr = threadIdx.x >> 4;          // frames  8*tr .. 8*tr+7
   const long long per = (n + splits - 1) / splits;
-  const long long r0 = per * blockIdx.y;
-  const long long r1 = min(n, r0 + per);
-  // lane qi (< kQB) of every warp owns that warp's list for query qi; worst = entry to replace
-  float* my_s = lsc + (warp * kQB + (lane & (kQB - 1))) * k;
-  long long* my_i = lid + (warp * kQB + (lane & (kQB - 1))) * k;
-  int filled = 0, worst = 0;
-  for (long long r = r0 + warp; r < r1; r += 8) {
-    const float* row = lib_raw + static_cast<size_t>(r) * d;
-    const float nrm = lib_norm[r];
-    // normalise the frame once (x / |x|, IEEE division), then one fp64 dot per query
-    constexpr int kMaxVec = 12;                       // d <= 1536 -> at most 12 float4 per lane
-    float4 rn[kMaxVec];
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int j = lane * 4 + i * 128;
-      if (j < d) {
-        const float4 v = *reinterpret_cast<const float4*>(row + j);
-        rn[i] = make_float4(__fdiv_rn(v.x, nrm), __fdiv_rn(v.y, nrm), __fdiv_rn(v.z, nrm), __fdiv_rn(v.w, nrm));
-      } else {
-        rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  const long long n_items = static_cast<long long>((nq + kEQ - 1) / kEQ) * splits;
+
+  // work items = (query group, library split), handed out grid-stride: a handful of uncertified
+  // queries still spreads over every SM, and an empty list costs one early exit per CTA
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int g0 = static_cast<int>(item / splits) * kEQ;
+    const int split = static_cast<int>(item % splits);
+    const long long r0 = per * split;
+    const long long r1 = min(n, r0 + per);
+    __syncthreads();
+    if (threadIdx.x < kEQ) {
+      const int slot = g0 + threadIdx.x;
+      const int q = slot < nq ? (q_list ? q_list[slot] : slot) : -1;
+      qids[threadIdx.x] = q;
+      qnrm[threadIdx.x] = q >= 0 ? q_norm[q] : 1.f;
+      lcount[threadIdx.x] = 0;
+      lworst[threadIdx.x] = 0;
     }
-    float mine = 0.f;
+    __syncthreads();
+
+    for (long long rb = r0; rb < r1; rb += kER) {
+      double acc[4][8];
 #pragma unroll
-    for (int qi = 0; qi < kQB; ++qi) {
-      const float* qv = qh + qi * d;
-      double acc = 0.0;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int i = 0; i < kMaxVec; ++i) {
-        const int j = lane * 4 + i * 128;
-        if (j < d) {
-          const float4 a = *reinterpret_cast<const float4*>(qv + j);
-          acc += static_cast<double>(a.x) * static_cast<double>(rn[i].x);
-          acc += static_cast<double>(a.y) * static_cast<double>(rn[i].y);
-          acc += static_cast<double>(a.z) * static_cast<double>(rn[i].z);
-          acc += static_cast<double>(a.w) * static_cast<double>(rn[i].w);
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+
+      for (int kc = 0; kc < d; kc += kEK) {
+        // ---- stage: queries (8 values per thread) and frames (16 values per thread), as doubles ----
+        {
+          const int qi = threadIdx.x >> 2, part = threadIdx.x & 3;        // 64 queries x 4 parts of 8
+          const int q = qids[qi];
+          const float qn = qnrm[qi];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = part * 8 + h * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q >= 0 && kc + c < d) v = *reinterpret_cast<const float4*>(q_raw + static_cast<size_t>(q) * d + kc + c);
+            Qd[(c + 0) * kEQ + qi] = static_cast<double>(__fdiv_rn(v.x, qn));
+            Qd[(c + 1) * kEQ + qi] = static_cast<double>(__fdiv_rn(v.y, qn));
+            Qd[(c + 2) * kEQ + qi] = static_cast<double>(__fdiv_rn(v.z, qn));
+            Qd[(c + 3) * kEQ + qi] = static_cast<double>(__fdiv_rn(v.w, qn));
+          }
+          const int ri = threadIdx.x >> 1, rpart = threadIdx.x & 1;       // 128 frames x 2 parts of 16
+          const long long row = rb + ri;
+          const bool ok = row < r1;
+          const float rn = ok ? lib_norm[row] : 1.f;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int c = rpart * 16 + h * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && kc + c < d) v = *reinterpret_cast<const float4*>(lib_raw + static_cast<size_t>(row) * d + kc + c);
+            Rd[(c + 0) * kER + ri] = static_cast<double>(__fdiv_rn(v.x, rn));
+            Rd[(c + 1) * kER + ri] = static_cast<double>(__fdiv_rn(v.y, rn));
+            Rd[(c + 2) * kER + ri] = static_cast<double>(__fdiv_rn(v.z, rn));
+            Rd[(c + 3) * kER + ri] = static_cast<double>(__fdiv_rn(v.w, rn));
+          }
+        }
+        __syncthreads();
+        // ---- 4 x 8 outer products per channel ----
+#pragma unroll 4
+        for (int j = 0; j < kEK; ++j) {
+          const double2 q01 = *reinterpret_cast<const double2*>(Qd + j * kEQ + 4 * tq);
+          const double2 q23 = *reinterpret_cast<const double2*>(Qd + j * kEQ + 4 * tq + 2);
+          const double qv[4] = {q01.x, q01.y, q23.x, q23.y};
+          double rv[8];
+#pragma unroll
+          for (int b = 0; b < 8; b += 2) {
+            const double2 r2 = *reinterpret_cast<const double2*>(Rd + j * kER + 8 * tr + b);
+            rv[b] = r2.x;
+            rv[b + 1] = r2.y;
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = fma(qv[a], rv[b], acc[a][b]);
+        }
+        __syncthreads();
+      }
+      // ---- scores of this tile ----
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) sc[(4 * tq + a) * kEScPitch + 8 * tr + b] = static_cast<float>(acc[a][b]);
+      __syncthreads();
+      // ---- fold into the running top-k lists: warp w owns queries 8w .. 8w+7 ----
+      for (int qq = 0; qq < kEQ / 8; ++qq) {
+        const int ql = warp * (kEQ / 8) + qq;
+        if (qids[ql] < 0) continue;                       // warp-uniform
+        float* my_s = ls + ql * k;
+        long long* my_i = li + ql * k;
+        for (int u = 0; u < kER / 32; ++u) {
+          const int b = lane + 32 * u;
+          const long long row = rb + b;
+          bool pending = row < r1;
+          const float s = sc[ql * kEScPitch + b];
+          while (true) {
+            const int cnt = lcount[ql];
+            const int wpos = lworst[ql];
+            const bool want = pending && (cnt < k || score_better(s, row, my_s[wpos], my_i[wpos]));
+            const unsigned m = __ballot_sync(0xffffffffu, want);
+            if (m == 0) break;
+            const int src = __ffs(static_cast<int>(m)) - 1;
+            if (lane == src) {
+              const int pos = cnt < k ? cnt : wpos;
+              my_s[pos] = s;
+              my_i[pos] = row;
+              if (cnt < k) lcount[ql] = cnt + 1;
+              pending = false;
+            }
+            __syncwarp();
+            if (lcount[ql] == k) {                        // list full: locate its worst entry
+              float ws = 0.f;
+              long long wi = -1;
+              int wp = -1;
+              for (int e = lane; e < k; e += 32) {
+                if (wp < 0 || score_better(ws, wi, my_s[e], my_i[e])) {
+                  ws = my_s[e];
+                  wi = my_i[e];
+                  wp = e;
+                }
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                const int op = __shfl_xor_sync(0xffffffffu, wp, o);
+                if (op >= 0 && (wp < 0 || score_better(ws, wi, os, oi))) {
+                  ws = os;
+                  wi = oi;
+                  wp = op;
+                }
+              }
+              if (lane == 0) lworst[ql] = wp;
+            }
+            __syncwarp();
+          }
         }
       }
-      acc = warp_sum_f64(acc);
-      if (lane == qi) mine = static_cast<float>(acc);
+      __syncthreads();
     }
-    if (lane < kQB && qids[lane] >= 0) {
-      if (filled < k) {
-        my_s[filled] = mine;
-        my_i[filled] = r;
-        ++filled;
-        if (filled == k) {
-          worst = 0;
-          for (int e = 1; e < k; ++e)
-            if (score_better(my_s[worst], my_i[worst], my_s[e], my_i[e])) worst = e;
-        }
-      } else if (score_better(mine, r, my_s[worst], my_i[worst])) {
-        my_s[worst] = mine;
-        my_i[worst] = r;
-        worst = 0;
-        for (int e = 1; e < k; ++e)
-          if (score_better(my_s[worst], my_i[worst], my_s[e], my_i[e])) worst = e;
-      }
+    // ---- this split's top-k of every query of the group (sorted) ----
+    for (int qq = 0; qq < kEQ / 8; ++qq) {
+      const int ql = warp * (kEQ / 8) + qq;
+      if (qids[ql] < 0) continue;
+      // pad unused entries so the selector skips them
+      for (int e = lcount[ql] + lane; e < k; e += 32) li[ql * k + e] = -1;
+      __syncwarp();
+      const size_t o = (static_cast<size_t>(g0 + ql) * splits + split) * k;
+      warp_select_topk(ls + ql * k, li + ql * k, k, k, part_score + o, part_idx + o, 0, lane);
     }
   }
-  __syncthreads();
-  // merge the 8 per-warp lists of each query (warp w finishes query w); region 0 is free now
-  float* scratch_s = qh;                                                  // [kQB][8*k] floats
-  long long* scratch_i = reinterpret_cast<long long*>(qh + kQB * 8 * k + ((kQB * 8 * k) & 1));
-  for (int e = threadIdx.x; e < kQB * 8 * k; e += blockDim.x) {
-    const int qi = e / (8 * k), rem = e % (8 * k), w = rem / k, j = rem % k;
-    scratch_s[e] = lsc[(w * kQB + qi) * k + j];
-    scratch_i[e] = lid[(w * kQB + qi) * k + j];
-  }
-  __syncthreads();
-  {
-    const int qi = warp;
-    if (qids[qi] >= 0) {
-      const size_t o = (static_cast<size_t>(g0 + qi) * splits + blockIdx.y) * k;
-      warp_select_topk(scratch_s + qi * 8 * k, scratch_i + qi * 8 * k, 8 * k, k, part_score + o, part_idx + o, 0, lane);
-    }
-  }
-  }   // grid-stride loop over query groups
 }
 
 __global__ void __launch_bounds__(128)
@@ -476,17 +546,13 @@ merge_kernel(const float* __restrict__ scores, const long long* __restrict__ idx
 }
 
 int exact_splits(int t, long long n, int k) {
-  // enough (query group, split) CTAs to fill the GPU, at least 256 frames per split
-  const long long groups = (static_cast<long long>(t) + kQB - 1) / kQB;
-  long long s = (2 * 148 + groups - 1) / groups;
-  // long libraries are always split (a handful of uncertified queries must not serialise on one CTA)
-  const long long s_long = (n + 8191) / 8192;
-  if (s < s_long) s = s_long;
-  const long long s_max = (n + 255) / 256;
-  if (s > s_max) s = s_max;
-  if (s > 64) s = 64;
+  // library splits of ~4096 frames (at most 256) so that even a handful of uncertified queries is
+  // spread over the whole GPU; the partial-list workspace (slots * splits * k * 12 B) is capped
+  long long s = (n + 4095) / 4096;
+  if (s > 256) s = 256;
   if (s < 1) s = 1;
-  while (s > 1 && static_cast<long long>(t) * s * k * 12 > (256ll << 20)) s /= 2;
+  const long long slots = ((static_cast<long long>(t) + kEQ - 1) / kEQ) * kEQ;
+  while (s > 1 && slots * s * k * 12 > (384ll << 20)) s /= 2;
   return static_cast<int>(s);
 }
 
@@ -534,8 +600,8 @@ extern "C" size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t 
   using namespace alive;
   if (t < 1 || k < 1) return 0;
   const int s = exact_splits(t, n, k);
-  const size_t groups = (static_cast<size_t>(t) + kQB - 1) / kQB;
-  return groups * kQB * s * k * 12 + 256;
+  const size_t groups = (static_cast<size_t>(t) + kEQ - 1) / kEQ;
+  return groups * kEQ * s * k * 12 + 256;
 }
 
 extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t, const float* lib_raw,
@@ -553,25 +619,23 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
                 "alive_knn_exact: raw buffers must be 16-byte aligned");
   if (t <= 0) return 0;
   const int splits = exact_splits(t, n, k);
-  const size_t groups = (static_cast<size_t>(t) + kQB - 1) / kQB;
-  // workspace layout: part_idx [groups*kQB*splits*k] int64, then part_score float
+  const size_t groups = (static_cast<size_t>(t) + kEQ - 1) / kEQ;
+  // workspace layout: part_idx [groups*kEQ*splits*k] int64, then part_score float
   long long* part_idx = reinterpret_cast<long long*>(workspace);
-  float* part_score = reinterpret_cast<float*>(part_idx + groups * kQB * splits * k);
-  const size_t smem_q = static_cast<size_t>(kQB) * d * 4;
-  const size_t smem_scratch = static_cast<size_t>(kQB) * 8 * k * 12 + 8;
-  const size_t region0 = ((smem_q > smem_scratch ? smem_q : smem_scratch) + 15) & ~static_cast<size_t>(15);
-  const size_t smem = region0 + static_cast<size_t>(8) * kQB * k * 12;
+  float* part_score = reinterpret_cast<float*>(part_idx + groups * kEQ * splits * k);
+  const size_t smem = static_cast<size_t>(kEK) * (kEQ + kER) * 8 + (static_cast<size_t>(kEQ) * kEScPitch + 1) * 4 +
+                      static_cast<size_t>(kEQ) * k * 12 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_done = true;
   }
   ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
-  // at most ~4 waves of CTAs; groups beyond that are reached by the grid-stride loop
-  const size_t gx_cap = (4 * 148 + splits - 1) / splits;
-  dim3 grid(static_cast<unsigned>(groups < gx_cap ? groups : gx_cap), static_cast<unsigned>(splits));
-  exact_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, n, d, k, q_list,
-                                                              q_count, splits, static_cast<int>(region0), part_score, part_idx);
+  // at most ~4 waves of CTAs; the (group, split) items beyond that are reached grid-stride
+  const size_t items = groups * static_cast<size_t>(splits);
+  const unsigned grid = static_cast<unsigned>(items < 4 * 148 ? items : 4 * 148);
+  exact_partial_kernel<<<grid, kEThreads, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, n, d, k, q_list,
+                                                                    q_count, splits, part_score, part_idx);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   ALIVE_REQUIRE(out == nullptr || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && idx_base == 0),
                 "alive_knn_exact: gather needs a 16-byte aligned `out` and an unsharded library");

@@ -1,7 +1,7 @@
 """Stage-by-stage GPU diagnostics for the alive_knn kernels (run on the B200 box).
 
-    python tools/gpu_diag.py            # runs every stage in its own subprocess
-    python tools/gpu_diag.py pack       # one stage in-process
+    python tests/gpu_tools/gpu_diag.py            # runs every stage in its own subprocess
+    python tests/gpu_tools/gpu_diag.py pack       # one stage in-process
 
 Each stage runs in a fresh process so that a trapped kernel (sticky CUDA error)
 cannot poison the following stages.  Output goes to stdout; the driver also writes
@@ -14,7 +14,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 STAGES = ["pack", "exact", "search1", "search2", "pipeline1", "pipeline2", "golden", "perf1", "perf2"]

@@ -69,5 +69,29 @@ def main():
               f"screen==exact: {same}")
 
 
+def sparse_fallback():
+    """a few uncertifiable queries inside a large, otherwise well-behaved batch"""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(11)
+    print("== sparse fallbacks (T=1000, N=1M iid + one tight cluster of 300 frames; 5 queries sit in the cluster)")
+    T, N = 1000, 1_000_000
+    ref = torch.randn(768, N, device=dev, generator=g)
+    c = torch.randn(768, 1, device=dev, generator=g)
+    where = torch.randperm(N, device=dev, generator=g)[:300]
+    ref[:, where] = c + 0.01 * torch.randn(768, 300, device=dev, generator=g)
+    src = torch.randn(1, 768, T, device=dev, generator=g)
+    lib = A.pack_library(ref[None])
+    ms0 = timed(lambda: M.run_match(src, lib, 4, 0.0, mode="screen"))
+    fb0 = M.last_info.fallback_queries()
+    src[0, :, :5] = c + 0.01 * torch.randn(768, 5, device=dev, generator=g)
+    ms1 = timed(lambda: M.run_match(src, lib, 4, 0.0, mode="screen"))
+    fb1 = M.last_info.fallback_queries()
+    _, idx_s, _ = M.run_match(src, lib, 4, 0.0, mode="screen")
+    _, idx_e, _ = M.run_match(src[:, :, :16].contiguous(), lib, 4, 0.0, mode="exact")
+    print(f"no cluster queries: {ms0:.3f} ms (fallback {fb0});  5 cluster queries: {ms1:.3f} ms (fallback {fb1}); "
+          f"first 16 queries screen==exact: {bool(torch.equal(idx_s[:, :16], idx_e))}")
+
+
 if __name__ == "__main__":
     main()
+    sparse_fallback()
