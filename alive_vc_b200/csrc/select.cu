@@ -550,8 +550,13 @@ int exact_splits(int t, long long n, int k) {
   // spread over the whole GPU; the partial-list workspace (slots * splits * k * 12 B) is capped
   long long s = (n + 4095) / 4096;
   if (s > 256) s = 256;
+  const long long groups = (static_cast<long long>(t) + kEQ - 1) / kEQ;
+  const long long s_fill = (2 * 148 + groups - 1) / groups;    // few query groups: split finer to fill the GPU
+  if (s < s_fill) s = s_fill;
+  const long long s_max = (n + kER - 1) / kER;                 // at least one 128-frame tile per split
+  if (s > s_max) s = s_max;
   if (s < 1) s = 1;
-  const long long slots = ((static_cast<long long>(t) + kEQ - 1) / kEQ) * kEQ;
+  const long long slots = groups * kEQ;
   while (s > 1 && slots * s * k * 12 > (384ll << 20)) s /= 2;
   return static_cast<int>(s);
 }

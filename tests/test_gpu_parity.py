@@ -360,3 +360,21 @@ def test_planted_neighbours_at_large_n():
                                       torch.cuda.current_stream().cuda_stream)
     _cabi.check(rc, "merge")
     assert torch.equal(top_i, pos) and torch.equal(top_s, score[0])
+
+
+def test_cfg4_scale_screen_equals_exhaustive_scan():
+    """BASELINE configs[3] library size (N = 10M frames on one GPU): the certified tensor-core path and
+    the exhaustive fp64 scan must agree bit for bit (indices and similarities) for a batch of queries.
+    The oracle cannot run at this size; the exhaustive scan is itself checked against the oracle at
+    small sizes (test_exact_scan_against_oracle)."""
+    import bench
+    dev = torch.device("cuda", 0)
+    lib = bench.build_library(0, 10_000_000, 3, dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    src = torch.randn(1, 768, 192, device=dev, generator=g)
+    out_s, idx_s, sc_s = M.run_match(src, lib, 4, 0.0, mode="screen")
+    assert M.last_info.fallback_queries() == 0
+    out_e, idx_e, sc_e = M.run_match(src, lib, 4, 0.0, mode="exact")
+    assert torch.equal(idx_s, idx_e) and torch.equal(sc_s, sc_e) and torch.equal(out_s, out_e)
+    del lib
+    torch.cuda.empty_cache()
