@@ -7,6 +7,7 @@
 //   approximates; ties resolve to the lowest frame index.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -250,7 +251,8 @@ __device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_ra
 constexpr int kFinishThreads = 256;
 constexpr int kFinishMaxStagedEntries = 6144;   // lists*8 entries staged in shared memory (48 KB) when they fit
 
-__global__ void __launch_bounds__(kFinishThreads)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kFinishThreads, kMinBlocks)
 finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
               const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
               const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
@@ -348,8 +350,10 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
 
   const int nq = q_count ? *q_count : t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tq = threadIdx.x & 15;          // queries 4*tq .. 4*tq+3
-  const int tr = threadIdx.x >> 4;          // frames  8*tr .. 8*tr+7
+  // a warp covers 8 queries x 128 frames (two 4-query blocks x sixteen 8-frame blocks): groups
+  // with few valid queries (sparse fallbacks) let whole warps skip the FMA loop
+  const int tq = threadIdx.x >> 4;          // queries 4*tq .. 4*tq+3
+  const int tr = threadIdx.x & 15;          // frames  8*tr .. 8*tr+7
   const long long per = (n + splits - 1) / splits;
   const long long n_items = static_cast<long long>((nq + kEQ - 1) / kEQ) * splits;
 
@@ -410,7 +414,8 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
           }
         }
         __syncthreads();
-        // ---- 4 x 8 outer products per channel ----
+        // ---- 4 x 8 outer products per channel (valid queries are a prefix of the group) ----
+        if (__any_sync(0xffffffffu, qids[4 * tq] >= 0)) {
 #pragma unroll 4
         for (int j = 0; j < kEK; ++j) {
           const double2 q01 = *reinterpret_cast<const double2*>(Qd + j * kEQ + 4 * tq);
@@ -427,6 +432,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
           for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 8; ++b) acc[a][b] = fma(qv[a], rv[b], acc[a][b]);
+        }
         }
         __syncthreads();
       }
@@ -688,15 +694,25 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
                       (staged ? static_cast<size_t>(entries) * 8 : 0);
   static bool attr_done = false;
+  static int variant = 4;   // 4 CTAs per SM (64 registers): the kernel is latency-bound, occupancy helps (measured +6% at cfg1)
   if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    const char* v = getenv("ALIVE_KNN_FINISH_BLOCKS");
+    if (v) variant = atoi(v);
     attr_done = true;
   }
   ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-  finish_kernel<<<t, kFinishThreads, smem, as_stream(stream)>>>(
-      cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1,
-      alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged);
+#define ALIVE_LAUNCH_FINISH(B)                                                                                       \
+  finish_kernel<B><<<t, kFinishThreads, smem, as_stream(stream)>>>(                                                  \
+      cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1, \
+      alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged)
+  if (variant == 6) ALIVE_LAUNCH_FINISH(6);
+  else if (variant == 4) ALIVE_LAUNCH_FINISH(4);
+  else ALIVE_LAUNCH_FINISH(3);
+#undef ALIVE_LAUNCH_FINISH
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
