@@ -353,7 +353,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
   // a warp covers 8 queries x 128 frames (two 4-query blocks x sixteen 8-frame blocks): groups
   // with few valid queries (sparse fallbacks) let whole warps skip the FMA loop
   const int tq = threadIdx.x >> 4;          // queries 4*tq .. 4*tq+3
-  const int tr = threadIdx.x & 15;          // frames  8*tr .. 8*tr+7
+  const int tr = threadIdx.x & 15;          // frames  32*(b/2) + 2*tr + (b&1), b < 8 (conflict-free 16-byte loads)
   const long long per = (n + splits - 1) / splits;
   const long long n_items = static_cast<long long>((nq + kEQ - 1) / kEQ) * splits;
 
@@ -424,7 +424,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
           double rv[8];
 #pragma unroll
           for (int b = 0; b < 8; b += 2) {
-            const double2 r2 = *reinterpret_cast<const double2*>(Rd + j * kER + 8 * tr + b);
+            const double2 r2 = *reinterpret_cast<const double2*>(Rd + j * kER + 16 * b + 2 * tr);
             rv[b] = r2.x;
             rv[b + 1] = r2.y;
           }
@@ -440,7 +440,8 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) sc[(4 * tq + a) * kEScPitch + 8 * tr + b] = static_cast<float>(acc[a][b]);
+        for (int b = 0; b < 8; ++b)
+          sc[(4 * tq + a) * kEScPitch + 32 * (b >> 1) + 2 * tr + (b & 1)] = static_cast<float>(acc[a][b]);
       __syncthreads();
       // ---- fold into the running top-k lists: warp w owns queries 8w .. 8w+7 ----
       for (int qq = 0; qq < kEQ / 8; ++qq) {

@@ -378,3 +378,24 @@ def test_cfg4_scale_screen_equals_exhaustive_scan():
     assert torch.equal(idx_s, idx_e) and torch.equal(sc_s, sc_e) and torch.equal(out_s, out_e)
     del lib
     torch.cuda.empty_cache()
+
+
+def test_functional_api_packs_the_library_once_and_follows_inplace_edits():
+    """realtime_inference.py:165 passes the same `tgt` tensor every chunk: it must be packed once,
+    re-packed when it is modified in place, and never confused with another tensor."""
+    M.clear_pack_cache()
+    g = torch.Generator(device="cuda").manual_seed(41)
+    tgt = torch.randn(1, 768, 4000, device="cuda", generator=g)
+    view = tgt[:, :, ::4]                                      # the [:, :, ::4] view of realtime_inference.py:88
+    chunk = torch.randn(1, 768, 24, device="cuda", generator=g)
+    a = A.match_features(chunk, view)
+    n_entries = len(M._pack_cache)
+    packed_first = next(iter(M._pack_cache.values()))[2]
+    b = A.match_features(chunk, view)
+    assert len(M._pack_cache) == n_entries and next(iter(M._pack_cache.values()))[2] is packed_first
+    assert torch.equal(a, b)
+    tgt[:, :, 0] += 1.0                                        # in-place edit through the base tensor
+    c = A.match_features(chunk, view)
+    assert next(iter(M._pack_cache.values()))[2] is not packed_first
+    want = A.match_features(chunk, view.contiguous())
+    assert torch.equal(c, want)
