@@ -268,6 +268,10 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   float* st_sc = reinterpret_cast<float*>(sel + r_max);                   // [entries] (staged only)
   int* st_ix = reinterpret_cast<int*>(st_sc + (staged ? lists * kListLen : 0));
   __shared__ int s_count;
+  __shared__ float s_cut;
+  __shared__ float s_tau[kFinishThreads / 32];
+  __shared__ int s_wcnt[kFinishThreads / 32];
+  __shared__ float s_wbest[(kFinishThreads / 32) * kListLen];
   __shared__ long long s_top[kMaxK];
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -285,16 +289,105 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   for (int j = threadIdx.x; j < d; j += kFinishThreads)
     qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
   __syncthreads();
-  if (warp == 0) {
-    const int count = prune_query(staged ? st_sc : g_sc, staged ? st_ix : g_ix, lists, k, q_err[q], qn, lib_stats,
-                                  r_max, sel, lane);
-    if (lane == 0) {
-      s_count = count;
+  // ---- certificate + survivor compaction, spread over the whole CTA (prune_query's logic) ----
+  {
+    const float* sc = staged ? st_sc : g_sc;
+    const int* ix = staged ? st_ix : g_ix;
+    const int n_entries = static_cast<int>(entries);
+    constexpr int kWarps = kFinishThreads / 32;
+    // tau = max of the list minima
+    float tau = -INFINITY;
+    for (int l = threadIdx.x; l < lists; l += kFinishThreads) tau = fmaxf(tau, sc[l * kListLen + kListLen - 1]);
+    tau = warp_max_f32(tau);
+    if (lane == 0) s_tau[warp] = tau;
+    // every warp: the k best entries of its contiguous slice, under (score desc, position asc)
+    const int e_lo = static_cast<int>(static_cast<long long>(n_entries) * warp / kWarps);
+    const int e_hi = static_cast<int>(static_cast<long long>(n_entries) * (warp + 1) / kWarps);
+    float prev_s = INFINITY;
+    int prev_p = -1;
+    for (int r = 0; r < k; ++r) {
+      float best_s = -INFINITY;
+      int best_p = 0x7fffffff;
+      for (int e = e_lo + lane; e < e_hi; e += 32) {
+        const float v = sc[e];
+        const bool after_prev = (v < prev_s) || (v == prev_s && e > prev_p);
+        if (after_prev && (v > best_s || (v == best_s && e < best_p))) {
+          best_s = v;
+          best_p = e;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, best_s, o);
+        const int op = __shfl_xor_sync(0xffffffffu, best_p, o);
+        if (os > best_s || (os == best_s && op < best_p)) {
+          best_s = os;
+          best_p = op;
+        }
+      }
+      prev_s = best_s;
+      prev_p = best_p;
+      if (lane == 0) s_wbest[warp * kListLen + r] = best_s;    // -inf when the slice ran out
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // S_k = k-th largest of the kWarps*k slice winners (values only; duplicates count)
+      float v = (lane < kWarps * k) ? s_wbest[(lane / k) * kListLen + (lane % k)] : -INFINITY;
+      float v2 = (lane + 32 < kWarps * k) ? s_wbest[((lane + 32) / k) * kListLen + ((lane + 32) % k)] : -INFINITY;
+      float sk = -INFINITY;
+      for (int r = 0; r < k; ++r) {
+        const float m = warp_max_f32(fmaxf(v, v2));
+        sk = m;
+        // remove ONE occurrence of the maximum (lowest lane first, first slot first)
+        const unsigned has = __ballot_sync(0xffffffffu, v == m || v2 == m);
+        if (has == 0) break;
+        const int src = __ffs(static_cast<int>(has)) - 1;
+        if (lane == src) {
+          if (v == m) v = -INFINITY;
+          else v2 = -INFINITY;
+        }
+      }
+      float t2 = (lane < kWarps) ? s_tau[lane] : -INFINITY;
+      t2 = warp_max_f32(t2);
+      const float le = __uint_as_float(lib_stats[0]);
+      const float qe = q_err[q];
+      const float eps = (le + qe + le * qe + kAccumSlack) * 1.00001f;
+      const float cut = sk - 2.0f * eps - 1e-7f;
+      const bool fb = lib_stats[1] != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > t2);
+      if (lane == 0) {
+        s_cut = cut;
+        s_count = fb ? -1 : 0;
+      }
+    }
+    __syncthreads();
+    if (s_count == 0) {
+      // ordered compaction of the survivors (entry order), whole CTA
+      const float cut = s_cut;
+      int base = 0;
+      for (int e0 = 0; e0 < n_entries; e0 += kFinishThreads) {
+        const int e = e0 + threadIdx.x;
+        const bool keep = e < n_entries && sc[e] >= cut && ix[e] >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += s_wcnt[w];
+        int total = 0;
+        for (int w = 0; w < kWarps; ++w) total += s_wcnt[w];
+        const int pos = before + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < r_max) sel[pos] = ix[e];
+        base += total;
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) s_count = (base > r_max || base < k) ? -1 : base;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const int count = s_count;
       sel_n[q] = count;
       if (count < 0) fb_list[atomicAdd(fb_count, 1)] = q;
     }
   }
-  __syncthreads();
   const int n_sel = s_count;
   if (n_sel < 0) return;   // the exact scan (and its gather) handle this query
   for (int c = warp; c < n_sel; c += kFinishThreads / 32) {
