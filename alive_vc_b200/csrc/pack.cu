@@ -96,6 +96,72 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
   }
 }
 
+// Tiny batches (streaming chunks, T <= 512): one CTA per frame, three channels per thread, two
+// block reductions - one load round trip instead of a 768-row staging loop on a handful of CTAs.
+__global__ void __launch_bounds__(kPackThreads)
+pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
+                  float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
+                  float* __restrict__ err, unsigned int* __restrict__ stats) {
+  __shared__ double red[kPackThreads / 32];
+  __shared__ int fin[kPackThreads / 32];
+  const long long row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kPer = 6;                      // d <= 1536
+  float v[kPer];
+  double ss = 0.0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int j = threadIdx.x + i * kPackThreads;
+    v[i] = (j < d) ? x[row * stride_n + j * stride_d] : 0.f;
+    if (j < d) raw[row * d + j] = v[i];
+    ss += static_cast<double>(v[i]) * static_cast<double>(v[i]);
+  }
+  ss = warp_sum_f64(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < kPackThreads / 32; ++w) tot += red[w];     // same order in every thread
+  const float nrm = static_cast<float>(sqrt(tot));
+  __syncthreads();
+  double e2 = 0.0;
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int j = threadIdx.x + i * kPackThreads;
+    if (j < d) {
+      const float a = __fdiv_rn(v[i], nrm);
+      const __nv_bfloat16 h = __float2bfloat16_rn(a);
+      const float da = __bfloat162float(h) - a;
+      e2 += static_cast<double>(da) * da;
+      finite = finite && isfinite(a);
+      packed[row * d + j] = h;
+    }
+  }
+  e2 = warp_sum_f64(e2);
+  finite = __all_sync(0xffffffffu, finite);
+  if (lane == 0) {
+    red[warp] = e2;
+    fin[warp] = finite ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double et = 0.0;
+    bool ok = true;
+    for (int w = 0; w < kPackThreads / 32; ++w) {
+      et += red[w];
+      ok = ok && fin[w];
+    }
+    norms[row] = nrm;
+    const float e = ok ? static_cast<float>(sqrt(et)) * 1.0001f + 1e-9f : 0.f;
+    if (err) err[row] = e;
+    if (stats) {
+      if (ok) atomicMax(&stats[0], __float_as_uint(e));
+      else atomicAdd(&stats[1], 1u);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace alive
 
@@ -115,7 +181,10 @@ extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stri
     attr_done = true;
   }
   __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
-  if (n <= 8192) {
+  if (n <= 512) {
+    pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw,
+                                                                                       norms, pk, err, stats);
+  } else if (n <= 8192) {
     const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
     pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
         x, n, d, stride_n, stride_d, raw, norms, pk, err, stats);
