@@ -692,10 +692,13 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
   // long (more, shorter lists make the completeness certificate easy), and as few idle
   // tile-slots in the last wave as possible.
   const int n_tiles = plan->n_tiles;
-  int s_lo = (slots + plan->m_units - 1) / plan->m_units;
-  if (s_lo < 16) s_lo = 16;
+  // candidates: from 16 segments (enough lists for the certificate) up to 4x what fills the
+  // machine; the cost model below picks the cheapest, ties go to FEWER segments (every unit start
+  // pays for a cold top list in the epilogue)
+  const int s_fill = (slots + plan->m_units - 1) / plan->m_units;
+  int s_lo = 16;
   if (s_lo > n_tiles) s_lo = n_tiles;
-  int s_hi = s_lo * 4;
+  int s_hi = 4 * (s_fill > 16 ? s_fill : 16);
   if (s_hi > n_tiles) s_hi = n_tiles;
   long long best_cost = -1;
   int best_tps = 1;
