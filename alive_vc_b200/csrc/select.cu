@@ -251,8 +251,8 @@ __device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_ra
 constexpr int kFinishThreads = 256;
 constexpr int kFinishMaxStagedEntries = 6144;   // lists*8 entries staged in shared memory (48 KB) when they fit
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kFinishThreads, kMinBlocks)
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
               const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
               const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
@@ -269,9 +269,9 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   int* st_ix = reinterpret_cast<int*>(st_sc + (staged ? lists * kListLen : 0));
   __shared__ int s_count;
   __shared__ float s_cut;
-  __shared__ float s_tau[kFinishThreads / 32];
-  __shared__ int s_wcnt[kFinishThreads / 32];
-  __shared__ float s_wbest[(kFinishThreads / 32) * kListLen];
+  __shared__ float s_tau[kThreads / 32];
+  __shared__ int s_wcnt[kThreads / 32];
+  __shared__ float s_wbest[(kThreads / 32) * kListLen];
   __shared__ long long s_top[kMaxK];
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,12 +281,12 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   const int* g_ix = cand_idx + q * entries;
   // stage the screened lists (coalesced) and normalise the query frame (x / |x|, IEEE division)
   if (staged) {
-    for (int e = threadIdx.x * 4; e < static_cast<int>(entries); e += kFinishThreads * 4) {
+    for (int e = threadIdx.x * 4; e < static_cast<int>(entries); e += kThreads * 4) {
       *reinterpret_cast<float4*>(st_sc + e) = *reinterpret_cast<const float4*>(g_sc + e);
       *reinterpret_cast<int4*>(st_ix + e) = *reinterpret_cast<const int4*>(g_ix + e);
     }
   }
-  for (int j = threadIdx.x; j < d; j += kFinishThreads)
+  for (int j = threadIdx.x; j < d; j += kThreads)
     qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
   __syncthreads();
   // ---- certificate + survivor compaction, spread over the whole CTA (prune_query's logic) ----
@@ -294,10 +294,10 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
     const float* sc = staged ? st_sc : g_sc;
     const int* ix = staged ? st_ix : g_ix;
     const int n_entries = static_cast<int>(entries);
-    constexpr int kWarps = kFinishThreads / 32;
+    constexpr int kWarps = kThreads / 32;
     // tau = max of the list minima
     float tau = -INFINITY;
-    for (int l = threadIdx.x; l < lists; l += kFinishThreads) tau = fmaxf(tau, sc[l * kListLen + kListLen - 1]);
+    for (int l = threadIdx.x; l < lists; l += kThreads) tau = fmaxf(tau, sc[l * kListLen + kListLen - 1]);
     tau = warp_max_f32(tau);
     if (lane == 0) s_tau[warp] = tau;
     // every warp: the k best entries of its contiguous slice, under (score desc, position asc)
@@ -364,7 +364,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
       // ordered compaction of the survivors (entry order), whole CTA
       const float cut = s_cut;
       int base = 0;
-      for (int e0 = 0; e0 < n_entries; e0 += kFinishThreads) {
+      for (int e0 = 0; e0 < n_entries; e0 += kThreads) {
         const int e = e0 + threadIdx.x;
         const bool keep = e < n_entries && sc[e] >= cut && ix[e] >= 0;
         const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -390,7 +390,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   }
   const int n_sel = s_count;
   if (n_sel < 0) return;   // the exact scan (and its gather) handle this query
-  for (int c = warp; c < n_sel; c += kFinishThreads / 32) {
+  for (int c = warp; c < n_sel; c += kThreads / 32) {
     const int idx = sel[c];
     const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
     if (lane == 0) {
@@ -408,7 +408,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   if (threadIdx.x < k) s_top[threadIdx.x] = top_idx[static_cast<size_t>(q) * k + threadIdx.x];
   __syncthreads();
   gather_mean_row(lib_raw, n, d, s_top, idx_base, k, q_raw + static_cast<size_t>(q) * d, a1, a0,
-                  out + static_cast<size_t>(q) * d, threadIdx.x, kFinishThreads);
+                  out + static_cast<size_t>(q) * d, threadIdx.x, kThreads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -788,24 +788,22 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
                       (staged ? static_cast<size_t>(entries) * 8 : 0);
   static bool attr_done = false;
-  static int variant = 4;   // 4 CTAs per SM (64 registers): the kernel is latency-bound, occupancy helps (measured +6% at cfg1)
+  static int variant = 256;   // 256 threads x 4 CTAs per SM (64 registers): latency-bound, occupancy helps
   if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(finish_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    const char* v = getenv("ALIVE_KNN_FINISH_BLOCKS");
+    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+    const char* v = getenv("ALIVE_KNN_FINISH_THREADS");
     if (v) variant = atoi(v);
     attr_done = true;
   }
   ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-#define ALIVE_LAUNCH_FINISH(B)                                                                                       \
-  finish_kernel<B><<<t, kFinishThreads, smem, as_stream(stream)>>>(                                                  \
+#define ALIVE_LAUNCH_FINISH(TH, B)                                                                                   \
+  finish_kernel<TH, B><<<t, TH, smem, as_stream(stream)>>>(                                                          \
       cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1, \
       alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged)
-  if (variant == 6) ALIVE_LAUNCH_FINISH(6);
-  else if (variant == 4) ALIVE_LAUNCH_FINISH(4);
-  else ALIVE_LAUNCH_FINISH(3);
+  if (variant == 128) ALIVE_LAUNCH_FINISH(128, 8);
+  else ALIVE_LAUNCH_FINISH(256, 4);
 #undef ALIVE_LAUNCH_FINISH
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;

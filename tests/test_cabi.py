@@ -79,3 +79,37 @@ def test_argument_validation_without_gpu(lib):
     assert lib.alive_knn_pack(None, 4, 768, 1, 4, None, None, None, None, None, None) != 0
     assert b"NULL" in lib.alive_knn_last_error()
     assert lib.alive_knn_exact_workspace_bytes(1000, 100000, 4) > 0
+
+
+@pytest.mark.parametrize("rows,n,k,mode", [(32, 200_000, 4, 1), (1000, 100_000, 4, 0), (10_000, 10_000_000, 4, 1),
+                                           (24, 512, 4, 0), (7, 64, 16, 0), (450, 3512, 4, 2)])
+def test_match_workspace_layout_is_consistent(lib, rows, n, k, mode):
+    """alive_knn_match_layout is host-only: 12 ascending, 256-byte aligned offsets, large enough for
+    every buffer the pipeline carves out of the single workspace."""
+    off = (ctypes.c_int64 * 12)()
+    assert lib.alive_knn_match_layout(rows, n, 768, k, 64, mode, 148, 0, off) == 0
+    o = list(off)
+    assert o[0] == 0 and all(x % 256 == 0 for x in o)
+    assert all(o[i] <= o[i + 1] for i in range(11))
+    assert o[1] - o[0] >= rows * 768 * 4          # q_raw
+    assert o[2] - o[1] >= rows * 4                # q_norm
+    assert o[3] - o[2] >= rows * 768 * 2          # q_packed
+    assert o[4] - o[3] >= rows * 4                # q_err
+    screen = mode == 1 or (mode == 0 and k <= 8)
+    if screen:
+        p = _cabi.Plan()
+        assert lib.alive_knn_plan(rows, n, 768, 148, 0, ctypes.byref(p)) == 0
+        assert o[5] - o[4] >= rows * p.lists * 8 * 4 and o[6] - o[5] >= rows * p.lists * 8 * 4
+        assert o[7] - o[6] >= rows * 64 * 4       # sel_idx
+    assert o[11] - o[10] >= lib.alive_knn_exact_workspace_bytes(rows, n, k)
+
+
+def test_match_rejects_bad_arguments_before_any_launch(lib):
+    lb = _cabi.Library(1, 1, 1, 1, 3, 768, 0)     # n = 3 frames
+    # k > n: the reference's torch.topk message (common.py:105)
+    rc = lib.alive_knn_match(1, 1, 4, 768 * 4, 1, 4, ctypes.byref(lb), 4, 0.0, 64, 0, 148, 0, 256, 1 << 20, None, 1, 1,
+                             None, None, None)
+    assert rc != 0 and b"selected index k out of range" in lib.alive_knn_last_error()
+    rc = lib.alive_knn_match(None, 1, 4, 768 * 4, 1, 4, ctypes.byref(lb), 1, 0.0, 64, 0, 148, 0, 256, 1 << 20, None, 1, 1,
+                             None, None, None)
+    assert rc != 0 and b"NULL" in lib.alive_knn_last_error()
