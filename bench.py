@@ -259,11 +259,12 @@ def gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if rank == 0:
-        entry.build()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        dist.barrier()
+    if rank == 0:
+        entry.build()          # no-op when the in-tree .so is current (it travels with the snapshot)
+    if world > 1:
+        dist.barrier()         # nobody loads the library before rank 0 has (re)built it
     B, T, N, desc = WORKLOADS[args.workload]
     peaks = load_peaks()
     variant = args.variant
