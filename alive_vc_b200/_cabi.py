@@ -27,7 +27,8 @@ EXPORTS = [
     "alive_knn_search", "alive_knn_prune", "alive_knn_rescore", "alive_knn_exact_workspace_bytes",
     "alive_knn_exact", "alive_knn_merge", "alive_knn_gather_mean", "alive_knn_gather_rows",
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
-    "alive_knn_finish",
+    "alive_knn_finish", "alive_knn_gather_mean_peers", "alive_knn_ipc_export", "alive_knn_ipc_open",
+    "alive_knn_ipc_close",
 ]
 
 
@@ -127,6 +128,14 @@ def _declare(lib):
     lib.alive_knn_mean_blend.argtypes = [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp]
     lib.alive_knn_scatter_grad.restype = ctypes.c_int
     lib.alive_knn_scatter_grad.argtypes = [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _i64, _vp]
+    lib.alive_knn_gather_mean_peers.restype = ctypes.c_int
+    lib.alive_knn_gather_mean_peers.argtypes = [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _f32, _vp, _vp]
+    lib.alive_knn_ipc_export.restype = ctypes.c_int
+    lib.alive_knn_ipc_export.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_i64)]
+    lib.alive_knn_ipc_open.restype = ctypes.c_int
+    lib.alive_knn_ipc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(_vp)]
+    lib.alive_knn_ipc_close.restype = ctypes.c_int
+    lib.alive_knn_ipc_close.argtypes = [_vp]
     lib.alive_knn_match_layout.restype = ctypes.c_int
     lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
     lib.alive_knn_match.restype = ctypes.c_int

@@ -1,6 +1,7 @@
 // Error plumbing and version of the alive_knn C ABI.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -139,5 +140,52 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
                          exact_ws, top_score, top_idx, alpha, out, stream);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA IPC helpers for the peer-memory gather (one process per GPU on one NVLink box): export
+// the allocation that contains a device pointer, open another process's export.  The mapping is
+// made in the CURRENT device's context with lazy peer access - no context is created on the
+// peer GPU in this process.
+// ---------------------------------------------------------------------------------------------
+extern "C" int alive_knn_ipc_export(const void* dev_ptr, uint8_t* handle64_host, int64_t* offset_host) {
+  using namespace alive;
+  ALIVE_REQUIRE(dev_ptr && handle64_host && offset_host, "alive_knn_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+  static GetRangeFn get_range = nullptr;
+  if (!get_range) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ALIVE_CHECK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q));
+    ALIVE_REQUIRE(q == cudaDriverEntryPointSuccess && fp, "cuMemGetAddressRange entry point not available");
+    get_range = reinterpret_cast<GetRangeFn>(fp);
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int rc = get_range(&base, &size, reinterpret_cast<unsigned long long>(dev_ptr));
+  ALIVE_REQUIRE(rc == 0, "cuMemGetAddressRange failed with CUresult %d", rc);
+  cudaIpcMemHandle_t h;
+  ALIVE_CHECK_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle64_host, &h, 64);
+  *offset_host = static_cast<int64_t>(reinterpret_cast<unsigned long long>(dev_ptr) - base);
+  return 0;
+}
+
+extern "C" int alive_knn_ipc_open(const uint8_t* handle64_host, void** base_out_host) {
+  using namespace alive;
+  ALIVE_REQUIRE(handle64_host && base_out_host, "alive_knn_ipc_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, 64);
+  void* p = nullptr;
+  ALIVE_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *base_out_host = p;
+  return 0;
+}
+
+extern "C" int alive_knn_ipc_close(void* base) {
+  using namespace alive;
+  if (base) ALIVE_CHECK_CUDA(cudaIpcCloseMemHandle(base));
   return 0;
 }

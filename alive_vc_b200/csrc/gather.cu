@@ -72,6 +72,42 @@ __global__ void mean_blend_kernel(const float* __restrict__ rows, int t, int k, 
   *reinterpret_cast<float4*>(out + static_cast<size_t>(q) * d + j) = finish4(acc, static_cast<float>(k), a1, qv, a0);
 }
 
+// Sharded gather over PEER memory: shard r of the raw library lives on GPU r and is mapped into
+// this process (CUDA IPC over NVLink); frame i belongs to the shard with bounds[r] <= i < bounds[r+1].
+// Same arithmetic as gather_mean_kernel, so every rank computes the bit-identical result without
+// any collective after the top-k merge.
+__global__ void gather_mean_peers_kernel(const float* const* __restrict__ shard_raw,
+                                         const long long* __restrict__ bounds, int shards, int d,
+                                         const long long* __restrict__ top_idx, int t, int k,
+                                         const float* __restrict__ q_raw, float a1, float a0,
+                                         float* __restrict__ out) {
+  const int q = blockIdx.x;
+  const int j = threadIdx.x * 4;
+  if (j >= d) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r0 = 0; r0 < k; r0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (r0 + u < k) {
+        long long idx = top_idx[static_cast<size_t>(q) * k + r0 + u];
+        const long long n_total = bounds[shards];
+        idx = idx < 0 ? 0 : (idx >= n_total ? n_total - 1 : idx);
+        int s = 0;
+        while (s + 1 < shards && idx >= bounds[s + 1]) ++s;
+        const float* base = shard_raw[s];
+        v[u] = *reinterpret_cast<const float4*>(base + static_cast<size_t>(idx - bounds[s]) * d + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (r0 + u < k) acc = (r0 + u == 0) ? v[u] : add4(acc, v[u]);
+    }
+  }
+  const float4 qv = *reinterpret_cast<const float4*>(q_raw + static_cast<size_t>(q) * d + j);
+  *reinterpret_cast<float4*>(out + static_cast<size_t>(q) * d + j) = finish4(acc, static_cast<float>(k), a1, qv, a0);
+}
+
 __global__ void scatter_grad_kernel(const float* __restrict__ grad_out, const long long* __restrict__ top_idx,
                                     int t, int k, int d, float scale, float* __restrict__ grad_rows, long long n) {
   const int qr = blockIdx.x;   // q*k + r
@@ -134,6 +170,23 @@ extern "C" int alive_knn_scatter_grad(const float* grad_out, const int64_t* top_
   if (t <= 0) return 0;
   scatter_grad_kernel<<<t * k, 256, 0, as_stream(stream)>>>(grad_out, reinterpret_cast<const long long*>(top_idx), t, k, d,
                                                              scale, grad_rows, n);
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int alive_knn_gather_mean_peers(const float* const* shard_raw, const int64_t* bounds, int32_t shards,
+                                           int32_t d, const int64_t* top_idx, int32_t t, int32_t k, const float* q_raw,
+                                           float alpha, float* out, alive_stream_t stream) {
+  using namespace alive;
+  ALIVE_REQUIRE(shard_raw && bounds && top_idx && q_raw && out, "alive_knn_gather_mean_peers: NULL argument");
+  ALIVE_REQUIRE(shards >= 1 && shards <= 64, "alive_knn_gather_mean_peers: shards must be in [1,64]");
+  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 4096, "alive_knn_gather_mean_peers: d must be a multiple of 4, <= 4096");
+  ALIVE_REQUIRE(k >= 1, "alive_knn_gather_mean_peers: bad k");
+  if (t <= 0) return 0;
+  const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
+  gather_mean_peers_kernel<<<t, threads_for(d), 0, as_stream(stream)>>>(
+      shard_raw, reinterpret_cast<const long long*>(bounds), shards, d, reinterpret_cast<const long long*>(top_idx), t, k,
+      q_raw, a1, alpha, out);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

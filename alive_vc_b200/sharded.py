@@ -107,6 +107,65 @@ class CudaShardBackend:
         return out
 
 
+class PeerShards:
+    """Every rank's raw [n_r, D] shard mapped into this process through CUDA IPC (NVLink peer
+    memory), so the final gather can read the k winning frames of each query wherever they live:
+    one kernel, no collective after the top-k merge (alive_knn_gather_mean_peers)."""
+
+    def __init__(self, local: M.PackedFrames, n_total: int, group=None):
+        import ctypes
+        c = _cabi.load()
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        dev = local.device
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64(0)
+        if local.n > 0:
+            _cabi.check(c.alive_knn_ipc_export(local.raw.data_ptr(), handle, ctypes.byref(off)), "alive_knn_ipc_export")
+        # exchange (handle, byte offset, rows, row_base) as a small byte tensor over the group
+        mine = torch.zeros(64 + 24, dtype=torch.uint8)
+        mine[:64] = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8)
+        mine[64:] = torch.tensor([off.value, local.n, local.row_base], dtype=torch.int64).view(torch.uint8)
+        everyone = torch.empty((world, 64 + 24), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine.to(dev), group=group)
+        everyone = everyone.cpu()
+        self._opened = []
+        ptrs, bounds = [], []
+        for r in range(world):
+            meta = everyone[r, 64:].view(torch.int64).tolist()
+            r_off, r_n, r_base = meta
+            bounds.append(r_base)
+            if r == rank or r_n == 0:
+                ptrs.append(local.raw.data_ptr() if r == rank else 0)
+                continue
+            base = ctypes.c_void_p(0)
+            _cabi.check(c.alive_knn_ipc_open(bytes(everyone[r, :64].tolist()), ctypes.byref(base)), "alive_knn_ipc_open")
+            self._opened.append(base.value)
+            ptrs.append(base.value + r_off)
+        bounds.append(n_total)
+        self.shards = world
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.bounds = torch.tensor(bounds, dtype=torch.int64, device=dev)
+        self._keep = local          # the exporting side must keep its allocation alive
+        dist.barrier(group=group)
+
+    def gather_mean(self, top_idx, q_raw, alpha, d):
+        t, k = top_idx.shape
+        out = torch.empty((t, d), dtype=torch.float32, device=top_idx.device)
+        rc = _cabi.load().alive_knn_gather_mean_peers(self.ptrs.data_ptr(), self.bounds.data_ptr(), self.shards, d,
+                                                      top_idx.data_ptr(), t, k, q_raw.data_ptr(), float(alpha),
+                                                      out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "alive_knn_gather_mean_peers")
+        M._count(1)
+        return out
+
+    def close(self):
+        c = _cabi.load()
+        for b in self._opened:
+            c.alive_knn_ipc_close(b)
+        self._opened = []
+
+
 class _Queries:
     def __init__(self, source):
         self.source = source
@@ -117,14 +176,18 @@ class _Queries:
 class ShardedLibrary:
     """A voice library whose frames are split by rows over the ranks of `group`."""
 
-    def __init__(self, backend, n_local: int, row_base: int, n_total: int, group=None):
+    def __init__(self, backend, n_local: int, row_base: int, n_total: int, group=None, peer_memory: bool = False):
         self.backend = backend
+        self.peers = None
         self.n_local = n_local
         self.row_base = row_base
         self.n_total = n_total
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if peer_memory and self.world > 1:
+            # raw shards of every rank mapped over NVLink (CUDA IPC): the gather needs no collective
+            self.peers = PeerShards(backend.local, n_total, group)
 
     def _reduce_scatter_ok(self) -> bool:
         """reduce_scatter_tensor exists on NCCL; gloo (CPU tests) keeps the all-reduce form."""
@@ -135,20 +198,21 @@ class ShardedLibrary:
 
     @classmethod
     def from_local_frames(cls, frames_dn: torch.Tensor, row_base: int, n_total: int, group=None,
-                          mode: str = "auto", variant: int = 0):
+                          mode: str = "auto", variant: int = 0, peer_memory: bool = False):
         """`frames_dn` [D, n_local]: this rank's frames, global rows [row_base, row_base+n_local)."""
         local = M.pack_frames(frames_dn)
         local.row_base = row_base
-        return cls(CudaShardBackend(local, mode, variant), local.n, row_base, n_total, group)
+        return cls(CudaShardBackend(local, mode, variant), local.n, row_base, n_total, group, peer_memory)
 
     @classmethod
-    def from_full(cls, reference: torch.Tensor, group=None, mode: str = "auto", variant: int = 0):
+    def from_full(cls, reference: torch.Tensor, group=None, mode: str = "auto", variant: int = 0,
+                  peer_memory: bool = False):
         """Every rank passes the same [1, D, N] library; each keeps only its row range."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         ref = reference[0] if reference.dim() == 3 else reference
         lo, hi = shard_bounds(ref.shape[1], world, rank)
-        return cls.from_local_frames(ref[:, lo:hi], lo, ref.shape[1], group, mode, variant)
+        return cls.from_local_frames(ref[:, lo:hi], lo, ref.shape[1], group, mode, variant, peer_memory)
 
     def match(self, source: torch.Tensor, k: int = 4, alpha: float = 0.0, return_indices: bool = False):
         """Same contract as match_features(source, whole_library): source [B, D, T] replicated
@@ -186,6 +250,15 @@ class ShardedLibrary:
             dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
             # 3. merge
             top_s, top_i = be.merge(all_s.view(self.world, t, k), all_i.view(self.world, t, k), k)
+        if self.peers is not None:
+            # 4'. one kernel reads the k winning frames of every query from whichever GPU owns them
+            if q.raw is None:
+                q.raw = M.pack_queries(q.source).raw
+            out_rows = self.peers.gather_mean(top_i, q.raw, alpha, D)
+            out = out_rows.view(B, T, D).transpose(1, 2)
+            if out.dtype != source.dtype:
+                out = out.to(source.dtype)
+            return (out, top_i.view(B, T, k)) if return_indices else out
         # 4. owned rows, zeros elsewhere;  5. exact sum over ranks;  6. mean + blend
         rows = be.gather_rows(top_i)
         if self.world > 1 and self._reduce_scatter_ok():

@@ -298,7 +298,8 @@ def gpu_arm(args):
     else:
         lo, hi = shard_bounds(N, world, rank)
         lib = build_library(lo, hi, args.seed, dev)
-        sharded = ShardedLibrary(CudaShardBackend(lib, "screen", variant), lib.n, lo, N, None)
+        sharded = ShardedLibrary(CudaShardBackend(lib, "screen", variant), lib.n, lo, N, None,
+                                 peer_memory=(args.exchange == "peer"))
         src_dev = torch.randn(B, D, T, device=dev, generator=g)
         if world > 1:
             dist.broadcast(src_dev, 0)
@@ -314,7 +315,10 @@ def gpu_arm(args):
         units_per_step = B * T
         n_local = hi - lo
         scaling = "strong"
-        parallelism = f"library rows sharded x{world}" + (", all-gather top-k + reduce-scatter rows + all-gather result" if world > 1 else "")
+        parallelism = f"library rows sharded x{world}" + (
+            "" if world == 1 else
+            ", all-gather top-k + one peer-memory (NVLink) gather kernel" if args.exchange == "peer" else
+            ", all-gather top-k + reduce-scatter rows + all-gather result")
     src_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
     src_host.copy_(src_dev)
     out_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
@@ -462,6 +466,8 @@ def main():
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="cfg2: do not use the CUDA-graph streaming matcher")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="multi-GPU row exchange: NCCL reduce-scatter/all-gather, or one gather kernel over CUDA-IPC peer memory")
     ap.add_argument("--torch-eager", action="store_true",
                     help="also time the reference's torch ops on the GPU (secondary line, where it fits)")
     args = ap.parse_args()

@@ -162,6 +162,22 @@ int alive_knn_gather_rows(const float* lib_raw, int64_t n, int32_t d, int64_t ro
 int alive_knn_mean_blend(const float* rows, int32_t t, int32_t k, int32_t d, const float* q_raw,
                          float alpha, float* out, alive_stream_t stream);
 
+/* Sharded variant over PEER memory (NVLink, CUDA IPC): shard_raw[r] (device array of `shards`
+ * device pointers, each mapped into this process) holds frames bounds[r] .. bounds[r+1]-1
+ * (bounds: device array of shards+1 int64).  Same arithmetic as alive_knn_gather_mean: every
+ * rank computes the full, bit-identical [t,d] result with no collective after the merge. */
+int alive_knn_gather_mean_peers(const float* const* shard_raw, const int64_t* bounds, int32_t shards,
+                                int32_t d, const int64_t* top_idx, int32_t t, int32_t k,
+                                const float* q_raw, float alpha, float* out, alive_stream_t stream);
+
+/* CUDA IPC plumbing for the peer-memory gather (host-side; one process per GPU, same box):
+ * export the allocation containing dev_ptr (64-byte handle + byte offset of dev_ptr inside it),
+ * open / close a handle exported by another process (mapped into the current device's context
+ * with lazy peer access; the returned pointer is the allocation BASE). */
+int alive_knn_ipc_export(const void* dev_ptr, uint8_t* handle64_host, int64_t* offset_host);
+int alive_knn_ipc_open(const uint8_t* handle64_host, void** base_out_host);
+int alive_knn_ipc_close(void* base);
+
 /* Backward of VoiceLibrary.match w.r.t. tokens (voice_library.py:31-33 under
  * autograd): grad_rows[top_idx[t,j],:] += scale * grad_out[t,:], scale=(1-alpha)/k.
  * grad_rows [n,d] float32 must be zeroed by the caller. */

@@ -29,10 +29,19 @@ def main():
         g = torch.Generator(device=dev).manual_seed(123)
         src = torch.randn(B, 768, T, device=dev, generator=g)
         ref = torch.randn(1, 768, N, device=dev, generator=g)
-        lib = ShardedLibrary.from_full(ref, mode="auto")
-        out, idx = lib.match(src, k, alpha, return_indices=True)
         want, widx = A.match_features(src, ref.expand(B, -1, -1), k, alpha, return_indices=True)
-        same = torch.equal(out, want) and torch.equal(idx, widx)
+        same = True
+        for peer in (False, True):
+            lib = ShardedLibrary.from_full(ref, mode="auto", peer_memory=peer)
+            out, idx = lib.match(src, k, alpha, return_indices=True)
+            ok = torch.equal(out, want) and torch.equal(idx, widx)
+            if not ok and rank == 0:
+                print(f"   MISMATCH with peer_memory={peer}", flush=True)
+            same = same and ok
+            if lib.peers is not None:
+                torch.cuda.synchronize()
+                dist.barrier()
+                lib.peers.close()
         flag = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
