@@ -120,20 +120,24 @@ class PeerShards:
         dev = local.device
         handle = ctypes.create_string_buffer(64)
         off = ctypes.c_int64(0)
-        if local.n > 0:
-            _cabi.check(c.alive_knn_ipc_export(local.raw.data_ptr(), handle, ctypes.byref(off)), "alive_knn_ipc_export")
-        # exchange (handle, byte offset, rows, row_base) as a small byte tensor over the group
-        mine = torch.zeros(64 + 24, dtype=torch.uint8)
+        export_error = ""
+        if local.n > 0 and c.alive_knn_ipc_export(local.raw.data_ptr(), handle, ctypes.byref(off)) != 0:
+            export_error = c.alive_knn_last_error().decode("utf-8", "replace")
+        # exchange (handle, byte offset, rows, row_base, export ok) as a small byte tensor over the
+        # group - every rank takes part in this collective even if its own export failed
+        mine = torch.zeros(64 + 32, dtype=torch.uint8)
         mine[:64] = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8)
-        mine[64:] = torch.tensor([off.value, local.n, local.row_base], dtype=torch.int64).view(torch.uint8)
-        everyone = torch.empty((world, 64 + 24), dtype=torch.uint8, device=dev)
+        mine[64:] = torch.tensor([off.value, local.n, local.row_base, 0 if export_error else 1],
+                                 dtype=torch.int64).view(torch.uint8)
+        everyone = torch.empty((world, 64 + 32), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(everyone, mine.to(dev), group=group)
         everyone = everyone.cpu()
+        if not all(int(everyone[r, 64:].view(torch.int64)[3]) == 1 for r in range(world)):
+            raise RuntimeError("CUDA IPC export failed on at least one rank" + (f": {export_error}" if export_error else ""))
         self._opened = []
         ptrs, bounds = [], []
         for r in range(world):
-            meta = everyone[r, 64:].view(torch.int64).tolist()
-            r_off, r_n, r_base = meta
+            r_off, r_n, r_base, _ = everyone[r, 64:].view(torch.int64).tolist()
             bounds.append(r_base)
             if r == rank or r_n == 0:
                 ptrs.append(local.raw.data_ptr() if r == rank else 0)
@@ -147,7 +151,6 @@ class PeerShards:
         self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
         self.bounds = torch.tensor(bounds, dtype=torch.int64, device=dev)
         self._keep = local          # the exporting side must keep its allocation alive
-        dist.barrier(group=group)
 
     def gather_mean(self, top_idx, q_raw, alpha, d):
         t, k = top_idx.shape
@@ -186,8 +189,20 @@ class ShardedLibrary:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if peer_memory and self.world > 1:
-            # raw shards of every rank mapped over NVLink (CUDA IPC): the gather needs no collective
-            self.peers = PeerShards(backend.local, n_total, group)
+            # raw shards of every rank mapped over NVLink (CUDA IPC): the gather needs no collective.
+            # Either every rank maps every peer or all of them use the NCCL exchange (never a mix).
+            try:
+                peers = PeerShards(backend.local, n_total, group)
+                ok = 1
+            except RuntimeError as e:          # e.g. an allocator whose blocks cannot be exported
+                peers, ok = None, 0
+                self.peer_error = str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=backend.local.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.peers = peers
+            elif peers is not None:
+                peers.close()
 
     def _reduce_scatter_ok(self) -> bool:
         """reduce_scatter_tensor exists on NCCL; gloo (CPU tests) keeps the all-reduce form."""
