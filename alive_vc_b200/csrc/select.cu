@@ -788,7 +788,10 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
                       (staged ? static_cast<size_t>(entries) * 8 : 0);
   static bool attr_done = false;
-  static int variant = 256;   // 256 threads x 4 CTAs per SM (64 registers): latency-bound, occupancy helps
+  // 0 = by batch size: 256 threads x 4 CTAs/SM finishes a small batch soonest (latency), 128 threads
+  // x 8 CTAs/SM keeps more queries in flight once the batch spans many waves (measured at T = 10k:
+  // 360 -> 286 us); ALIVE_KNN_FINISH_THREADS=128|256 forces one
+  static int variant = 0;
   if (!attr_done) {
     ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
     ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
@@ -802,7 +805,8 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
   finish_kernel<TH, B><<<t, TH, smem, as_stream(stream)>>>(                                                          \
       cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1, \
       alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged)
-  if (variant == 128) ALIVE_LAUNCH_FINISH(128, 8);
+  const int threads = variant == 128 || variant == 256 ? variant : (t >= 4096 ? 128 : 256);
+  if (threads == 128) ALIVE_LAUNCH_FINISH(128, 8);
   else ALIVE_LAUNCH_FINISH(256, 4);
 #undef ALIVE_LAUNCH_FINISH
   ALIVE_CHECK_CUDA(cudaGetLastError());
