@@ -37,11 +37,21 @@ __global__ void gather_mean_kernel(const float* __restrict__ lib_raw, long long 
   const int j = threadIdx.x * 4;
   if (j >= d) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = 0; r < k; ++r) {
-    long long idx = top_idx[static_cast<size_t>(q) * k + r];
-    idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);   // never read out of bounds
-    const float4 v = *reinterpret_cast<const float4*>(lib_raw + static_cast<size_t>(idx) * d + j);
-    acc = (r == 0) ? v : add4(acc, v);
+  for (int r0 = 0; r0 < k; r0 += 8) {
+    // all (up to 8) row loads are issued before the order-preserving sequential sum
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (r0 + u < k) {
+        long long idx = top_idx[static_cast<size_t>(q) * k + r0 + u];
+        idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);   // never read out of bounds
+        v[u] = *reinterpret_cast<const float4*>(lib_raw + static_cast<size_t>(idx) * d + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (r0 + u < k) acc = (r0 + u == 0) ? v[u] : add4(acc, v[u]);
+    }
   }
   const float4 qv = *reinterpret_cast<const float4*>(q_raw + static_cast<size_t>(q) * d + j);
   *reinterpret_cast<float4*>(out + static_cast<size_t>(q) * d + j) = finish4(acc, static_cast<float>(k), a1, qv, a0);

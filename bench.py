@@ -306,8 +306,9 @@ def gpu_arm(args):
 
         def step(src):
             return sharded.match(src, K, 0.0)
-        if args.workload == "cfg2" and world == 1 and not args.no_graph:
-            # streaming chunk: fixed shape, pre-allocated, the whole pipeline replayed as one CUDA graph
+        if args.workload in ("cfg1", "cfg2") and world == 1 and not args.no_graph:
+            # fixed-shape chunks (inference.py / realtime_inference.py call the match once per chunk with
+            # the same T): pre-allocated buffers, the whole pipeline replayed as one CUDA graph
             streamer = M.StreamingMatcher(lib, T, K, 0.0, batch=B, mode="screen", variant=variant)
 
             def step(src):                                             # noqa: F811
@@ -371,7 +372,7 @@ def gpu_arm(args):
     value = units_per_step / (ms_per_step * 1e-3)
 
     # ---- end-to-end: host buffers through the public API ----
-    streaming = args.workload == "cfg2" and world == 1 and not args.no_graph
+    streaming = args.workload in ("cfg1", "cfg2") and world == 1 and not args.no_graph
 
     def e2e_step():
         # the streaming matcher copies the pinned host chunk straight into its static input buffer
@@ -421,6 +422,35 @@ def gpu_arm(args):
                     "peak_kind": "sustained" if sustained else "burst", "peak_source": peaks["source"],
                     "frac_of_burst": achieved / peaks["bf16_burst"],
                     "frac_of_sustained": achieved / peaks["bf16_sustained"]}
+        # K4 alone (north_star: "fraction of HBM bandwidth for the gather"): the standalone gather-mean
+        # kernel on this step's own neighbour indices; in the pipeline the same arithmetic is fused
+        # into finish_kernel.  Algorithmic bytes per query frame: k*D*4 read + D*4 write (+ D*4 query).
+        gather_roof = None
+        if args.workload != "cfg5" and world == 1:
+            info = M.last_info
+            ws = getattr(info, "_workspace", None)
+            if ws is not None:
+                rows = B * T
+                q_view = M.PackedFrames(n=rows, d=D, raw=ws[: rows * D * 4].view(torch.float32).view(rows, D),
+                                        norms=None, packed=None, err=None, stats=None)
+                _, g_idx, _ = M.run_match(src_dev, lib, K, 0.0, "screen", variant, want_out=False)
+                g_out = torch.empty((rows, D), dtype=torch.float32, device=dev)
+                for _ in range(3):
+                    M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
+                torch.cuda.synchronize()
+                ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 20
+                ge0.record()
+                for _ in range(reps):
+                    M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
+                ge1.record()
+                torch.cuda.synchronize()
+                g_ms = ge0.elapsed_time(ge1) / reps
+                g_bytes = rows * (K * D * 4 + D * 4 + D * 4)
+                gather_roof = {"bound": "hbm", "kernel": "gather_mean_kernel", "achieved": g_bytes / (g_ms * 1e-3) / 1e9,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                               "avg_kernel_ms": g_ms, "bytes_per_query_frame": g_bytes // rows,
+                               "note": "standalone K4 on this step's indices; random 3 KB rows of the raw library"}
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = run_cpu_arm(args.workload, 3, 1)
@@ -436,7 +466,9 @@ def gpu_arm(args):
                        "l2": "library (bf16 %.1f GB per GPU) is far larger than L2, no flush needed"
                              % (n_local * D * 2 / 1e9) if n_local * D * 2 > 256e6 else
                              "library smaller than 2x L2: numbers are warm-L2 steady state of a resident library",
-                       "variant": variant, "fallback_queries_last_step": fallback},
+                       "variant": variant, "fallback_queries_last_step": fallback,
+                       "api": "StreamingMatcher (one CUDA graph per chunk)" if streaming else
+                              ("match_packed per speaker" if args.workload == "cfg5" else "ShardedLibrary.match")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "query_frames/s", "h2d_bytes_per_step": io_bytes,
                     "d2h_bytes_per_step": io_bytes, "ms_per_step": e2e_ms / args.steps},
@@ -446,6 +478,8 @@ def gpu_arm(args):
         }
         if eager is not None:
             line["torch_eager_gpu"] = eager
+        if gather_roof is not None:
+            line["roofline_gather"] = gather_roof
         if lat:
             line["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                                   "min": lat[0]}
@@ -465,7 +499,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="0 default, 1 = cta_group::1, 2 = CTA pair")
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-graph", action="store_true", help="cfg2: do not use the CUDA-graph streaming matcher")
+    ap.add_argument("--no-graph", action="store_true", help="cfg1/cfg2: do not use the CUDA-graph streaming matcher")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                     help="multi-GPU row exchange: NCCL reduce-scatter/all-gather, or one gather kernel over CUDA-IPC peer memory")
     ap.add_argument("--torch-eager", action="store_true",
