@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 # every symbol include/alive_knn.h declares
 EXPORTS = [
-    "alive_knn_last_error", "alive_knn_abi_version", "alive_knn_pack", "alive_knn_plan",
+    "alive_knn_last_error", "alive_knn_abi_version", "alive_knn_pack", "alive_knn_plan", "alive_knn_plan_batched",
     "alive_knn_search", "alive_knn_prune", "alive_knn_rescore", "alive_knn_exact_workspace_bytes",
     "alive_knn_exact", "alive_knn_merge", "alive_knn_gather_mean", "alive_knn_gather_rows",
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
@@ -38,7 +38,7 @@ class Plan(ctypes.Structure):
         ("t", ctypes.c_int32), ("n", ctypes.c_int64), ("d", ctypes.c_int32),
         ("ctas_per_unit", ctypes.c_int32), ("m_units", ctypes.c_int32), ("n_tiles", ctypes.c_int32),
         ("segments", ctypes.c_int32), ("tiles_per_segment", ctypes.c_int32), ("lists", ctypes.c_int32),
-        ("grid", ctypes.c_int32),
+        ("grid", ctypes.c_int32), ("items", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -50,6 +50,7 @@ class Library(ctypes.Structure):
     _fields_ = [
         ("packed", ctypes.c_void_p), ("raw", ctypes.c_void_p), ("norms", ctypes.c_void_p),
         ("stats", ctypes.c_void_p), ("n", ctypes.c_int64), ("d", ctypes.c_int32), ("row_base", ctypes.c_int64),
+        ("items", ctypes.c_int32),
     ]
 
 
@@ -104,6 +105,8 @@ def _declare(lib):
     lib.alive_knn_pack.argtypes = [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.alive_knn_plan.restype = ctypes.c_int
     lib.alive_knn_plan.argtypes = [_i32, _i64, _i32, _i32, _i32, ctypes.POINTER(Plan)]
+    lib.alive_knn_plan_batched.restype = ctypes.c_int
+    lib.alive_knn_plan_batched.argtypes = [_i32, _i32, _i64, _i32, _i32, _i32, ctypes.POINTER(Plan)]
     lib.alive_knn_search.restype = ctypes.c_int
     lib.alive_knn_search.argtypes = [_vp, _vp, ctypes.POINTER(Plan), _vp, _vp, _vp]
     lib.alive_knn_prune.restype = ctypes.c_int
@@ -111,13 +114,13 @@ def _declare(lib):
     lib.alive_knn_rescore.restype = ctypes.c_int
     lib.alive_knn_rescore.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]
     lib.alive_knn_exact_workspace_bytes.restype = ctypes.c_size_t
-    lib.alive_knn_exact_workspace_bytes.argtypes = [_i32, _i64, _i32]
+    lib.alive_knn_exact_workspace_bytes.argtypes = [_i32, _i64, _i32, _i32]
     lib.alive_knn_exact.restype = ctypes.c_int
     lib.alive_knn_exact.argtypes = [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _f32,
-                                    _vp, _vp]
+                                    _vp, _i32, _vp]
     lib.alive_knn_finish.restype = ctypes.c_int
     lib.alive_knn_finish.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64,
-                                     _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+                                     _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]
     lib.alive_knn_merge.restype = ctypes.c_int
     lib.alive_knn_merge.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]
     lib.alive_knn_gather_mean.restype = ctypes.c_int
@@ -137,7 +140,7 @@ def _declare(lib):
     lib.alive_knn_ipc_close.restype = ctypes.c_int
     lib.alive_knn_ipc_close.argtypes = [_vp]
     lib.alive_knn_match_layout.restype = ctypes.c_int
-    lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
+    lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
     lib.alive_knn_match.restype = ctypes.c_int
     lib.alive_knn_match.argtypes = [_vp, _i32, _i32, _i64, _i64, _i64, ctypes.POINTER(Library), _i32, _f32, _i32,
                                     _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -156,7 +159,7 @@ def load():
                     "(nvcc, sm_100a). alive_vc_b200 has no CPU or PyTorch fallback.")
             lib = ctypes.CDLL(LIB_PATH)
             _declare(lib)
-            if lib.alive_knn_abi_version() != 1:
+            if lib.alive_knn_abi_version() != 2:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")
             _lib = lib
     return _lib

@@ -39,7 +39,7 @@ int resolve_mode(int mode, int64_t n, int d, int k) {
 }
 
 int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t num_sms, int32_t variant, int mode,
-           alive_knn_plan_t* plan, int64_t* off) {
+           int32_t items, alive_knn_plan_t* plan, int64_t* off) {
   size_t cur = 0;
   auto take = [&](int slot, size_t bytes) {
     off[slot] = static_cast<int64_t>(cur);
@@ -51,7 +51,7 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
   take(kOffQErr, static_cast<size_t>(rows) * 4);
   size_t lists = 0;
   if (mode == 1) {
-    int rc = alive_knn_plan(rows, n, d, num_sms, variant, plan);
+    int rc = alive_knn_plan_batched(items, rows / items, n, d, num_sms, variant, plan);
     if (rc) return rc;
     lists = static_cast<size_t>(plan->lists);
   }
@@ -60,8 +60,8 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
   take(kOffSelIdx, mode == 1 ? static_cast<size_t>(rows) * r_max * 4 : 0);
   take(kOffSelN, static_cast<size_t>(rows) * 4);
   take(kOffFbList, static_cast<size_t>(rows) * 4);
-  take(kOffFbCount, 4);
-  take(kOffExact, alive_knn_exact_workspace_bytes(rows, n, k));
+  take(kOffFbCount, static_cast<size_t>(items) * 4);
+  take(kOffExact, alive_knn_exact_workspace_bytes(rows, n, k, items));
   off[kOffTotal] = static_cast<int64_t>(cur);
   return 0;
 }
@@ -70,12 +70,13 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
 }  // namespace alive
 
 extern "C" int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
-                                      int32_t num_sms, int32_t variant, int64_t* offsets12) {
+                                      int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets12) {
   using namespace alive;
   ALIVE_REQUIRE(offsets12 != nullptr, "alive_knn_match_layout: offsets is NULL");
   ALIVE_REQUIRE(rows >= 1 && n >= 1 && k >= 1 && k <= ALIVE_KNN_MAX_K, "alive_knn_match_layout: bad sizes");
+  ALIVE_REQUIRE(items >= 1 && rows % items == 0, "alive_knn_match_layout: rows must be a multiple of items");
   alive_knn_plan_t plan;
-  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), &plan, offsets12);
+  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets12);
 }
 
 extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
@@ -91,12 +92,16 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   ALIVE_REQUIRE(k <= ALIVE_KNN_MAX_K, "alive_knn_match: k must be <= %d", ALIVE_KNN_MAX_K);
   const int32_t rows = batch * t;
   const int32_t d = lib->d;
+  const int32_t items = lib->items < 1 ? 1 : lib->items;
+  ALIVE_REQUIRE(items == 1 || items == batch,
+                "alive_knn_match: a library of %d items needs a query batch of the same size (got %d)", items, batch);
+  ALIVE_REQUIRE(items == 1 || lib->row_base == 0, "alive_knn_match: batched items cannot be row-sharded");
   mode = resolve_mode(mode, lib->n, d, k);
   ALIVE_REQUIRE(mode == 1 || mode == 2, "alive_knn_match: mode must be 0 (auto), 1 (screen) or 2 (exact)");
   ALIVE_REQUIRE(mode == 2 || k <= ALIVE_KNN_LIST_LEN, "alive_knn_match: the screened path needs k <= %d", ALIVE_KNN_LIST_LEN);
   alive_knn_plan_t plan;
   int64_t off[12];
-  int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, &plan, off);
+  int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, items, &plan, off);
   if (rc) return rc;
   ALIVE_REQUIRE(static_cast<size_t>(off[kOffTotal]) <= workspace_bytes,
                 "alive_knn_match: workspace too small (%zu < %lld)", workspace_bytes, static_cast<long long>(off[kOffTotal]));
@@ -127,17 +132,17 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
     if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
     rc = alive_knn_finish(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
-                          lib->stats, lib->n, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
-                          fb_count, stream);
+                          lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
+                          fb_count, items, stream);
     if (rc) return rc;
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, fb_list, fb_count, lib->row_base,
-                         exact_ws, top_score, top_idx, alpha, out, stream);
+                         exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;
   } else {
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
-    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, 4, as_stream(stream)));
+    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, 4 * items, as_stream(stream)));
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
-                         exact_ws, top_score, top_idx, alpha, out, stream);
+                         exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;
   }
   return 0;

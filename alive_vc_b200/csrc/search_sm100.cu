@@ -58,8 +58,9 @@ template <int kCtas> struct Cfg {
 };
 
 struct SearchParams {
-  int t;
-  int n;
+  int items;           // independent problems laid out back to back (1 = plain)
+  int t;               // query frames per item
+  int n;               // library frames per item
   int k_blocks;        // d / 64
   int m_units;
   int segments;
@@ -351,7 +352,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const bool leader = cta_rank == 0;
   const int unit_stride = gridDim.x / kCtas;
   const int first_unit = blockIdx.x / kCtas;
-  const int total_units = p.m_units * p.segments;
+  const int units_per_item = p.m_units * p.segments;
+  const int total_units = units_per_item * p.items;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -386,11 +388,16 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       uint32_t it = 0;
       int my_tiles = 0, epoch = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
-        const int m_unit = unit % p.m_units;
-        const int seg = unit / p.m_units;
+        const int item = unit / units_per_item;
+        const int rem = unit - item * units_per_item;
+        const int m_unit = rem % p.m_units;
+        const int seg = rem / p.m_units;
         const int tile0 = seg * p.tiles_per_segment;
         const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
-        const int q_row = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+        // item i: query rows [i*t, (i+1)*t), library rows [i*n, (i+1)*n); rows of a tile that spill
+        // into the next item (or past the end: TMA zero fill) are masked in the epilogue
+        const int q_row = item * p.t + (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+        const int lib_row0 = item * p.n;
         for (int tile = tile0; tile < tile1; ++tile, ++my_tiles) {
           if (p.sync_ctr != nullptr && epoch < p.sync_rounds && my_tiles == (epoch + 1) * p.sync_every) {
             // Pacing, not correctness: CTAs that stream the same library segment drift apart (all of
@@ -406,7 +413,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             __syncwarp();
             ++epoch;
           }
-          const int lib_row = tile * kBlockN + static_cast<int>(cta_rank) * C::kBRows;
+          const int lib_row = lib_row0 + tile * kBlockN + static_cast<int>(cta_rank) * C::kBRows;
           for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
             const uint32_t stage = it % kStages;
             const uint32_t phase = (it / kStages) & 1u;
@@ -428,7 +435,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       constexpr uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN);
       uint32_t it = 0, tile_count = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
-        const int seg = unit / p.m_units;
+        const int seg = (unit % units_per_item) / p.m_units;
         const int tile0 = seg * p.tiles_per_segment;
         const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
         for (int tile = tile0; tile < tile1; ++tile, ++tile_count) {
@@ -468,12 +475,17 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                      (threadIdx.x - kFirstEpiWarp * 32);
     uint32_t tile_count = 0;
     for (int unit = first_unit; unit < total_units; unit += unit_stride) {
-      const int m_unit = unit % p.m_units;
-      const int seg = unit / p.m_units;
+      const int item = unit / units_per_item;
+      const int rem = unit - item * units_per_item;
+      const int m_unit = rem % p.m_units;
+      const int seg = rem / p.m_units;
       const int tile0 = seg * p.tiles_per_segment;
       const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
-      const int row = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
-      const bool row_valid = row < p.t;
+      const int row_in_item = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
+      const bool row_valid = row_in_item < p.t;
+      const int row = item * p.t + row_in_item;          // global query index
+      const int col_item0 = item * p.n;                  // frame indices are global: item*n + frame
+      const int n_valid = col_item0 + p.n;
 
       float s[kListLen];
       uint32_t id[kListLen];
@@ -489,7 +501,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
         tcgen05_fence_after();
         const uint32_t taddr = taddr_base + acc * kBlockN;
-        const int col0 = tile * kBlockN + half * 128;
+        const int col0 = col_item0 + tile * kBlockN + half * 128;
         if (p.debug == 2) {
           tcgen05_fence_before();
           __syncwarp();
@@ -513,7 +525,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               else mbar_arrive_cluster(tempty0 + 8 * acc);
             }
           }
-          if (p.debug == 0) scan_chunk(v, col0 + 32 * c, p.n, s, id, scratch);
+          if (p.debug == 0) scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
           else s[0] = fmaxf(s[0], __uint_as_float(v[0] ^ v[13] ^ v[31]));
         }
       }
@@ -596,11 +608,13 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
                   int32_t* cand_idx, cudaStream_t stream) {
   using C = Cfg<kCtas>;
   CUtensorMap mq, ml;
-  int rc = make_map(&mq, q, static_cast<uint64_t>(plan.t), static_cast<uint64_t>(plan.d), kBlockM);
+  const uint64_t items = static_cast<uint64_t>(plan.items < 1 ? 1 : plan.items);
+  int rc = make_map(&mq, q, items * static_cast<uint64_t>(plan.t), static_cast<uint64_t>(plan.d), kBlockM);
   if (rc) return rc;
-  rc = make_map(&ml, lib, static_cast<uint64_t>(plan.n), static_cast<uint64_t>(plan.d), C::kBRows);
+  rc = make_map(&ml, lib, items * static_cast<uint64_t>(plan.n), static_cast<uint64_t>(plan.d), C::kBRows);
   if (rc) return rc;
   SearchParams p;
+  p.items = static_cast<int>(items);
   p.t = plan.t;
   p.n = static_cast<int>(plan.n);
   p.k_blocks = plan.d / kBlockK;
@@ -631,11 +645,11 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
     p.sync_every = se ? atoi(se) : 128;   // measured at cfg4: DRAM reads 57 -> 23 GB per launch, +6.6 % throughput
     p.sync_ctr = nullptr;
     p.sync_rounds = 0;
-    const long long total_units = static_cast<long long>(plan.m_units) * plan.segments;
+    const long long total_units = static_cast<long long>(plan.m_units) * plan.segments * static_cast<long long>(items);
     const long long clusters = plan.grid / kCtas;
     const int last_seg_tiles = plan.n_tiles - (plan.segments - 1) * plan.tiles_per_segment;
     const long long min_tiles = (total_units / clusters) * (last_seg_tiles < plan.tiles_per_segment ? last_seg_tiles : plan.tiles_per_segment);
-    if (p.sync_every > 0 && plan.m_units > 1 && min_tiles / p.sync_every >= 1) {
+    if (p.sync_every > 0 && (plan.m_units > 1 || items > 1) && min_tiles / p.sync_every >= 1) {
       p.sync_ctr = pacing_slot(stream);
       p.sync_rounds = static_cast<int>(min_tiles / p.sync_every);
       if ((static_cast<long long>(p.sync_rounds) + 1) * plan.grid >= (1ll << 32)) p.sync_ctr = nullptr;
@@ -667,12 +681,15 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
 }  // namespace
 }  // namespace alive
 
-extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
-                              alive_knn_plan_t* plan) {
+extern "C" int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
+                                      alive_knn_plan_t* plan) {
   using namespace alive;
   ALIVE_REQUIRE(plan != nullptr, "alive_knn_plan: plan is NULL");
+  ALIVE_REQUIRE(items >= 1, "alive_knn_plan: items must be >= 1 (got %d)", items);
   ALIVE_REQUIRE(t >= 1, "alive_knn_plan: t must be >= 1 (got %d)", t);
   ALIVE_REQUIRE(n >= 1 && n < (1ll << 31) - 512, "alive_knn_plan: n out of range (%lld)", static_cast<long long>(n));
+  ALIVE_REQUIRE(static_cast<long long>(items) * n < (1ll << 31) - 512 && static_cast<long long>(items) * t < (1ll << 31) - 512,
+                "alive_knn_plan: items * n and items * t must stay below 2^31");
   ALIVE_REQUIRE(d >= 64 && d % 64 == 0 && d <= 8192, "alive_knn_plan: d must be a multiple of 64 (got %d)", d);
   ALIVE_REQUIRE(num_sms >= 2, "alive_knn_plan: num_sms must be >= 2");
   // default: the CTA-pair kernel (cta_group::2) once there is more than one 128-query tile - it
@@ -685,17 +702,19 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
   plan->t = t;
   plan->n = n;
   plan->d = d;
+  plan->items = items;
   plan->ctas_per_unit = ctas;
   plan->m_units = (t + kBlockM * ctas - 1) / (kBlockM * ctas);
   plan->n_tiles = static_cast<int32_t>((n + kBlockN - 1) / kBlockN);
-  // Segments: enough units to fill every SM, at least 16 per query group when the library is
-  // long (more, shorter lists make the completeness certificate easy), and as few idle
-  // tile-slots in the last wave as possible.
+  // Segments (per item): at least 16 when the library is long (more, shorter lists make the
+  // completeness certificate easy), enough units to fill every SM, and as few idle tile-slots in
+  // the last wave as possible.
   const int n_tiles = plan->n_tiles;
+  const long long mi = static_cast<long long>(plan->m_units) * items;    // query groups over all items
   // candidates: from 16 segments (enough lists for the certificate) up to 4x what fills the
   // machine; the cost model below picks the cheapest, ties go to FEWER segments (every unit start
   // pays for a cold top list in the epilogue)
-  const int s_fill = (slots + plan->m_units - 1) / plan->m_units;
+  const int s_fill = static_cast<int>((slots + mi - 1) / mi);
   int s_lo = 16;
   if (s_lo > n_tiles) s_lo = n_tiles;
   int s_hi = 4 * (s_fill > 16 ? s_fill : 16);
@@ -705,7 +724,7 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
   for (int s = s_lo; s <= s_hi; ++s) {
     const int tps = (n_tiles + s - 1) / s;
     const int s_eff = (n_tiles + tps - 1) / tps;
-    const long long units = static_cast<long long>(plan->m_units) * s_eff;
+    const long long units = mi * s_eff;
     const long long waves = (units + slots - 1) / slots;
     const long long cost = waves * tps;
     if (best_cost < 0 || cost < best_cost) {
@@ -716,9 +735,14 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
   plan->tiles_per_segment = best_tps;
   plan->segments = (n_tiles + best_tps - 1) / best_tps;
   plan->lists = plan->segments * 2;
-  const long long units = static_cast<long long>(plan->m_units) * plan->segments;
+  const long long units = mi * plan->segments;
   plan->grid = static_cast<int32_t>((units < slots ? units : slots) * ctas);
   return 0;
+}
+
+extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
+                              alive_knn_plan_t* plan) {
+  return alive_knn_plan_batched(1, t, n, d, num_sms, variant, plan);
 }
 
 extern "C" int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,

@@ -259,7 +259,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
               const unsigned int* __restrict__ lib_stats, long long n, int d, int r_max, long long idx_base,
               float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
               long long* __restrict__ top_idx, int* __restrict__ sel_n, int* __restrict__ fb_list,
-              int* __restrict__ fb_count, int staged) {
+              int* __restrict__ fb_count, int staged, int t_item) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qh = reinterpret_cast<float*>(smem_raw);                         // [d]
   long long* cid = reinterpret_cast<long long*>(qh + d);                  // [r_max]
@@ -385,7 +385,10 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
     if (threadIdx.x == 0) {
       const int count = s_count;
       sel_n[q] = count;
-      if (count < 0) fb_list[atomicAdd(fb_count, 1)] = q;
+      if (count < 0) {
+        const int item = q / t_item;                      // uncertified queries are listed per item
+        fb_list[static_cast<size_t>(item) * t_item + atomicAdd(&fb_count[item], 1)] = q;
+      }
     }
   }
   const int n_sel = s_count;
@@ -429,7 +432,17 @@ __global__ void __launch_bounds__(kEThreads)
 exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm, int t,
                      const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
                      int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
-                     float* __restrict__ part_score, long long* __restrict__ part_idx) {
+                     float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item) {
+  // blockIdx.y = item: its queries are q_list[item][..] (or [item*t_item, (item+1)*t_item) when no
+  // list is given) and its frames are rows [item*n, (item+1)*n) of lib_raw; t = queries PER ITEM
+  const int item = blockIdx.y;
+  if (q_list) q_list += static_cast<size_t>(item) * t_item;
+  if (q_count) q_count += item;
+  lib_raw += static_cast<size_t>(item) * n * d;
+  lib_norm += static_cast<size_t>(item) * n;
+  const long long item_row0 = static_cast<long long>(item) * n;
+  const int item_q0 = item * t_item;
+  const size_t item_slot0 = static_cast<size_t>(item) * ((t_item + kEQ - 1) / kEQ) * kEQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Qd = reinterpret_cast<double*>(smem_raw);                       // [kEK][kEQ]
   double* Rd = Qd + kEK * kEQ;                                            // [kEK][kER]
@@ -460,7 +473,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
     __syncthreads();
     if (threadIdx.x < kEQ) {
       const int slot = g0 + threadIdx.x;
-      const int q = slot < nq ? (q_list ? q_list[slot] : slot) : -1;
+      const int q = slot < nq ? (q_list ? q_list[slot] : item_q0 + slot) : -1;
       qids[threadIdx.x] = q;
       qnrm[threadIdx.x] = q >= 0 ? q_norm[q] : 1.f;
       lcount[threadIdx.x] = 0;
@@ -550,14 +563,14 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
           while (true) {
             const int cnt = lcount[ql];
             const int wpos = lworst[ql];
-            const bool want = pending && (cnt < k || score_better(s, row, my_s[wpos], my_i[wpos]));
+            const bool want = pending && (cnt < k || score_better(s, row + item_row0, my_s[wpos], my_i[wpos]));
             const unsigned m = __ballot_sync(0xffffffffu, want);
             if (m == 0) break;
             const int src = __ffs(static_cast<int>(m)) - 1;
             if (lane == src) {
               const int pos = cnt < k ? cnt : wpos;
               my_s[pos] = s;
-              my_i[pos] = row;
+              my_i[pos] = row + item_row0;              // global frame index
               if (cnt < k) lcount[ql] = cnt + 1;
               pending = false;
             }
@@ -599,7 +612,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
       // pad unused entries so the selector skips them
       for (int e = lcount[ql] + lane; e < k; e += 32) li[ql * k + e] = -1;
       __syncwarp();
-      const size_t o = (static_cast<size_t>(g0 + ql) * splits + split) * k;
+      const size_t o = ((item_slot0 + g0 + ql) * splits + split) * k;
       warp_select_topk(ls + ql * k, li + ql * k, k, k, part_score + o, part_idx + o, 0, lane);
     }
   }
@@ -610,13 +623,16 @@ exact_final_kernel(int t, int k, const int* __restrict__ q_list, const int* __re
                    const float* __restrict__ part_score, const long long* __restrict__ part_idx,
                    long long idx_base, float* __restrict__ top_score, long long* __restrict__ top_idx,
                    const float* __restrict__ lib_raw, long long n, int d, const float* __restrict__ q_raw,
-                   float a1, float a0, float* __restrict__ out) {
-  const int nq = q_count ? *q_count : t;
+                   float a1, float a0, float* __restrict__ out, int t_item) {
+  // blockIdx.y = item; t = queries PER ITEM; n = frames of ALL items (gather reads global indices)
+  const int item = blockIdx.y;
+  const int nq = q_count ? q_count[item] : t;
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (slot >= nq) return;
   const int lane = threadIdx.x & 31;
-  const int q = q_list ? q_list[slot] : slot;
-  const size_t o = static_cast<size_t>(slot) * splits * k;
+  const int q = q_list ? q_list[static_cast<size_t>(item) * t_item + slot] : item * t_item + slot;
+  const size_t item_slot0 = static_cast<size_t>(item) * ((t_item + kEQ - 1) / kEQ) * kEQ;
+  const size_t o = (item_slot0 + slot) * splits * k;
   warp_select_topk(part_score + o, part_idx + o, splits * k, k, top_score + static_cast<size_t>(q) * k,
                    top_idx + static_cast<size_t>(q) * k, idx_base, lane);
   if (out == nullptr) return;
@@ -701,18 +717,18 @@ extern "C" int alive_knn_rescore(const float* q_raw, const float* q_norm, int32_
   return 0;
 }
 
-extern "C" size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k) {
+extern "C" size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k, int32_t items) {
   using namespace alive;
-  if (t < 1 || k < 1) return 0;
+  if (t < 1 || k < 1 || items < 1) return 0;
   const int s = exact_splits(t, n, k);
-  const size_t groups = (static_cast<size_t>(t) + kEQ - 1) / kEQ;
-  return groups * kEQ * s * k * 12 + 256;
+  const size_t groups = (static_cast<size_t>(t / items) + kEQ - 1) / kEQ;      // per item
+  return static_cast<size_t>(items) * groups * kEQ * s * k * 12 + 256;
 }
 
 extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t, const float* lib_raw,
                                const float* lib_norm, int64_t n, int32_t d, int32_t k, const int32_t* q_list,
                                const int32_t* q_count, int64_t idx_base, void* workspace, float* top_score,
-                               int64_t* top_idx, float alpha, float* out, alive_stream_t stream) {
+                               int64_t* top_idx, float alpha, float* out, int32_t items, alive_stream_t stream) {
   using namespace alive;
   ALIVE_REQUIRE(q_raw && q_norm && lib_raw && lib_norm && workspace && top_score && top_idx,
                 "alive_knn_exact: NULL argument");
@@ -723,11 +739,14 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
   ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw)) & 15) == 0,
                 "alive_knn_exact: raw buffers must be 16-byte aligned");
   if (t <= 0) return 0;
+  ALIVE_REQUIRE(items >= 1 && t % items == 0, "alive_knn_exact: t must be a multiple of items");
+  ALIVE_REQUIRE(items == 1 || idx_base == 0, "alive_knn_exact: batched items cannot be row-sharded");
+  const int t_item = t / items;
   const int splits = exact_splits(t, n, k);
-  const size_t groups = (static_cast<size_t>(t) + kEQ - 1) / kEQ;
-  // workspace layout: part_idx [groups*kEQ*splits*k] int64, then part_score float
+  const size_t groups = (static_cast<size_t>(t_item) + kEQ - 1) / kEQ;          // per item
+  // workspace layout: part_idx [items*groups*kEQ*splits*k] int64, then part_score float
   long long* part_idx = reinterpret_cast<long long*>(workspace);
-  float* part_score = reinterpret_cast<float*>(part_idx + groups * kEQ * splits * k);
+  float* part_score = reinterpret_cast<float*>(part_idx + static_cast<size_t>(items) * groups * kEQ * splits * k);
   const size_t smem = static_cast<size_t>(kEK) * (kEQ + kER) * 8 + (static_cast<size_t>(kEQ) * kEScPitch + 1) * 4 +
                       static_cast<size_t>(kEQ) * k * 12 + 16;
   static bool attr_done = false;
@@ -737,17 +756,21 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
   }
   ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
   // at most ~4 waves of CTAs; the (group, split) items beyond that are reached grid-stride
-  const size_t items = groups * static_cast<size_t>(splits);
-  const unsigned grid = static_cast<unsigned>(items < 4 * 148 ? items : 4 * 148);
-  exact_partial_kernel<<<grid, kEThreads, smem, as_stream(stream)>>>(q_raw, q_norm, t, lib_raw, lib_norm, n, d, k, q_list,
-                                                                    q_count, splits, part_score, part_idx);
+  const size_t work = groups * static_cast<size_t>(splits);
+  size_t gx = (4 * 148 + items - 1) / items;
+  if (gx > work) gx = work;
+  if (gx < 1) gx = 1;
+  dim3 pgrid(static_cast<unsigned>(gx), static_cast<unsigned>(items));
+  exact_partial_kernel<<<pgrid, kEThreads, smem, as_stream(stream)>>>(q_raw, q_norm, t_item, lib_raw, lib_norm, n, d, k,
+                                                                     q_list, q_count, splits, part_score, part_idx, t_item);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   ALIVE_REQUIRE(out == nullptr || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && idx_base == 0),
                 "alive_knn_exact: gather needs a 16-byte aligned `out` and an unsharded library");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-  exact_final_kernel<<<(t + 3) / 4, 128, 0, as_stream(stream)>>>(t, k, q_list, q_count, splits, part_score, part_idx,
-                                                                 idx_base, top_score, reinterpret_cast<long long*>(top_idx),
-                                                                 lib_raw, n, d, q_raw, a1, alpha, out);
+  dim3 fgrid(static_cast<unsigned>((t_item + 3) / 4), static_cast<unsigned>(items));
+  exact_final_kernel<<<fgrid, 128, 0, as_stream(stream)>>>(t_item, k, q_list, q_count, splits, part_score, part_idx, idx_base,
+                                                           top_score, reinterpret_cast<long long*>(top_idx), lib_raw,
+                                                           n * items, d, q_raw, a1, alpha, out, t_item);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -770,19 +793,21 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
                                 const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
                                 const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
                                 int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx,
-                                int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, alive_stream_t stream) {
+                                int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, int32_t items,
+                                alive_stream_t stream) {
   using namespace alive;
   ALIVE_REQUIRE(cand_score && cand_idx && q_raw && q_norm && q_err && lib_raw && lib_norm && lib_stats && top_score &&
                     top_idx && sel_n && fb_list && fb_count,
                 "alive_knn_finish: NULL argument");
   ALIVE_REQUIRE(t >= 1 && lists >= 1, "alive_knn_finish: bad sizes");
+  ALIVE_REQUIRE(items >= 1 && t % items == 0, "alive_knn_finish: t must be a multiple of items");
   ALIVE_REQUIRE(k >= 1 && k <= kListLen, "alive_knn_finish: k must be in [1,%d] for the screened path (got %d)", kListLen, k);
   ALIVE_REQUIRE(r_max >= k && r_max <= kMaxRMax, "alive_knn_finish: r_max must be in [k,%d]", kMaxRMax);
   ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 8192, "alive_knn_finish: d must be a multiple of 4");
   ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "alive_knn_finish: raw/out buffers must be 16-byte aligned");
   ALIVE_REQUIRE(out == nullptr || idx_base == 0, "alive_knn_finish: gather needs an unsharded library");
-  ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), as_stream(stream)));
+  ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * items, as_stream(stream)));
   const int entries = lists * kListLen;
   const int staged = entries <= kFinishMaxStagedEntries ? 1 : 0;
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
@@ -804,7 +829,7 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
 #define ALIVE_LAUNCH_FINISH(TH, B)                                                                                   \
   finish_kernel<TH, B><<<t, TH, smem, as_stream(stream)>>>(                                                          \
       cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1, \
-      alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged)
+      alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items)
   const int threads = variant == 128 || variant == 256 ? variant : (t >= 4096 ? 128 : 256);
   if (threads == 128) ALIVE_LAUNCH_FINISH(128, 8);
   else ALIVE_LAUNCH_FINISH(256, 4);

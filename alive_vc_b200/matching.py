@@ -61,14 +61,19 @@ class PackedFrames:
     err: torch.Tensor        # [n]   float32, ||bf16(x/|x|) - x/|x|||_2
     stats: torch.Tensor      # [2]   int32 (uint32 bit patterns): max err, non-finite row count
     row_base: int = 0        # global index of frame 0 (sharded libraries)
+    items: int = 1           # > 1: `items` independent libraries of n // items frames each, back to back
     _handle: object = field(default=None, repr=False)
+
+    @property
+    def n_item(self) -> int:
+        return self.n // self.items
 
     def handle(self) -> "_cabi.Library":
         """alive_knn_library_t view of these buffers (rebuilt if row_base changed)."""
         h = self._handle
-        if h is None or h.row_base != self.row_base:
+        if h is None or h.row_base != self.row_base or h.items != self.items:
             h = _cabi.Library(self.packed.data_ptr(), self.raw.data_ptr(), self.norms.data_ptr(),
-                              self.stats.data_ptr(), self.n, self.d, self.row_base)
+                              self.stats.data_ptr(), self.n // self.items, self.d, self.row_base, self.items)
             self._handle = h
         return h
 
@@ -124,9 +129,26 @@ def pack_library(reference: torch.Tensor) -> PackedFrames:
     """[1, D, N] (or [D, N]) library tensor -> PackedFrames."""
     if reference.dim() == 3:
         if reference.shape[0] != 1:
-            raise RuntimeError("pack_library expects a single library [1, D, N]")
+            raise RuntimeError("pack_library expects a single library [1, D, N] (see pack_libraries)")
         reference = reference[0]
     return pack_frames(reference)
+
+
+def pack_libraries(reference: torch.Tensor) -> PackedFrames:
+    """[B, D, N] -> ONE PackedFrames holding B independent libraries of N frames back to back
+    (items = B): batch item b of a query tensor is matched against library b only, all of them in
+    a single launch (BASELINE cfg5; train_decoder.py:134-135's per-utterance libraries)."""
+    _require_cuda(reference, "reference")
+    if reference.dim() != 3:
+        raise RuntimeError("pack_libraries expects [B, D, N]")
+    if reference.dtype != torch.float32:
+        reference = reference.float()
+    B, D, N = reference.shape
+    out = alloc_packed(B * N, D, reference.device)
+    out.items = B
+    for b in range(B):
+        pack_into(out, b * N, reference[b])
+    return out
 
 
 # ---------------------------------------------------------------------------------------
@@ -209,6 +231,30 @@ def cached_pack(owner: torch.Tensor, frames_dn: torch.Tensor, tag=0) -> PackedFr
     return packed
 
 
+def cached_pack_many(owner: torch.Tensor, reference_bdn: torch.Tensor) -> PackedFrames:
+    """pack_libraries with the same invisible cache as cached_pack (keyed on the tensor object)."""
+    oid = (id(owner), "many")
+    ent = _pack_cache.get(oid)
+    key = _cache_key(owner)
+    if ent is not None:
+        ref, old_key, packed = ent
+        if ref() is owner and old_key == key:
+            return packed
+        del _pack_cache[oid]
+    packed = pack_libraries(reference_bdn)
+
+    def _drop(_ref, oid=oid):
+        _pack_cache.pop(oid, None)
+
+    try:
+        if len(_pack_cache) >= _PACK_CACHE_MAX:
+            del _pack_cache[next(iter(_pack_cache))]
+        _pack_cache[oid] = (weakref.ref(owner, _drop), key, packed)
+    except TypeError:
+        pass
+    return packed
+
+
 def clear_pack_cache():
     _pack_cache.clear()
 
@@ -226,7 +272,7 @@ class SearchInfo:
     launches: int = 0
 
     def fallback_queries(self) -> int:
-        return int(self.fb_count.item()) if self.fb_count is not None else 0
+        return int(self.fb_count.sum().item()) if self.fb_count is not None else 0
 
 
 last_info: Optional[SearchInfo] = None
@@ -258,13 +304,13 @@ def exact_topk(q: PackedFrames, lib: PackedFrames, k: int, top_score=None, top_i
     if top_score is None:
         top_score = torch.empty((t, k), dtype=torch.float32, device=dev)
         top_idx = torch.empty((t, k), dtype=torch.int64, device=dev)
-    ws_bytes = c.alive_knn_exact_workspace_bytes(t, lib.n, k)
+    ws_bytes = c.alive_knn_exact_workspace_bytes(t, lib.n, k, 1)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     rc = c.alive_knn_exact(q.raw.data_ptr(), q.norms.data_ptr(), t, lib.raw.data_ptr(), lib.norms.data_ptr(),
                            lib.n, lib.d, k,
                            q_list.data_ptr() if q_list is not None else None,
                            q_count.data_ptr() if q_count is not None else None,
-                           lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), 0.0, None,
+                           lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), 0.0, None, 1,
                            _stream_ptr())
     _cabi.check(rc, "alive_knn_exact")
     _count(2)
@@ -357,7 +403,8 @@ _MODES = {"auto": 0, "screen": 1, "exact": 2}
 
 def _layout(rows: int, lib: PackedFrames, k: int, r_max: int, mode: int, variant: int, device):
     off = (ctypes.c_int64 * 12)()
-    rc = _cabi.load().alive_knn_match_layout(rows, lib.n, lib.d, k, r_max, mode, _num_sms(device), variant, off)
+    rc = _cabi.load().alive_knn_match_layout(rows, lib.n_item, lib.d, k, r_max, mode, _num_sms(device), variant,
+                                             lib.items, off)
     _cabi.check(rc, "alive_knn_match_layout")
     return list(off)
 
@@ -373,17 +420,19 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
     B, D, T = source.shape
     if D != lib.d:
         raise RuntimeError(f"feature dims differ: queries {D}, library {lib.d}")
-    if not isinstance(k, int) or k < 1 or k > lib.n:
+    if not isinstance(k, int) or k < 1 or k > lib.n_item:
         raise RuntimeError("selected index k out of range")   # torch.topk's message (common.py:105)
     if k > MAX_K:
         raise RuntimeError(f"alive_vc_b200 supports k <= {MAX_K} (got {k})")
+    if lib.items > 1 and lib.items != B:
+        raise RuntimeError(f"a packed set of {lib.items} libraries needs a query batch of {lib.items} (got {B})")
     _require_cuda(source, "source")
     assert source.dtype == torch.float32
     dev = source.device
     rows = B * T
     m = _MODES[mode]
     if m == 0:
-        m = 2 if (k > LIST_LEN or lib.n < EXACT_BELOW_N or lib.d % 64 != 0) else 1
+        m = 2 if (k > LIST_LEN or lib.n_item < EXACT_BELOW_N or lib.d % 64 != 0) else 1
     off = _layout(rows, lib, k, r_max, m, variant, dev)
     if workspace is None:
         workspace = torch.empty((off[11],), dtype=torch.uint8, device=dev)
@@ -408,7 +457,7 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
     _cabi.check(rc, "alive_knn_match")
     _count(B + (4 if m == 1 else 2))
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
-                           fb_count=workspace[off[9]:off[9] + 4].view(torch.int32),
+                           fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
                            launches=B + (4 if m == 1 else 2))
     last_info._workspace = workspace
@@ -417,9 +466,13 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
 
 def match_packed(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0,
                  mode: str = "auto", variant: int = 0, r_max: int = DEFAULT_R_MAX):
-    """All B*T query frames of `source` [B,D,T] against ONE packed library.
-    Returns (out [B,T,D] float32 contiguous, top_idx [B,T,k] int64, top_score [B,T,k])."""
-    return run_match(source, lib, k, alpha, mode, variant, r_max)
+    """All B*T query frames of `source` [B,D,T] against ONE packed library - or, when `lib` holds
+    B libraries (pack_libraries), batch item b against library b.  Returns (out [B,T,D] float32
+    contiguous, top_idx [B,T,k] int64 relative to the item's own library, top_score [B,T,k])."""
+    out, idx, score = run_match(source, lib, k, alpha, mode, variant, r_max)
+    if lib.items > 1:
+        idx = idx - (torch.arange(lib.items, device=idx.device, dtype=idx.dtype) * lib.n_item).view(-1, 1, 1)
+    return out, idx, score
 
 
 class StreamingMatcher:
@@ -516,15 +569,11 @@ def _match_impl(source, reference, k, alpha, mode, variant, want_out=True):
         owner = reference if (reference.dtype == torch.float32) else ref32
         lib = cached_pack(owner, ref32[0])
         return match_packed(src32, lib, k, alpha, mode, variant)
-    outs, idxs, scs = [], [], []
-    for b in range(B):
-        owner = reference if (reference.dtype == torch.float32) else ref32
-        lib = cached_pack(owner, ref32[b], tag=b + 1)
-        o, i, s = match_packed(src32[b:b + 1], lib, k, alpha, mode, variant)
-        outs.append(o)
-        idxs.append(i)
-        scs.append(s)
-    return torch.cat(outs, 0), torch.cat(idxs, 0), torch.cat(scs, 0)
+    # a different library per batch item (train_decoder.py:134-135, BASELINE cfg5): all items are
+    # packed back to back and matched in ONE pipeline launch
+    owner = reference if (reference.dtype == torch.float32) else ref32
+    lib = cached_pack_many(owner, ref32)
+    return match_packed(src32, lib, k, alpha, mode, variant)
 
 
 class _BlendGrad(torch.autograd.Function):

@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* alive_stream_t; /* cudaStream_t */
 
-#define ALIVE_KNN_ABI_VERSION 1
+#define ALIVE_KNN_ABI_VERSION 2
 #define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
 #define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
 #define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
@@ -51,6 +51,7 @@ typedef struct alive_knn_plan {
   int32_t tiles_per_segment;
   int32_t lists;             /* running lists per query = 2 * segments */
   int32_t grid;              /* CTAs launched (multiple of ctas_per_unit) */
+  int32_t items;             /* independent (query batch, library) pairs laid out back to back; 1 = plain */
 } alive_knn_plan_t;
 
 /* Library statistics produced by alive_knn_pack (2 x uint32 on the device):
@@ -81,15 +82,20 @@ int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64
  * `num_sms` SMs.  variant: 1 or 2 CTAs per unit (0 = library default). Host only. */
 int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
                    alive_knn_plan_t* plan_host);
+/* Batched form (BASELINE cfg5, train_decoder.py:134-135): `items` independent problems of t
+ * queries x n frames each, queries stored as [items*t, d] and libraries as [items*n, d]; item i's
+ * queries only see item i's frames.  One launch covers all items. */
+int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32_t d, int32_t num_sms,
+                           int32_t variant, alive_knn_plan_t* plan_host);
 
 /* K2 - fused similarity + running top list.  Replaces the bmm of
  * common.py:104 and the first pass of torch.topk :105 WITHOUT materialising
  * the [T,N] score matrix: TMA-fed tcgen05 bf16 MMAs accumulate 128x256 score
  * tiles in TMEM; epilogue warps keep, per query and per list, the
  * ALIVE_KNN_LIST_LEN best (score, frame) pairs.
- *   q_packed [t,d] bf16, lib_packed [n,d] bf16 (from alive_knn_pack)
- *   cand_score [t, plan.lists, 8] float32 (descending, -inf padded)
- *   cand_idx   [t, plan.lists, 8] int32   (-1 padded) */
+ *   q_packed [items*t,d] bf16, lib_packed [items*n,d] bf16 (from alive_knn_pack)
+ *   cand_score [items*t, plan.lists, 8] float32 (descending, -inf padded)
+ *   cand_idx   [items*t, plan.lists, 8] int32   (-1 padded; frame index inside [items*n]) */
 int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,
                      const alive_knn_plan_t* plan_host,
                      float* cand_score, int32_t* cand_idx, alive_stream_t stream);
@@ -118,25 +124,30 @@ int alive_knn_rescore(const float* q_raw, const float* q_norm, int32_t t,
 
 /* K2b+K3+K4 fused, one CTA per query: alive_knn_prune + alive_knn_rescore (+ the
  * gather+mean+blend of alive_knn_gather_mean when out != NULL) in one launch.  Uncertified
- * queries are appended to fb_list (sel_n = -1) and left to alive_knn_exact. */
+ * queries are appended to fb_list (sel_n = -1) and left to alive_knn_exact.  t = ALL query
+ * frames (items * t_item); with items > 1 the lists are kept per item: fb_list [items][t/items],
+ * fb_count [items]. */
 int alive_knn_finish(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
                      const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
                      const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
                      int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx,
-                     int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, alive_stream_t stream);
+                     int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, int32_t items,
+                     alive_stream_t stream);
 
 /* Exact scan (no screen): common.py:102-105 for the queries listed in
  * q_list[0..*q_count) (both device; NULL/NULL = all t queries) against all n
  * frames, same arithmetic and tie rule as alive_knn_rescore; NaN similarities
  * rank first like torch.topk.  workspace: alive_knn_exact_workspace_bytes().
+ * items > 1: t = items * t_item queries, item i scans frames [i*n, (i+1)*n) of lib_raw
+ * ([items*n, d]); q_list is [items][t_item], q_count [items]; indices are global (i*n + frame).
  * out (nullable, [t,d] f32): when given, the scanned queries are also gathered
  * (common.py:107-109, same arithmetic as alive_knn_gather_mean with `alpha`). */
-size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k);
+size_t alive_knn_exact_workspace_bytes(int32_t t, int64_t n, int32_t k, int32_t items);
 int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t,
                     const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, int32_t k,
                     const int32_t* q_list, const int32_t* q_count, int64_t idx_base,
                     void* workspace, float* top_score, int64_t* top_idx, float alpha, float* out,
-                    alive_stream_t stream);
+                    int32_t items, alive_stream_t stream);
 
 /* Multi-GPU merge: after an all-gather of every rank's exact local top-k,
  * scores/idx are [ranks,t,k]; writes the global top-k (score desc, frame asc). */
@@ -191,15 +202,18 @@ typedef struct alive_knn_library {
   const float* raw;         /* [n,d] f32  */
   const float* norms;       /* [n]   f32  */
   const uint32_t* stats;    /* [2]   u32  */
-  int64_t n;
+  int64_t n;                /* frames per item */
   int32_t d;
   int64_t row_base;         /* global index of frame 0 (row-sharded libraries), else 0 */
+  int32_t items;            /* >= 1: independent libraries of n frames each, stored back to back */
 } alive_knn_library_t;
 
 /* One-call pipeline = module/common.py:96-109 for `batch` x `t` query frames against one
  * packed library: pack queries -> search -> prune -> rescore -> exact scan of uncertified
  * queries -> gather+mean+blend.  source[b*stride_b + i*stride_t + j*stride_d] (the
  * reference's [B,D,T] layout: stride_b=D*T, stride_t=1, stride_d=T).
+ *   lib->items > 1: `batch` must equal lib->items; batch item b is matched against frames
+ *   [b*n, (b+1)*n) only (one launch for all items); indices are global (b*n + frame)
  *   mode: 0 auto (screen; exact scan when k > 8 or d % 64 != 0), 1 screen, 2 exact scan
  *   workspace: 256-byte aligned, at least offsets[11] bytes of alive_knn_match_layout
  *   out [batch*t, d] f32 (NULL = skip the gather, e.g. for a sharded library),
@@ -211,7 +225,7 @@ typedef struct alive_knn_library {
  *   0 q_raw 1 q_norm 2 q_packed 3 q_err 4 cand_score 5 cand_idx 6 sel_idx 7 sel_n
  *   8 fb_list 9 fb_count 10 exact scratch 11 TOTAL bytes. */
 int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
-                           int32_t num_sms, int32_t variant, int64_t* offsets12_host);
+                           int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets12_host);
 int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
                     int64_t stride_d, const alive_knn_library_t* lib_host, int32_t k, float alpha,
                     int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,

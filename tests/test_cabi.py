@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     assert sorted(_cabi.EXPORTS) == declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in alive_knn.h but not exported"
-    assert lib.alive_knn_abi_version() == 1
+    assert lib.alive_knn_abi_version() == 2
 
 
 def test_sass_is_blackwell_native():
@@ -78,7 +78,7 @@ def test_argument_validation_without_gpu(lib):
     # NULL pointers are rejected before any CUDA call is made
     assert lib.alive_knn_pack(None, 4, 768, 1, 4, None, None, None, None, None, None) != 0
     assert b"NULL" in lib.alive_knn_last_error()
-    assert lib.alive_knn_exact_workspace_bytes(1000, 100000, 4) > 0
+    assert lib.alive_knn_exact_workspace_bytes(1000, 100000, 4, 1) > 0
 
 
 @pytest.mark.parametrize("rows,n,k,mode", [(32, 200_000, 4, 1), (1000, 100_000, 4, 0), (10_000, 10_000_000, 4, 1),
@@ -87,7 +87,7 @@ def test_match_workspace_layout_is_consistent(lib, rows, n, k, mode):
     """alive_knn_match_layout is host-only: 12 ascending, 256-byte aligned offsets, large enough for
     every buffer the pipeline carves out of the single workspace."""
     off = (ctypes.c_int64 * 12)()
-    assert lib.alive_knn_match_layout(rows, n, 768, k, 64, mode, 148, 0, off) == 0
+    assert lib.alive_knn_match_layout(rows, n, 768, k, 64, mode, 148, 0, 1, off) == 0
     o = list(off)
     assert o[0] == 0 and all(x % 256 == 0 for x in o)
     assert all(o[i] <= o[i + 1] for i in range(11))
@@ -101,11 +101,11 @@ def test_match_workspace_layout_is_consistent(lib, rows, n, k, mode):
         assert lib.alive_knn_plan(rows, n, 768, 148, 0, ctypes.byref(p)) == 0
         assert o[5] - o[4] >= rows * p.lists * 8 * 4 and o[6] - o[5] >= rows * p.lists * 8 * 4
         assert o[7] - o[6] >= rows * 64 * 4       # sel_idx
-    assert o[11] - o[10] >= lib.alive_knn_exact_workspace_bytes(rows, n, k)
+    assert o[11] - o[10] >= lib.alive_knn_exact_workspace_bytes(rows, n, k, 1)
 
 
 def test_match_rejects_bad_arguments_before_any_launch(lib):
-    lb = _cabi.Library(1, 1, 1, 1, 3, 768, 0)     # n = 3 frames
+    lb = _cabi.Library(1, 1, 1, 1, 3, 768, 0, 1)     # n = 3 frames, one item
     # k > n: the reference's torch.topk message (common.py:105)
     rc = lib.alive_knn_match(1, 1, 4, 768 * 4, 1, 4, ctypes.byref(lb), 4, 0.0, 64, 0, 148, 0, 256, 1 << 20, None, 1, 1,
                              None, None, None)
@@ -113,3 +113,20 @@ def test_match_rejects_bad_arguments_before_any_launch(lib):
     rc = lib.alive_knn_match(None, 1, 4, 768 * 4, 1, 4, ctypes.byref(lb), 1, 0.0, 64, 0, 148, 0, 256, 1 << 20, None, 1, 1,
                              None, None, None)
     assert rc != 0 and b"NULL" in lib.alive_knn_last_error()
+
+
+def test_batched_plan_and_layout(lib):
+    """items > 1 (BASELINE cfg5): one plan / one workspace for all (query batch, library) pairs"""
+    p = _cabi.Plan()
+    assert lib.alive_knn_plan_batched(64, 1000, 500_000, 768, 148, 0, ctypes.byref(p)) == 0
+    assert p.items == 64 and p.t == 1000 and p.n == 500_000 and p.ctas_per_unit == 2
+    assert p.m_units == 4 and p.segments * p.tiles_per_segment >= p.n_tiles and p.lists == 2 * p.segments
+    units = 64 * p.m_units * p.segments
+    waves = -(-units // 74)
+    assert waves * p.tiles_per_segment * 74 <= 1.05 * 64 * p.m_units * p.n_tiles     # < 5 % idle tile slots
+    off = (ctypes.c_int64 * 12)()
+    assert lib.alive_knn_match_layout(64 * 1000, 500_000, 768, 4, 64, 1, 148, 0, 64, off) == 0
+    o = list(off)
+    assert o[10] - o[9] >= 64 * 4                          # one uncertified-query counter per item
+    assert lib.alive_knn_match_layout(1001, 500_000, 768, 4, 64, 1, 148, 0, 64, off) != 0   # rows % items
+    assert lib.alive_knn_plan_batched(0, 10, 10, 768, 148, 0, ctypes.byref(p)) != 0

@@ -399,3 +399,28 @@ def test_functional_api_packs_the_library_once_and_follows_inplace_edits():
     assert next(iter(M._pack_cache.values()))[2] is not packed_first
     want = A.match_features(chunk, view.contiguous())
     assert torch.equal(c, want)
+
+
+def test_batched_libraries_equal_per_item_matches():
+    """B different libraries packed back to back and matched in ONE launch (BASELINE cfg5,
+    train_decoder.py:134-135) == B separate single-library matches, bit for bit; also vs the oracle."""
+    rng = np.random.default_rng(91)
+    for (B, T, N, k, alpha, mode) in [(3, 130, 1500, 4, 0.0, "auto"), (5, 7, 300, 2, 0.25, "auto"),
+                                      (2, 40, 900, 16, 0.0, "auto"), (4, 300, 5000, 4, 0.0, "screen")]:
+        src = rng.standard_normal((B, 768, T), dtype=np.float32)
+        ref = rng.standard_normal((B, 768, N), dtype=np.float32)
+        if B == 3:
+            ref[1, :, 100:140] = ref[1, :, 60:100]                 # duplicated frames inside item 1
+            src[1, :, :10] = ref[1, :, 60:70]                      # ... queried exactly: exact ties
+        s, r = _cuda(src), _cuda(ref)
+        out, idx = A.match_features(s, r, k, alpha, return_indices=True, mode=mode)
+        assert M.last_info.launches == B + (4 if M.last_info.mode == "screen" else 2)      # one pipeline
+        for b in range(B):
+            o1, i1 = A.match_features(s[b:b + 1], r[b:b + 1], k, alpha, return_indices=True, mode=mode)
+            assert torch.equal(idx[b:b + 1], i1) and torch.equal(out[b:b + 1], o1)
+        _assert_parity(out, idx, src, ref, k, alpha)
+    # explicit handle
+    lib = A.pack_libraries(r)
+    assert lib.items == B and lib.n_item == N
+    o2, i2, _ = A.match_packed(s, lib, k, alpha)
+    assert torch.equal(o2.transpose(1, 2), out) and torch.equal(i2, idx)
