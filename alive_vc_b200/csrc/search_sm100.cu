@@ -419,8 +419,12 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t phase = (it / kStages) & 1u;
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             if (elect_one_sync()) {
-              if (leader) mbar_expect_tx(bar_full + 8 * stage, C::kTxBytes);
-              tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row, p.hint_q);
+              // debug 3 (timing experiment only, results are garbage): query tiles are loaded for the
+              // first library tile of a unit only - an upper bound for what a resident query tile would buy
+              const bool load_q = p.debug != 3 || tile == tile0;
+              if (leader) mbar_expect_tx(bar_full + 8 * stage, load_q ? C::kTxBytes : C::kBBytes * kCtas);
+              if (load_q)
+                tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row, p.hint_q);
               tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row, p.hint_lib);
             }
             __syncwarp();
@@ -525,7 +529,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               else mbar_arrive_cluster(tempty0 + 8 * acc);
             }
           }
-          if (p.debug == 0) scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
+          if (p.debug == 0 || p.debug == 3) scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
           else s[0] = fmaxf(s[0], __uint_as_float(v[0] ^ v[13] ^ v[31]));
         }
       }

@@ -67,6 +67,28 @@ def main():
                                     str(T), str(N)], cwd=ROOT)
     elif what == "one":
         one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif what == "sustain":
+        # the search kernel alone, back to back for seconds (power-capped regime), at a bench shape
+        import torch
+        import bench
+        from alive_vc_b200 import _cabi, matching as M
+        T, N, variant = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+        lib = bench.build_library(0, N, 7, torch.device("cuda", 0))
+        q = M.pack_frames(torch.randn(768, T, device="cuda"))
+        plan = M.make_plan(T, N, 768, q.device, variant)
+        cs = torch.empty((T, plan.lists, 8), device="cuda")
+        ci = torch.empty((T, plan.lists, 8), dtype=torch.int32, device="cuda")
+        c = _cabi.load()
+        st = torch.cuda.current_stream().cuda_stream
+
+        def run():
+            _cabi.check(c.alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
+                                           cs.data_ptr(), ci.data_ptr(), st), "search")
+        for _ in range(5):
+            run()
+        ms = time_it(run, 15)
+        print(f"sustain T={T} N={N} variant={variant} debug={os.environ.get('ALIVE_KNN_DEBUG_EPILOGUE', '0')}: "
+              f"{ms:.3f} ms  {2.0 * T * N * 768 / (ms * 1e-3) / 1e12:.1f} TFLOP/s", flush=True)
     elif what == "pipeline":
         # the whole one-call pipeline a few times (for an ncu launch list / per-kernel breakdown)
         import torch
