@@ -424,3 +424,25 @@ def test_batched_libraries_equal_per_item_matches():
     assert lib.items == B and lib.n_item == N
     o2, i2, _ = A.match_packed(s, lib, k, alpha)
     assert torch.equal(o2.transpose(1, 2), out) and torch.equal(i2, idx)
+
+
+@pytest.mark.parametrize("D,mode", [(64, "screen"), (256, "screen"), (1024, "screen"), (100, "auto"), (1536, "screen")])
+def test_other_feature_dims(D, mode):
+    """VoiceLibrary(num_tokens, hubert_dim) takes any feature dim (voice_library.py:7): multiples of
+    64 run on the tensor-core screen, everything else (multiple of 4) on the exact scan."""
+    rng = np.random.default_rng(D)
+    src = rng.standard_normal((2, D, 37), dtype=np.float32)
+    tok = rng.standard_normal((1, D, 1300), dtype=np.float32)
+    vl = A.VoiceLibrary(num_tokens=1300, hubert_dim=D).cuda()
+    with torch.no_grad():
+        vl.tokens.copy_(_cuda(tok))
+    out, idx = vl.match(_cuda(src), k=4, alpha=0.1, return_indices=True, mode=mode)
+    assert M.last_info.mode == ("exact" if D % 64 else "screen")
+    want_out, want_idx, _ = O.voice_library_match_np(tok, src, 4, 0.1, True)
+    ref_b = np.broadcast_to(tok, (2,) + tok.shape[1:])
+    scores = O.cosine_scores_np(src, ref_b)
+    ok, n_exact, n_tie, bad = O.indices_match_mod_ties(idx.cpu().numpy(), want_idx, scores, TIE_TOL)
+    assert ok, bad
+    same = (idx.cpu().numpy() == want_idx).all(axis=2)
+    o = out.detach().cpu().numpy()
+    assert np.array_equal(np.swapaxes(o, 1, 2)[same], np.swapaxes(want_out, 1, 2)[same])
