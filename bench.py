@@ -44,11 +44,15 @@ WORKLOADS = {
     "cfg3": (1, 100_000, 1_000_000, "cfg3: offline batch T=100k frames vs 1M-frame library"),
     "cfg4": (1, 10_000, 10_000_000, "cfg4: T=10k frames vs 10M-frame library row-sharded over the GPUs"),
     "cfg5": (64, 1000, 500_000, "cfg5: 64 utterances x 1000 frames vs 64 per-speaker 500k-frame libraries"),
+    # the reference's own default operating points: --chunk 48000 -> T=450 per call,
+    # realtime chunk 960 x buffer 8 -> T=24 per call, library = one target utterance + 512 tokens
+    "real_offline": (1, 450, 3512, "inference.py defaults: T=450 frames per chunk vs N=3512-frame library"),
+    "real_realtime": (1, 24, 3512, "realtime_inference.py defaults: T=24 frames per chunk vs N=3512-frame library"),
 }
 
 
 # cfg2 is a latency config: SURVEY §8(d) asks for >= 1000 timed calls
-DEFAULT_STEPS = {"cfg1": 50, "cfg2": 1000, "cfg3": 5, "cfg4": 5, "cfg5": 3}
+DEFAULT_STEPS = {"cfg1": 50, "cfg2": 1000, "cfg3": 5, "cfg4": 5, "cfg5": 3, "real_offline": 1000, "real_realtime": 1000}
 
 
 def load_traffic(workload: str, world: int):
@@ -144,6 +148,8 @@ def cpu_sample_shape(workload: str):
     if workload == "cfg4":
         return 64, 1_000_000, 0.1, ("T=64-frame tile vs a 1M-frame slice (1/10 of the 10M library); "
                                     "rate scaled x0.1 linearly in N (extrapolated)")
+    if workload in ("real_offline", "real_realtime"):
+        return T, N, 1.0, f"full {workload} (T={T}, N={N})"
     return 256, 500_000, 1.0, "T=256-frame tile of one speaker vs its 500k-frame library (per-frame rate)"
 
 
@@ -313,7 +319,7 @@ def gpu_arm(args):
 
         def step(src):
             return sharded.match(src, K, 0.0)
-        if args.workload in ("cfg1", "cfg2") and world == 1 and not args.no_graph:
+        if args.workload in ("cfg1", "cfg2", "real_offline", "real_realtime") and world == 1 and not args.no_graph:
             # fixed-shape chunks (inference.py / realtime_inference.py call the match once per chunk with
             # the same T): pre-allocated buffers, the whole pipeline replayed as one CUDA graph
             streamer = M.StreamingMatcher(lib, T, K, 0.0, batch=B, mode="screen", variant=variant)
@@ -345,7 +351,8 @@ def gpu_arm(args):
     lat = []
     barrier()
     e0.record()
-    if args.workload == "cfg2":
+    latency_workload = args.workload in ("cfg2", "real_offline", "real_realtime")
+    if latency_workload:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         evs[0].record()
         for i in range(args.steps):
@@ -368,7 +375,7 @@ def gpu_arm(args):
         torch.cuda.synchronize()
         search_ms = [a.elapsed_time(b) for a, b in M.search_events]
     M.search_events = None
-    if args.workload == "cfg2":
+    if latency_workload:
         lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
     fallback = M.last_info.fallback_queries() if M.last_info is not None else 0
     if world > 1:
@@ -379,7 +386,7 @@ def gpu_arm(args):
     value = units_per_step / (ms_per_step * 1e-3)
 
     # ---- end-to-end: host buffers through the public API ----
-    streaming = args.workload in ("cfg1", "cfg2") and world == 1 and not args.no_graph
+    streaming = args.workload in ("cfg1", "cfg2", "real_offline", "real_realtime") and world == 1 and not args.no_graph
 
     def e2e_step():
         # the streaming matcher copies the pinned host chunk straight into its static input buffer
@@ -410,7 +417,7 @@ def gpu_arm(args):
         else:
             flops_per_launch = 2.0 * B * T * n_local * D
         avg_search_ms = sum(search_ms) / max(1, len(search_ms))
-        if args.workload == "cfg2":
+        if latency_workload:
             bytes_per_launch = float(n_local) * D * 2
             achieved = bytes_per_launch / (avg_search_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
