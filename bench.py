@@ -335,7 +335,10 @@ def gpu_arm(args):
             ", all-gather top-k + reduce-scatter rows + all-gather result")
     src_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
     src_host.copy_(src_dev)
-    out_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
+    # the result is a transposed view of a contiguous [B,T,D] block (like the reference's); the pinned
+    # host buffer has the same strides, so the device->host read is one plain memcpy
+    _b, _d, _t = src_dev.shape
+    out_host = torch.empty((_b, _t, _d), dtype=torch.float32).pin_memory().transpose(1, 2)
     barrier()
 
     # ---- device-resident timing ----
