@@ -129,7 +129,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+    if (clock64() - t0 > 20000000000LL) {   // ~10-15 s: far beyond any legitimate wait, short enough to fail fast
       printf("alive_knn_search: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
              blockIdx.x, threadIdx.x, bar, parity);
       __trap();
