@@ -241,7 +241,7 @@ def stage_golden():
         o = out.detach().cpu().numpy()
         same = (idx.cpu().numpy() == g["indices"]).all(axis=2)
         bit = np.array_equal(np.swapaxes(o, 1, 2)[same], np.swapaxes(g["out"], 1, 2)[same])
-        close = name == "mf_dupes" or np.allclose(o, g["out"], rtol=1e-5, atol=1e-6)
+        close = name in ("mf_dupes", "mf_clustered") or np.allclose(o, g["out"], rtol=1e-5, atol=1e-6)   # tie rows differ legitimately
         st_ok = tuple(out.stride()) == tuple(g["out_strides"]) or o.shape[2] == 1
         print(f"{name}: idx ok={i_ok} (exact rows {n_exact}, ties {n_tie}) bit-exact={bit} close={close} "
               f"strides ok={st_ok} grads ok={gt_ok and gs_ok}")
