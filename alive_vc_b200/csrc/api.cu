@@ -57,7 +57,7 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
   }
   take(kOffCandScore, static_cast<size_t>(rows) * lists * ALIVE_KNN_LIST_LEN * 4);
   take(kOffCandIdx, static_cast<size_t>(rows) * lists * ALIVE_KNN_LIST_LEN * 4);
-  take(kOffSelIdx, mode == 1 ? static_cast<size_t>(rows) * r_max * 4 : 0);
+  take(kOffSelIdx, 0);   // survivors stay in finish_kernel's shared memory (slot kept for ABI stability)
   take(kOffSelN, static_cast<size_t>(rows) * 4);
   take(kOffFbList, static_cast<size_t>(rows) * 4);
   take(kOffFbCount, static_cast<size_t>(items) * 4);
@@ -113,7 +113,6 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   float* q_err = reinterpret_cast<float*>(ws + off[kOffQErr]);
   float* cand_score = reinterpret_cast<float*>(ws + off[kOffCandScore]);
   int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + off[kOffCandIdx]);
-  int32_t* sel_idx = reinterpret_cast<int32_t*>(ws + off[kOffSelIdx]);
   int32_t* sel_n = reinterpret_cast<int32_t*>(ws + off[kOffSelN]);
   int32_t* fb_list = reinterpret_cast<int32_t*>(ws + off[kOffFbList]);
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws + off[kOffFbCount]);

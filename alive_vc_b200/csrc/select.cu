@@ -422,6 +422,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
 // each warp folds the tile's scores into its queries' running top-k lists.
 // grid = (query groups [grid-stride], library splits); partial lists go to part_score/part_idx.
 // ------------------------------------------------------------------------------------------
+constexpr int kFewQueries = 16; // at most this many queries (per item): warp-per-frame kernel instead
 constexpr int kEQ = 64;         // queries per CTA
 constexpr int kER = 128;        // frames per tile
 constexpr int kEK = 32;         // channels per staged chunk
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(kEThreads)
 exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm, int t,
                      const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
                      int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
-                     float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item) {
+                     float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item, int few) {
   // blockIdx.y = item: its queries are q_list[item][..] (or [item*t_item, (item+1)*t_item) when no
   // list is given) and its frames are rows [item*n, (item+1)*n) of lib_raw; t = queries PER ITEM
   const int item = blockIdx.y;
@@ -455,6 +456,7 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
   __shared__ int lworst[kEQ];
 
   const int nq = q_count ? *q_count : t;
+  if (nq <= few) return;                    // exact_rows_kernel takes the small lists
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // a warp covers 8 queries x 128 frames (two 4-query blocks x sixteen 8-frame blocks): groups
   // with few valid queries (sparse fallbacks) let whole warps skip the FMA loop
@@ -618,6 +620,187 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
   }
 }
 
+// Few queries (a handful of uncertified queries in an otherwise clean batch; tiny realtime
+// batches in exact mode): the 64-query tile above would be mostly empty.  Here a CTA takes 8
+// queries (normalised, as doubles, in shared memory) and one library split; every WARP owns whole
+// frames: load + normalise the frame once, 8 fp64 dot products, warp-reduce, lane q keeps query q's
+// running top-k.  Same arithmetic, same partial-list layout as exact_partial_kernel.
+constexpr int kRQ = 8;   // queries per CTA
+constexpr int kRR = 4;   // frames per warp bundle
+
+// bytes of the query area (it is reused for the final merge of the per-lane lists)
+__host__ __device__ inline size_t rows_query_bytes(int d, int k) {
+  const size_t q = static_cast<size_t>(kRQ) * d * 8;
+  const size_t tmp = (static_cast<size_t>(kRQ) * 8 * kRR * k * 12 + 16 + 15) / 16 * 16;
+  return q > tmp ? q : tmp;
+}
+
+__global__ void __launch_bounds__(256)
+exact_rows_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_norm, int t,
+                  const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
+                  int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
+                  float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item, int few) {
+  const int item = blockIdx.y;
+  if (q_list) q_list += static_cast<size_t>(item) * t_item;
+  if (q_count) q_count += item;
+  const int nq = q_count ? *q_count : t;
+  if (nq > few || nq <= 0) return;
+  lib_raw += static_cast<size_t>(item) * n * d;
+  lib_norm += static_cast<size_t>(item) * n;
+  const long long item_row0 = static_cast<long long>(item) * n;
+  const int item_q0 = item * t_item;
+  const size_t item_slot0 = static_cast<size_t>(item) * ((t_item + kEQ - 1) / kEQ) * kEQ;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* qd = reinterpret_cast<double*>(smem_raw);                        // [kRQ][d]
+  const size_t q_bytes = rows_query_bytes(d, k);
+  long long* lid = reinterpret_cast<long long*>(smem_raw + q_bytes);       // [8 warps][32 lanes][k]
+  float* lsc = reinterpret_cast<float*>(lid + 8 * 32 * k);                 // [8 warps][32 lanes][k]
+  __shared__ int qids[kRQ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long per = (n + splits - 1) / splits;
+  const int n_groups = (nq + kRQ - 1) / kRQ;
+  const long long n_items = static_cast<long long>(n_groups) * splits;
+
+  for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int g0 = static_cast<int>(it / splits) * kRQ;
+    const int split = static_cast<int>(it % splits);
+    const long long r0 = per * split;
+    const long long r1 = min(n, r0 + per);
+    __syncthreads();
+    if (threadIdx.x < kRQ) {
+      const int slot = g0 + threadIdx.x;
+      qids[threadIdx.x] = slot < nq ? (q_list ? q_list[slot] : item_q0 + slot) : -1;
+    }
+    __syncthreads();
+    for (int qi = 0; qi < kRQ; ++qi) {
+      const int q = qids[qi];
+      const float qn = q >= 0 ? q_norm[q] : 1.f;
+      for (int j = threadIdx.x; j < d; j += blockDim.x)
+        qd[qi * d + j] = q >= 0 ? static_cast<double>(__fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn)) : 0.0;
+    }
+    for (int e = threadIdx.x; e < 8 * 32 * k; e += blockDim.x) lid[e] = -1;
+    __syncthreads();
+
+    // lane l keeps the list of query (l & 7) over the rows whose position in a 4-row bundle is (l >> 3)
+    float* my_s = lsc + (warp * 32 + lane) * k;
+    long long* my_i = lid + (warp * 32 + lane) * k;
+    const bool q_ok = qids[lane & (kRQ - 1)] >= 0;
+    const int my_rr = lane >> 3;
+    int filled = 0, worst = 0;
+    constexpr int kMaxVec = 12;                         // d <= 1536 -> at most 12 float4 per lane
+    for (long long rb = r0 + warp * kRR; rb < r1; rb += 8 * kRR) {
+      const float* row[kRR];
+      float nrm[kRR];
+#pragma unroll
+      for (int rr = 0; rr < kRR; ++rr) {
+        const long long r = min(rb + rr, r1 - 1);       // bundle tail: re-read the last frame, never inserted
+        row[rr] = lib_raw + static_cast<size_t>(r) * d;
+        nrm[rr] = lib_norm[r];
+      }
+      // acc[rr * 8 + qi]: 32 independent fp64 chains per lane; every query double2 read from shared
+      // memory feeds 4 frames (shared-memory bandwidth is what bounds this kernel)
+      double acc[kRR * kRQ];
+#pragma unroll
+      for (int e = 0; e < kRR * kRQ; ++e) acc[e] = 0.0;
+      float4 nxt[kRR];
+#pragma unroll
+      for (int rr = 0; rr < kRR; ++rr)
+        nxt[rr] = lane * 4 < d ? *reinterpret_cast<const float4*>(row[rr] + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i) {
+        const int j = lane * 4 + i * 128;
+        if (i * 128 < d) {                               // warp-uniform
+          double rn[kRR][4];
+#pragma unroll
+          for (int rr = 0; rr < kRR; ++rr) {
+            rn[rr][0] = static_cast<double>(__fdiv_rn(nxt[rr].x, nrm[rr]));
+            rn[rr][1] = static_cast<double>(__fdiv_rn(nxt[rr].y, nrm[rr]));
+            rn[rr][2] = static_cast<double>(__fdiv_rn(nxt[rr].z, nrm[rr]));
+            rn[rr][3] = static_cast<double>(__fdiv_rn(nxt[rr].w, nrm[rr]));
+          }
+          if (i + 1 < kMaxVec) {
+            const int jn = j + 128;
+#pragma unroll
+            for (int rr = 0; rr < kRR; ++rr)
+              nxt[rr] = jn < d ? *reinterpret_cast<const float4*>(row[rr] + jn) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (j < d) {
+#pragma unroll
+            for (int qi = 0; qi < kRQ; ++qi) {
+              const double2 a01 = *reinterpret_cast<const double2*>(qd + qi * d + j);
+              const double2 a23 = *reinterpret_cast<const double2*>(qd + qi * d + j + 2);
+#pragma unroll
+              for (int rr = 0; rr < kRR; ++rr) {
+                double a = acc[rr * kRQ + qi];
+                a = fma(a01.x, rn[rr][0], a);
+                a = fma(a01.y, rn[rr][1], a);
+                a = fma(a23.x, rn[rr][2], a);
+                a = fma(a23.y, rn[rr][3], a);
+                acc[rr * kRQ + qi] = a;
+              }
+            }
+          }
+        }
+      }
+      // transposing butterfly: 31 exchanges leave lane l with the full sum of entry l (= rr * 8 + qi)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int e = 0; e < o; ++e) {
+          const double keep = hi ? acc[e + o] : acc[e];
+          const double send = hi ? acc[e] : acc[e + o];
+          acc[e] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      const float mine = static_cast<float>(acc[0]);
+      const long long r = rb + my_rr;
+      if (q_ok && r < r1) {
+        const long long gi = r + item_row0;             // global frame index
+        if (filled < k) {
+          my_s[filled] = mine;
+          my_i[filled] = gi;
+          ++filled;
+          if (filled == k) {
+            worst = 0;
+            for (int e = 1; e < k; ++e)
+              if (score_better(my_s[worst], my_i[worst], my_s[e], my_i[e])) worst = e;
+          }
+        } else if (score_better(mine, gi, my_s[worst], my_i[worst])) {
+          my_s[worst] = mine;
+          my_i[worst] = gi;
+          worst = 0;
+          for (int e = 1; e < k; ++e)
+            if (score_better(my_s[worst], my_i[worst], my_s[e], my_i[e])) worst = e;
+        }
+      }
+    }
+    __syncthreads();
+    // merge the 8 x kRR per-lane lists of each query: warp w finishes query w.  The lists are copied
+    // next to each other into the (now free) query area and go through the selector.
+    {
+      const int qi = warp;
+      constexpr int kLists = 8 * kRR;
+      if (qi < kRQ && qids[qi] >= 0) {
+        float* tmp_s = reinterpret_cast<float*>(qd) + qi * kLists * k;
+        long long* tmp_i =
+            reinterpret_cast<long long*>(reinterpret_cast<float*>(qd) + kRQ * kLists * k + (kRQ * kLists * k & 1)) +
+            qi * kLists * k;
+        for (int e = lane; e < kLists * k; e += 32) {
+          const int l = e / k, j = e % k;                // l = warp' * kRR + rr'
+          const int src = ((l / kRR) * 32 + (l % kRR) * kRQ + qi) * k + j;
+          tmp_s[e] = lsc[src];
+          tmp_i[e] = lid[src];
+        }
+        __syncwarp();
+        const size_t o = ((item_slot0 + g0 + qi) * splits + split) * k;
+        warp_select_topk(tmp_s, tmp_i, kLists * k, k, part_score + o, part_idx + o, 0, lane);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 exact_final_kernel(int t, int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
                    const float* __restrict__ part_score, const long long* __restrict__ part_idx,
@@ -761,9 +944,29 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
   if (gx > work) gx = work;
   if (gx < 1) gx = 1;
   dim3 pgrid(static_cast<unsigned>(gx), static_cast<unsigned>(items));
+  // lists of at most `few` queries per item go to the warp-per-frame kernel (chosen on the device from
+  // q_count); its per-lane lists only fit in shared memory for moderate k
+  const size_t rsmem = rows_query_bytes(d, k) + static_cast<size_t>(8) * 32 * k * 12;
+  const int few = rsmem <= 200 * 1024 ? kFewQueries : 0;
   exact_partial_kernel<<<pgrid, kEThreads, smem, as_stream(stream)>>>(q_raw, q_norm, t_item, lib_raw, lib_norm, n, d, k,
-                                                                     q_list, q_count, splits, part_score, part_idx, t_item);
+                                                                     q_list, q_count, splits, part_score, part_idx, t_item,
+                                                                     few);
   ALIVE_CHECK_CUDA(cudaGetLastError());
+  if (few > 0) {
+    static bool rattr_done = false;
+    if (!rattr_done) {
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      rattr_done = true;
+    }
+    const size_t rwork = static_cast<size_t>((few + kRQ - 1) / kRQ) * splits;
+    size_t rgx = (4 * 148 + items - 1) / items;
+    if (rgx > rwork) rgx = rwork;
+    if (rgx < 1) rgx = 1;
+    dim3 rgrid(static_cast<unsigned>(rgx), static_cast<unsigned>(items));
+    exact_rows_kernel<<<rgrid, 256, rsmem, as_stream(stream)>>>(q_raw, q_norm, t_item, lib_raw, lib_norm, n, d, k, q_list,
+                                                               q_count, splits, part_score, part_idx, t_item, few);
+    ALIVE_CHECK_CUDA(cudaGetLastError());
+  }
   ALIVE_REQUIRE(out == nullptr || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && idx_base == 0),
                 "alive_knn_exact: gather needs a 16-byte aligned `out` and an unsharded library");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));

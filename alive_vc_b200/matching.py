@@ -26,7 +26,7 @@ from . import _cabi
 
 LIST_LEN = 8            # ALIVE_KNN_LIST_LEN
 MAX_K = 64              # ALIVE_KNN_MAX_K
-DEFAULT_R_MAX = 64      # survivors rescored per query before falling back to the exact scan
+DEFAULT_R_MAX = 256     # survivors rescored per query before falling back to the exact scan
 EXACT_BELOW_N = 0       # the tensor-core screen handles any library size (exact scan: k > 8 or d % 64 != 0)
 
 _sm_count: dict = {}

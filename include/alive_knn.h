@@ -222,7 +222,7 @@ typedef struct alive_knn_library {
  *   (used by bench.py to time the dominant kernel inside the timed region), else NULL.
  * Everything is enqueued on `stream`; no host synchronisation (CUDA-graph capturable).
  * alive_knn_match_layout fills 12 byte offsets into the workspace:
- *   0 q_raw 1 q_norm 2 q_packed 3 q_err 4 cand_score 5 cand_idx 6 sel_idx 7 sel_n
+ *   0 q_raw 1 q_norm 2 q_packed 3 q_err 4 cand_score 5 cand_idx 6 (unused) 7 sel_n
  *   8 fb_list 9 fb_count 10 exact scratch 11 TOTAL bytes. */
 int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
                            int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets12_host);

@@ -100,7 +100,6 @@ def test_match_workspace_layout_is_consistent(lib, rows, n, k, mode):
         p = _cabi.Plan()
         assert lib.alive_knn_plan(rows, n, 768, 148, 0, ctypes.byref(p)) == 0
         assert o[5] - o[4] >= rows * p.lists * 8 * 4 and o[6] - o[5] >= rows * p.lists * 8 * 4
-        assert o[7] - o[6] >= rows * 64 * 4       # sel_idx
     assert o[11] - o[10] >= lib.alive_knn_exact_workspace_bytes(rows, n, k, 1)
 
 

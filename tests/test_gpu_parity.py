@@ -98,7 +98,8 @@ def test_screened_path_against_oracle(variant, B, T, N, k, alpha):
 
 
 @pytest.mark.parametrize("T,N,k", [(50, 300, 4), (7, 64, 4), (40, 1000, 8), (10, 700, 16), (5, 4, 4), (33, 20000, 4),
-                                   (3, 70, 64)])
+                                   (3, 70, 64), (16, 5003, 4), (1, 1001, 1), (9, 302, 32), (13, 40001, 8),
+                                   (17, 777, 4)])
 def test_exact_scan_against_oracle(T, N, k):
     rng = np.random.default_rng(T * N + k)
     src = rng.standard_normal((1, 768, T), dtype=np.float32)
