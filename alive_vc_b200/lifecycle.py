@@ -1,0 +1,208 @@
+"""Callers either side of the match: building a voice library on the GPU, matching
+all overlapped windows of an utterance in one call, and the host-buffer realtime loop.
+
+Reference call sites mirrored here (nothing below re-implements the encoders/decoder around them):
+    generate_voice_library.py:30-42   512 random frames written into random slots of `tokens`, saved
+    inference.py:67-84                library = cat([CE(target), VL.tokens], dim=2)
+    inference.py:96-134               per 3x-overlapped window: feat = match_features(CE(spec), tgt)
+    realtime_inference.py:130-191     per audio block: host chunk -> device -> match -> host
+All device work goes through the C ABI (include/alive_knn.h); torch is used for buffers and copies.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import matching as M
+
+
+class LibraryBuilder:
+    """Accumulates library frames on the GPU and emits them in the packed layout.
+
+    `put(slots, frames)` has the semantics of the reference's generation loop
+    (`VL.tokens.data[:, :, n] = t`, generate_voice_library.py:36-38): writes are applied in order, the
+    last write to a slot wins, untouched slots keep their previous content.  `append(frames)` grows
+    the library by whole utterances (inference.py:76 / realtime_inference.py:88 concatenate encoder
+    output the same way), so a library of arbitrary N can be built from a corpus without ever leaving
+    the device.  `packed()` runs K1 (alive_knn_pack) once over the accumulated frames.
+    """
+
+    def __init__(self, d: int = 768, capacity: int = 512, device="cuda", tokens: torch.Tensor | None = None):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("alive_vc_b200: LibraryBuilder needs a CUDA device (no CPU path)")
+        if d < 1 or capacity < 0:
+            raise ValueError("LibraryBuilder: d >= 1 and capacity >= 0 expected")
+        self.d = d
+        self._rows = torch.zeros((max(capacity, 1), d), dtype=torch.float32, device=dev)   # [cap, D] row-major
+        self._n = 0
+        self._packed = None
+        if tokens is not None:
+            self.append(tokens)
+
+    # -- geometry -----------------------------------------------------------------------------
+    def __len__(self) -> int:
+        return self._n
+
+    @property
+    def device(self):
+        return self._rows.device
+
+    def _reserve(self, n: int):
+        if n <= self._rows.shape[0]:
+            return
+        cap = max(n, 2 * self._rows.shape[0])
+        grown = torch.zeros((cap, self.d), dtype=torch.float32, device=self.device)
+        grown[:self._n] = self._rows[:self._n]
+        self._rows = grown
+
+    @staticmethod
+    def _as_dn(frames: torch.Tensor, d: int) -> torch.Tensor:
+        """[1, D, n] / [D, n] / [D] -> [D, n] float32 view."""
+        if frames.dim() == 3:
+            if frames.shape[0] != 1:
+                raise RuntimeError("LibraryBuilder: frames must be [1, D, n], [D, n] or [D]")
+            frames = frames[0]
+        if frames.dim() == 1:
+            frames = frames.unsqueeze(1)
+        if frames.dim() != 2 or frames.shape[0] != d:
+            raise RuntimeError(f"LibraryBuilder: expected {d} channels, got shape {tuple(frames.shape)}")
+        return frames.detach().float()
+
+    # -- writes -------------------------------------------------------------------------------
+    def append(self, frames: torch.Tensor) -> "LibraryBuilder":
+        """Add the n frames of a [1, D, n] / [D, n] tensor after the current last frame."""
+        f = self._as_dn(frames, self.d).to(self.device)
+        n = f.shape[1]
+        self._reserve(self._n + n)
+        self._rows[self._n:self._n + n].copy_(f.t())
+        self._n += n
+        self._packed = None
+        return self
+
+    def put(self, slots, frames: torch.Tensor) -> "LibraryBuilder":
+        """`tokens[:, :, slots[i]] = frames[:, i]` for i = 0..m-1 IN ORDER (last write wins)."""
+        f = self._as_dn(frames, self.d).to(self.device)
+        slots = torch.as_tensor(slots, dtype=torch.int64, device=self.device).reshape(-1)
+        m = slots.numel()
+        if f.shape[1] != m:
+            raise RuntimeError(f"LibraryBuilder.put: {m} slots but {f.shape[1]} frames")
+        if m == 0:
+            return self
+        lo, hi = int(slots.min()), int(slots.max())
+        if lo < 0:
+            raise IndexError("LibraryBuilder.put: negative slot")
+        self._reserve(hi + 1)
+        self._n = max(self._n, hi + 1)
+        # position of the last write to every slot; only those writes land
+        last = torch.full((hi + 1,), -1, dtype=torch.int64, device=self.device)
+        last.scatter_reduce_(0, slots, torch.arange(m, device=self.device), reduce="amax", include_self=True)
+        written = (last >= 0).nonzero().reshape(-1)
+        self._rows[written] = f.t()[last[written]]
+        self._packed = None
+        return self
+
+    # -- reads --------------------------------------------------------------------------------
+    def tokens(self) -> torch.Tensor:
+        """The library as the reference stores it: [1, D, N] float32 (module/voice_library.py:9)."""
+        return self._rows[:self._n].t().unsqueeze(0).contiguous()
+
+    def packed(self) -> M.PackedFrames:
+        if self._n == 0:
+            raise RuntimeError("selected index k out of range")      # an empty library cannot be matched
+        if self._packed is None:
+            self._packed = M.pack_frames(self._rows[:self._n].t())    # [D, N] view of the row-major block
+        return self._packed
+
+    def save(self, path: str):
+        """Packed layout + the reference's own `tokens` key in one file (save_packed_library)."""
+        M.save_packed_library(self.packed(), path, include_legacy_tokens=True)
+
+
+def match_windows(windows, lib: M.PackedFrames, k: int = 4, alpha: float = 0.0, mode: str = "auto"):
+    """All windows of an utterance against one packed library in ONE pipeline launch.
+
+    The reference converts an utterance as 3x-overlapped windows and runs the match once per window
+    (inference.py:96-134, `feat = match_features(feat, tgt, ...)` at :129).  Every window is matched
+    against the same library and frames are matched independently, so the windows can be laid end to
+    end: `windows` is a [W, D, Tw] tensor or a sequence of [1, D, T_i] / [D, T_i] tensors of ragged
+    length.  Returns a list of [1, D, T_i] tensors (transposed views of one contiguous [sum T, D]
+    block), bit-identical to W separate match_features calls.
+    """
+    if isinstance(windows, torch.Tensor):
+        if windows.dim() != 3:
+            raise RuntimeError("match_windows expects [W, D, Tw] or a sequence of [1, D, T_i]")
+        pieces = [windows[w] for w in range(windows.shape[0])]
+    else:
+        pieces = [w[0] if w.dim() == 3 else w for w in windows]
+    if not pieces:
+        return []
+    for p in pieces:
+        if p.dim() != 2 or p.shape[0] != lib.d:
+            raise RuntimeError(f"match_windows: every window must have {lib.d} channels")
+    lens = [int(p.shape[1]) for p in pieces]
+    total = sum(lens)
+    dev = lib.device
+    if total == 0:
+        return [torch.empty((1, lib.d, 0), dtype=torch.float32, device=dev) for _ in pieces]
+    # frames of all windows end to end, already in the kernels' [T, D] row-major order
+    rows = torch.empty((total, lib.d), dtype=torch.float32, device=dev)
+    at = 0
+    for p, n in zip(pieces, lens):
+        rows[at:at + n].copy_(p.t())
+        at += n
+    out, _, _ = M.match_packed(rows.t().unsqueeze(0), lib, k, float(alpha), mode)     # [1, total, D]
+    res, at = [], 0
+    for n in lens:
+        res.append(out[:, at:at + n].transpose(1, 2))
+        at += n
+    return res
+
+
+class HostStreamingMatcher:
+    """The realtime loop's chunk step with HOST buffers (realtime_inference.py:158-176 moves every
+    block host -> device -> host): pinned input and output buffers, and ONE CUDA graph holding the
+    host->device copy, the whole match pipeline and the device->host copy.  A call is a memcpy into
+    the pinned buffer, one graph launch and one event wait.
+
+        hm = HostStreamingMatcher(pack_library(tgt), T=24)
+        out = hm(chunk_cpu)            # [B, D, T] float32 CPU tensor -> [B, D, T] view of the pinned result
+    """
+
+    def __init__(self, lib: M.PackedFrames, T: int, k: int = 4, alpha: float = 0.0, batch: int = 1,
+                 mode: str = "auto", variant: int = 0, r_max: int = M.DEFAULT_R_MAX):
+        dev = lib.device
+        self.inner = M.StreamingMatcher(lib, T, k, alpha, batch, mode, variant, r_max, use_graph=False)
+        self.src_host = torch.zeros((batch, lib.d, T), dtype=torch.float32).pin_memory()
+        self.out_host = torch.zeros((batch, T, lib.d), dtype=torch.float32).pin_memory()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.done = torch.cuda.Event()
+        self.launches_per_call = batch + 4
+        with torch.cuda.stream(self.stream):
+            self._enqueue()                            # warm-up outside capture
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._enqueue()
+
+    def _enqueue(self):
+        self.inner.src.copy_(self.src_host, non_blocking=True)
+        self.inner._run()
+        self.out_host.copy_(self.inner.out, non_blocking=True)
+
+    def submit(self, chunk: torch.Tensor):
+        """Stage `chunk` (CPU, [B, D, T]) and launch; returns immediately (see `result`)."""
+        self.src_host.copy_(chunk)
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+            self.done.record(self.stream)
+        M._count(self.launches_per_call)
+
+    def result(self) -> torch.Tensor:
+        self.done.synchronize()
+        return self.out_host.transpose(1, 2)
+
+    def __call__(self, chunk: torch.Tensor) -> torch.Tensor:
+        self.submit(chunk)
+        return self.result()

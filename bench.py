@@ -412,6 +412,21 @@ def gpu_arm(args):
     e2e_value = units_per_step / (e2e_ms / args.steps * 1e-3)
     io_bytes = src_host.numel() * 4
 
+    # latency workloads: the synchronous host-to-host chunk time of the realtime loop
+    # (realtime_inference.py:158-176) - pinned buffers, ONE graph (H2D + pipeline + D2H), one event wait
+    host_lat = []
+    if latency_workload and world == 1 and not args.no_graph:
+        from alive_vc_b200.lifecycle import HostStreamingMatcher
+        hm = HostStreamingMatcher(lib, T, K, 0.0, batch=B, mode="screen", variant=variant)
+        chunk = src_host.clone()
+        for _ in range(20):
+            hm(chunk)
+        for _ in range(min(args.steps, 2000)):
+            t0 = time.perf_counter()
+            hm(chunk)
+            host_lat.append((time.perf_counter() - t0) * 1e3)
+        host_lat.sort()
+
     if rank == 0:
         # roofline of the dominant kernel: algorithmic flops of ONE alive_knn_search launch
         # (2 * T * N_local * D) over its average CUDA-event duration
@@ -500,6 +515,10 @@ def gpu_arm(args):
         if lat:
             line["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                                   "min": lat[0]}
+        if host_lat:
+            line["host_chunk_latency_ms"] = {"p50": host_lat[len(host_lat) // 2],
+                                             "p99": host_lat[min(len(host_lat) - 1, int(len(host_lat) * 0.99))],
+                                             "min": host_lat[0], "timer": "perf_counter around one blocking call"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

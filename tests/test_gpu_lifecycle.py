@@ -1,0 +1,134 @@
+"""GPU tests of the callers either side of the match: LibraryBuilder
+(generate_voice_library.py:30-42), match_windows (inference.py:96-134) and HostStreamingMatcher
+(realtime_inference.py:158-176), each against the oracle / the plain per-call path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import alive_vc_b200 as A                                   # noqa: E402
+from alive_vc_b200 import matching as M                      # noqa: E402
+from alive_vc_b200.lifecycle import HostStreamingMatcher, LibraryBuilder, match_windows   # noqa: E402
+from oracle import knn_oracle as O                           # noqa: E402
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_builder_put_follows_the_reference_generation_loop():
+    """generate_voice_library.py:36-38: sequential writes into random slots, the last write wins,
+    untouched slots keep the initial tokens."""
+    rng = np.random.default_rng(5)
+    D, N, writes = 768, 512, 513
+    tokens = rng.standard_normal((1, D, N), dtype=np.float32)           # VoiceLibrary() initial randn
+    slots = rng.integers(0, N, size=writes)
+    frames = rng.standard_normal((D, writes), dtype=np.float32)
+    want = tokens.copy()
+    for i in range(writes):                                             # the reference loop, literally
+        want[:, :, slots[i]] = frames[:, i]
+    b = LibraryBuilder(d=D, capacity=N, tokens=_cuda(tokens))
+    assert len(b) == N
+    b.put(slots, _cuda(frames))
+    got = b.tokens()
+    assert tuple(got.shape) == (1, D, N)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # the packed layout is what pack_library makes of the same tokens, bit for bit
+    p, q = b.packed(), A.pack_library(_cuda(want))
+    for name in ("raw", "norms", "packed", "err"):
+        assert torch.equal(getattr(p, name), getattr(q, name)), name
+    # and it matches like the reference library does
+    src = rng.standard_normal((1, D, 40), dtype=np.float32)
+    out, idx, _ = A.match_packed(_cuda(src), p, 4, 0.0)
+    w_out, w_idx, _ = O.match_features_np(src, want, 4, 0.0, True)
+    assert np.array_equal(idx.cpu().numpy(), w_idx)
+    assert np.array_equal(out.cpu().numpy(), np.swapaxes(w_out, 1, 2))
+
+
+def test_builder_append_grows_and_saves(tmp_path):
+    """inference.py:67-84: library = cat([CE(target), VL.tokens], dim=2), any N."""
+    rng = np.random.default_rng(6)
+    D = 768
+    parts = [rng.standard_normal((1, D, n), dtype=np.float32) for n in (130, 1, 700, 0, 2049)]
+    b = LibraryBuilder(d=D, capacity=16)
+    for p in parts:
+        b.append(_cuda(p))
+    want = np.concatenate(parts, axis=2)
+    assert len(b) == want.shape[2]
+    assert np.array_equal(b.tokens().cpu().numpy(), want)
+    path = str(tmp_path / "voice_library.pt")
+    b.save(path)
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    assert np.array_equal(blob["tokens"].numpy(), want)                 # the reference's own key
+    lib = A.load_packed_library(path)
+    src = rng.standard_normal((1, D, 33), dtype=np.float32)
+    _, idx, _ = A.match_packed(_cuda(src), lib, 4, 0.0)
+    _, w_idx, _ = O.match_features_np(src, want, 4, 0.0, True)
+    assert np.array_equal(idx.cpu().numpy(), w_idx)
+    # a strided view (realtime_inference.py:88 subsamples [:, :, ::4]) appends like its copy
+    b2 = LibraryBuilder(d=D, capacity=4)
+    big = _cuda(parts[2])
+    b2.append(big[:, :, ::4])
+    assert np.array_equal(b2.tokens().cpu().numpy(), parts[2][:, :, ::4])
+
+
+def test_builder_errors():
+    b = LibraryBuilder(d=8, capacity=4)
+    with pytest.raises(RuntimeError):
+        b.packed()                                                      # empty library
+    with pytest.raises(RuntimeError):
+        b.append(torch.zeros(1, 7, 3, device="cuda"))                   # wrong channel count
+    with pytest.raises(RuntimeError):
+        b.put([0, 1], torch.zeros(8, 3, device="cuda"))                 # slots / frames mismatch
+    with pytest.raises(IndexError):
+        b.put([-1], torch.zeros(8, 1, device="cuda"))
+
+
+@pytest.mark.parametrize("lens", [[150, 150, 150, 150], [150, 150, 37], [1], [0, 5, 0]])
+def test_match_windows_equals_one_call_per_window(lens):
+    """inference.py:129 runs the match once per overlapped window; one batched launch must give the
+    same bits."""
+    rng = np.random.default_rng(7)
+    D, N, k, alpha = 768, 3512, 4, 0.25
+    ref = rng.standard_normal((1, D, N), dtype=np.float32)
+    lib = A.pack_library(_cuda(ref))
+    wins = [_cuda(rng.standard_normal((1, D, n), dtype=np.float32)) for n in lens]
+    got = match_windows(wins, lib, k, alpha)
+    assert len(got) == len(wins)
+    for w, g in zip(wins, got):
+        assert tuple(g.shape) == tuple(w.shape)
+        if w.shape[2] == 0:
+            continue
+        want = A.match_features(w, _cuda(ref), k, alpha)
+        assert torch.equal(g, want)
+        w_out = O.match_features_np(w.cpu().numpy(), ref, k, alpha)
+        np.testing.assert_allclose(g.cpu().numpy(), w_out, rtol=1e-5, atol=1e-6)
+    if len(set(lens)) == 1:                                             # the [W, D, Tw] tensor form
+        stacked = torch.cat(wins, dim=0)
+        got2 = match_windows(stacked, lib, k, alpha)
+        for a, b_ in zip(got, got2):
+            assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("T,N,batch", [(24, 3512, 1), (32, 20000, 1), (16, 1000, 3)])
+def test_host_streaming_matcher(T, N, batch):
+    """realtime_inference.py:158-176 with host buffers: graph(H2D + pipeline + D2H) == plain call."""
+    rng = np.random.default_rng(8)
+    D, k, alpha = 768, 4, 0.0
+    ref = rng.standard_normal((1, D, N), dtype=np.float32)
+    lib = A.pack_library(_cuda(ref))
+    hm = HostStreamingMatcher(lib, T, k, alpha, batch=batch)
+    for it in range(3):
+        chunk = torch.from_numpy(rng.standard_normal((batch, D, T), dtype=np.float32))
+        out = hm(chunk)
+        assert not out.is_cuda and tuple(out.shape) == (batch, D, T)
+        want, _, _ = A.match_packed(chunk.cuda(), lib, k, alpha)
+        assert torch.equal(out, want.transpose(1, 2).cpu())
+        w_out = O.match_features_np(chunk.numpy(), np.broadcast_to(ref, (batch, D, N)), k, alpha)
+        np.testing.assert_allclose(out.numpy(), w_out, rtol=1e-5, atol=1e-6)
+    # submit / result split: the host may do other work between the two
+    chunk = torch.from_numpy(rng.standard_normal((batch, D, T), dtype=np.float32))
+    hm.submit(chunk)
+    want, _, _ = A.match_packed(chunk.cuda(), lib, k, alpha)
+    assert torch.equal(hm.result(), want.transpose(1, 2).cpu())

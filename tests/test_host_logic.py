@@ -63,3 +63,11 @@ def test_shard_bounds_partition(n, world):
         assert lo == prev and hi >= lo and hi - lo in (n // world, n // world + 1)
         prev = hi
     assert prev == n
+
+
+def test_lifecycle_host_logic_without_a_gpu():
+    """LibraryBuilder has no CPU path; match_windows of nothing is nothing."""
+    from alive_vc_b200.lifecycle import LibraryBuilder, match_windows
+    with pytest.raises(RuntimeError, match="CUDA"):
+        LibraryBuilder(device="cpu")
+    assert match_windows([], None) == []
