@@ -157,7 +157,8 @@ def load():
                 raise RuntimeError(
                     f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                     "(nvcc, sm_100a). alive_vc_b200 has no CPU or PyTorch fallback.")
-            lib = ctypes.CDLL(LIB_PATH)
+            # ALIVE_KNN_LIB: an instrumented build of the same sources (tests/gpu_tools/finish_phases.py)
+            lib = ctypes.CDLL(os.environ.get("ALIVE_KNN_LIB") or LIB_PATH)
             _declare(lib)
             if lib.alive_knn_abi_version() != 2:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")

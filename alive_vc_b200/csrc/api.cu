@@ -120,8 +120,10 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
 
   for (int32_t b = 0; b < batch; ++b) {
     const size_t r0 = static_cast<size_t>(b) * t;
-    rc = alive_knn_pack(source + static_cast<int64_t>(b) * stride_b, t, d, stride_t, stride_d, q_raw + r0 * d,
-                        q_norm + r0, q_packed + r0 * d, q_err + r0, nullptr, stream);
+    // the first pack launch also zeroes the per-item fallback counters (no separate memset node)
+    rc = pack_impl(source + static_cast<int64_t>(b) * stride_b, t, d, stride_t, stride_d, q_raw + r0 * d,
+                   q_norm + r0, q_packed + r0 * d, q_err + r0, nullptr, b == 0 ? fb_count : nullptr, b == 0 ? items : 0,
+                   stream);
     if (rc) return rc;
   }
   if (mode == 1) {
@@ -130,16 +132,15 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
     if (rc) return rc;
     if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
-    rc = alive_knn_finish(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
-                          lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
-                          fb_count, items, stream);
+    rc = finish_impl(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
+                     lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
+                     fb_count, items, 0, stream);
     if (rc) return rc;
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, fb_list, fb_count, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;
   } else {
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
-    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, 4 * items, as_stream(stream)));
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;

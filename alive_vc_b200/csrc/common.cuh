@@ -29,6 +29,17 @@ void set_error(const char* fmt, ...);
     }                                     \
   } while (0)
 
+// internal variants of two ABI entry points used by the one-call pipeline (api.cu): the query pack also
+// zeroes the per-item fallback counters, so that alive_knn_finish needs no memset node of its own
+int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
+              uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
+              alive_stream_t stream);
+int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
+                const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
+                const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
+                int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx, int32_t* sel_n,
+                int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, alive_stream_t stream);
+
 static inline cudaStream_t as_stream(alive_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Ordering used everywhere a top-k is taken (mirrors torch.topk: NaN ranks above

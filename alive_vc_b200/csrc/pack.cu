@@ -31,8 +31,10 @@ template <int kFrames>
 __global__ void __launch_bounds__(kPackThreads)
 pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
             float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
-            float* __restrict__ err, unsigned int* __restrict__ stats) {
+            float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
   extern __shared__ float tile[];          // [d][kFrames + 1]
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
   const int ld = kFrames + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long f0 = static_cast<long long>(blockIdx.x) * kFrames;
@@ -101,8 +103,10 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
 __global__ void __launch_bounds__(kPackThreads)
 pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
                   float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
-                  float* __restrict__ err, unsigned int* __restrict__ stats) {
+                  float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
   __shared__ double red[kPackThreads / 32];
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
   __shared__ int fin[kPackThreads / 32];
   const long long row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,15 +169,18 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long str
 }  // namespace
 }  // namespace alive
 
-extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
-                              float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
-                              alive_stream_t stream) {
-  using namespace alive;
+namespace alive {
+int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
+              uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
+              alive_stream_t stream) {
   ALIVE_REQUIRE(x && raw && norms && packed, "alive_knn_pack: NULL argument");
   ALIVE_REQUIRE(n >= 0 && n < (1ll << 31), "alive_knn_pack: n out of range (%lld)", static_cast<long long>(n));
   ALIVE_REQUIRE(d >= 2 && d % 2 == 0 && d <= 1536, "alive_knn_pack: d must be even and <= 1536 (got %d)", d);
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 3) == 0, "alive_knn_pack: packed must be 4-byte aligned");
-  if (n == 0) return 0;
+  if (n == 0) {
+    if (n_zero > 0) ALIVE_CHECK_CUDA(cudaMemsetAsync(zero_words, 0, sizeof(int32_t) * n_zero, as_stream(stream)));
+    return 0;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
@@ -183,16 +190,23 @@ extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stri
   __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
   if (n <= 512) {
     pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw,
-                                                                                       norms, pk, err, stats);
+                                                                                       norms, pk, err, stats, zero_words, n_zero);
   } else if (n <= 8192) {
     const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
     pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats);
+        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
   } else {
     const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
     pack_kernel<32><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats);
+        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
   }
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+}  // namespace alive
+
+extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
+                              float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
+                              alive_stream_t stream) {
+  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream);
 }

@@ -110,14 +110,26 @@ prune_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dot_norm_f64(const float* __restrict__ qh, const float* __restrict__ row,
                                                float nrm, int d, int lane) {
+  // the frame's chunks are fetched 6 at a time BEFORE any arithmetic: one DRAM round trip per
+  // 768 channels instead of one per 128 (this runs at low occupancy, latency is the cost);
+  // the accumulation order (j ascending per lane) does not change
+  constexpr int kBatch = 6;
   double acc = 0.0;
-  for (int j = lane * 4; j < d; j += 128) {
-    const float4 r = *reinterpret_cast<const float4*>(row + j);
-    const float4 a = *reinterpret_cast<const float4*>(qh + j);
-    acc += static_cast<double>(a.x) * static_cast<double>(__fdiv_rn(r.x, nrm));
-    acc += static_cast<double>(a.y) * static_cast<double>(__fdiv_rn(r.y, nrm));
-    acc += static_cast<double>(a.z) * static_cast<double>(__fdiv_rn(r.z, nrm));
-    acc += static_cast<double>(a.w) * static_cast<double>(__fdiv_rn(r.w, nrm));
+  for (int j0 = lane * 4; j0 < d; j0 += kBatch * 128) {
+    float4 r[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      if (j0 + i * 128 < d) r[i] = *reinterpret_cast<const float4*>(row + j0 + i * 128);
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      if (j0 + i * 128 < d) {
+        const float4 a = *reinterpret_cast<const float4*>(qh + j0 + i * 128);
+        acc += static_cast<double>(a.x) * static_cast<double>(__fdiv_rn(r[i].x, nrm));
+        acc += static_cast<double>(a.y) * static_cast<double>(__fdiv_rn(r[i].y, nrm));
+        acc += static_cast<double>(a.z) * static_cast<double>(__fdiv_rn(r[i].z, nrm));
+        acc += static_cast<double>(a.w) * static_cast<double>(__fdiv_rn(r[i].w, nrm));
+      }
+    }
   }
   return warp_sum_f64(acc);
 }
@@ -248,8 +260,31 @@ __device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_ra
   }
 }
 
+#ifdef ALIVE_FINISH_TIMING
+__device__ unsigned long long g_finish_t[16];
+#define ALIVE_FT(i)                                                         \
+  do {                                                                      \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                              \
+      g_finish_t[i] = static_cast<unsigned long long>(clock64());          \
+    }                                                                       \
+  } while (0)
+#else
+#define ALIVE_FT(i)
+#endif
 constexpr int kFinishThreads = 256;
 constexpr int kFinishMaxStagedEntries = 6144;   // lists*8 entries staged in shared memory (48 KB) when they fit
+
+// monotone map score -> uint32 (larger score = larger key, -0 == +0, NaN above everything, 0 is
+// below every score): lets the selections below run on redux.sync instead of shuffle trees
+__device__ __forceinline__ unsigned score_key(float s) {
+  if (s != s) return 0xFFFFFFFFu;
+  const unsigned u = __float_as_uint(s + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_score(unsigned key) {
+  if (key == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
+  return __uint_as_float((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key);
+}
 
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
@@ -262,20 +297,26 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
               int* __restrict__ fb_count, int staged, int t_item) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qh = reinterpret_cast<float*>(smem_raw);                         // [d]
-  long long* cid = reinterpret_cast<long long*>(qh + d);                  // [r_max]
+  long long* cid = reinterpret_cast<long long*>(qh + d);                  // [r_max] (layout shared with rescore_kernel)
   float* csc = reinterpret_cast<float*>(cid + r_max);                     // [r_max]
   int* sel = reinterpret_cast<int*>(csc + r_max);                         // [r_max]
   float* st_sc = reinterpret_cast<float*>(sel + r_max);                   // [entries] (staged only)
   int* st_ix = reinterpret_cast<int*>(st_sc + (staged ? lists * kListLen : 0));
-  __shared__ int s_count;
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int s_total;
+  __shared__ int s_fb;
   __shared__ float s_cut;
-  __shared__ float s_tau[kThreads / 32];
-  __shared__ int s_wcnt[kThreads / 32];
-  __shared__ float s_wbest[(kThreads / 32) * kListLen];
+  __shared__ unsigned s_tau[kWarps];
+  __shared__ unsigned s_wbest[kWarps * kListLen];
   __shared__ long long s_top[kMaxK];
+  ALIVE_FT(0);
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // everything the certificate needs from global memory is requested up front
   const float qn = q_norm[q];
+  const float qe = q_err[q];
+  const unsigned le_bits = lib_stats[0];
+  const unsigned lib_bad = lib_stats[1];
   const size_t entries = static_cast<size_t>(lists) * kListLen;
   const float* g_sc = cand_score + q * entries;
   const int* g_ix = cand_idx + q * entries;
@@ -288,130 +329,168 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   }
   for (int j = threadIdx.x; j < d; j += kThreads)
     qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
+  if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
+  ALIVE_FT(1);
   // ---- certificate + survivor compaction, spread over the whole CTA (prune_query's logic) ----
+  const float* sc = staged ? st_sc : g_sc;
+  const int* ix = staged ? st_ix : g_ix;
+  const int n_entries = static_cast<int>(entries);
   {
-    const float* sc = staged ? st_sc : g_sc;
-    const int* ix = staged ? st_ix : g_ix;
-    const int n_entries = static_cast<int>(entries);
-    constexpr int kWarps = kThreads / 32;
     // tau = max of the list minima
-    float tau = -INFINITY;
-    for (int l = threadIdx.x; l < lists; l += kThreads) tau = fmaxf(tau, sc[l * kListLen + kListLen - 1]);
-    tau = warp_max_f32(tau);
+    unsigned tau = 0u;
+    for (int l = threadIdx.x; l < lists; l += kThreads) tau = max(tau, score_key(sc[l * kListLen + kListLen - 1]));
+    tau = __reduce_max_sync(0xffffffffu, tau);
     if (lane == 0) s_tau[warp] = tau;
-    // every warp: the k best entries of its contiguous slice, under (score desc, position asc)
+    // every warp: the k largest keys of its contiguous slice (duplicates count).  A lane keeps the
+    // sorted top-k of its own entries in registers, then k rounds of redux-max + pop.
     const int e_lo = static_cast<int>(static_cast<long long>(n_entries) * warp / kWarps);
     const int e_hi = static_cast<int>(static_cast<long long>(n_entries) * (warp + 1) / kWarps);
-    float prev_s = INFINITY;
-    int prev_p = -1;
-    for (int r = 0; r < k; ++r) {
-      float best_s = -INFINITY;
-      int best_p = 0x7fffffff;
-      for (int e = e_lo + lane; e < e_hi; e += 32) {
-        const float v = sc[e];
-        const bool after_prev = (v < prev_s) || (v == prev_s && e > prev_p);
-        if (after_prev && (v > best_s || (v == best_s && e < best_p))) {
-          best_s = v;
-          best_p = e;
-        }
-      }
+    unsigned best[kListLen];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float os = __shfl_xor_sync(0xffffffffu, best_s, o);
-        const int op = __shfl_xor_sync(0xffffffffu, best_p, o);
-        if (os > best_s || (os == best_s && op < best_p)) {
-          best_s = os;
-          best_p = op;
-        }
+    for (int i = 0; i < kListLen; ++i) best[i] = 0u;
+    for (int e = e_lo + lane; e < e_hi; e += 32) {
+      unsigned v = score_key(sc[e]);
+#pragma unroll
+      for (int i = 0; i < kListLen; ++i) {       // sorted insert (descending); entries beyond k are never read
+        const unsigned hi = max(best[i], v);
+        v = min(best[i], v);
+        best[i] = hi;
       }
-      prev_s = best_s;
-      prev_p = best_p;
-      if (lane == 0) s_wbest[warp * kListLen + r] = best_s;    // -inf when the slice ran out
     }
-    __syncthreads();
-    if (warp == 0) {
-      // S_k = k-th largest of the kWarps*k slice winners (values only; duplicates count)
-      float v = (lane < kWarps * k) ? s_wbest[(lane / k) * kListLen + (lane % k)] : -INFINITY;
-      float v2 = (lane + 32 < kWarps * k) ? s_wbest[((lane + 32) / k) * kListLen + ((lane + 32) % k)] : -INFINITY;
-      float sk = -INFINITY;
-      for (int r = 0; r < k; ++r) {
-        const float m = warp_max_f32(fmaxf(v, v2));
-        sk = m;
-        // remove ONE occurrence of the maximum (lowest lane first, first slot first)
-        const unsigned has = __ballot_sync(0xffffffffu, v == m || v2 == m);
-        if (has == 0) break;
-        const int src = __ffs(static_cast<int>(has)) - 1;
-        if (lane == src) {
-          if (v == m) v = -INFINITY;
-          else v2 = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      const unsigned m = __reduce_max_sync(0xffffffffu, best[0]);
+      if (lane == 0) s_wbest[warp * kListLen + r] = m;      // 0 when the slice ran out
+      const unsigned has = __ballot_sync(0xffffffffu, best[0] == m);
+      if (lane == __ffs(static_cast<int>(has)) - 1) {
+#pragma unroll
+        for (int i = 0; i + 1 < kListLen; ++i) best[i] = best[i + 1];
+        best[kListLen - 1] = 0u;
+      }
+    }
+  }
+  __syncthreads();
+  ALIVE_FT(2);
+  if (warp == 0) {
+    // S_k = k-th largest of the kWarps*k slice winners (values only; duplicates count)
+    constexpr int kPer = (kWarps * kListLen + 31) / 32;
+    unsigned v[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int e = lane + 32 * i;
+      v[i] = (e < kWarps * k) ? s_wbest[(e / k) * kListLen + (e % k)] : 0u;
+    }
+    unsigned sk_key = 0u;
+    for (int r = 0; r < k; ++r) {
+      unsigned m = v[0];
+#pragma unroll
+      for (int i = 1; i < kPer; ++i) m = max(m, v[i]);
+      const unsigned mine = m;
+      m = __reduce_max_sync(0xffffffffu, m);
+      sk_key = m;
+      // remove ONE occurrence of the maximum (lowest lane first, first slot first)
+      const unsigned has = __ballot_sync(0xffffffffu, mine == m);
+      if (lane == __ffs(static_cast<int>(has)) - 1) {
+        bool gone = false;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          if (!gone && v[i] == m) {
+            v[i] = 0u;
+            gone = true;
+          }
         }
       }
-      float t2 = (lane < kWarps) ? s_tau[lane] : -INFINITY;
-      t2 = warp_max_f32(t2);
-      const float le = __uint_as_float(lib_stats[0]);
-      const float qe = q_err[q];
+    }
+    unsigned t2k = (lane < kWarps) ? s_tau[lane] : 0u;     // kWarps <= 32
+    t2k = __reduce_max_sync(0xffffffffu, t2k);
+    if (lane == 0) {
+      const float sk = sk_key == 0u ? -INFINITY : key_score(sk_key);
+      const float t2 = t2k == 0u ? -INFINITY : key_score(t2k);
+      const float le = __uint_as_float(le_bits);
       const float eps = (le + qe + le * qe + kAccumSlack) * 1.00001f;
       const float cut = sk - 2.0f * eps - 1e-7f;
-      const bool fb = lib_stats[1] != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > t2);
-      if (lane == 0) {
-        s_cut = cut;
-        s_count = fb ? -1 : 0;
+      const bool fb = lib_bad != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > t2);
+      s_cut = cut;
+      s_fb = fb ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  ALIVE_FT(3);
+  int n_sel = -1;
+  if (s_fb == 0) {
+    // compaction of the survivors: one shared-memory atomic per warp and pass (the order of the
+    // survivors is immaterial - the final selection is a total order on (score, index))
+    const float cut = s_cut;
+    for (int e0 = 0; e0 < n_entries; e0 += kThreads) {
+      const int e = e0 + threadIdx.x;
+      const bool keep = e < n_entries && sc[e] >= cut && ix[e] >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m != 0u) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_total, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < r_max) sel[pos] = ix[e];
       }
     }
     __syncthreads();
-    if (s_count == 0) {
-      // ordered compaction of the survivors (entry order), whole CTA
-      const float cut = s_cut;
-      int base = 0;
-      for (int e0 = 0; e0 < n_entries; e0 += kThreads) {
-        const int e = e0 + threadIdx.x;
-        const bool keep = e < n_entries && sc[e] >= cut && ix[e] >= 0;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_wcnt[warp] = __popc(m);
-        __syncthreads();
-        int before = base;
-        for (int w = 0; w < warp; ++w) before += s_wcnt[w];
-        int total = 0;
-        for (int w = 0; w < kWarps; ++w) total += s_wcnt[w];
-        const int pos = before + __popc(m & ((1u << lane) - 1u));
-        if (keep && pos < r_max) sel[pos] = ix[e];
-        base += total;
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) s_count = (base > r_max || base < k) ? -1 : base;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      const int count = s_count;
-      sel_n[q] = count;
-      if (count < 0) {
-        const int item = q / t_item;                      // uncertified queries are listed per item
-        fb_list[static_cast<size_t>(item) * t_item + atomicAdd(&fb_count[item], 1)] = q;
-      }
+    const int total = s_total;
+    n_sel = (total > r_max || total < k) ? -1 : total;
+  }
+  ALIVE_FT(4);
+  if (threadIdx.x == 0) {
+    sel_n[q] = n_sel;
+    if (n_sel < 0) {
+      const int item = q / t_item;                      // uncertified queries are listed per item
+      fb_list[static_cast<size_t>(item) * t_item + atomicAdd(&fb_count[item], 1)] = q;
     }
   }
-  const int n_sel = s_count;
   if (n_sel < 0) return;   // the exact scan (and its gather) handle this query
-  for (int c = warp; c < n_sel; c += kThreads / 32) {
+  for (int c = warp; c < n_sel; c += kWarps) {
     const int idx = sel[c];
     const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
-    if (lane == 0) {
-      csc[c] = static_cast<float>(acc);
-      cid[c] = idx;
+    if (lane == 0) csc[c] = static_cast<float>(acc);
+  }
+  __syncthreads();
+  ALIVE_FT(5);
+  if (warp == 0) {
+    // exact top-k of the survivors under (score desc, NaN first, index asc): k rounds of
+    // redux-max on the score key, redux-min on the index among the lanes that hold that key
+    unsigned taken = 0u;                                  // bit i: entry lane + 32*i is already out
+    for (int r = 0; r < k; ++r) {
+      unsigned bk = 0u;
+      int bi = 0x7fffffff, bslot = -1;
+      for (int i = 0, c = lane; c < n_sel; ++i, c += 32) {
+        if (taken & (1u << i)) continue;
+        const unsigned key = score_key(csc[c]);
+        const int idx = sel[c];
+        if (bslot < 0 || key > bk || (key == bk && idx < bi)) {
+          bk = key;
+          bi = idx;
+          bslot = i;
+        }
+      }
+      const unsigned m = __reduce_max_sync(0xffffffffu, bslot >= 0 ? bk : 0u);
+      const int cand = (bslot >= 0 && bk == m) ? bi : 0x7fffffff;
+      const int wi = __reduce_min_sync(0xffffffffu, cand);
+      if (bslot >= 0 && bk == m && bi == wi) {              // exactly one lane: indices are distinct
+        taken |= 1u << bslot;
+        const float sv = csc[lane + 32 * bslot];
+        s_top[r] = static_cast<long long>(wi) + idx_base;
+        top_score[static_cast<size_t>(q) * k + r] = sv;
+        top_idx[static_cast<size_t>(q) * k + r] = static_cast<long long>(wi) + idx_base;
+      }
     }
   }
-  __syncthreads();
-  if (warp == 0) {
-    warp_select_topk(csc, cid, n_sel, k, top_score + static_cast<size_t>(q) * k, top_idx + static_cast<size_t>(q) * k,
-                     idx_base, lane);
-  }
   if (out == nullptr) return;
-  __syncthreads();   // top_idx of this query was written by warp 0: stage it for the whole CTA
-  if (threadIdx.x < k) s_top[threadIdx.x] = top_idx[static_cast<size_t>(q) * k + threadIdx.x];
   __syncthreads();
+  ALIVE_FT(7);
   gather_mean_row(lib_raw, n, d, s_top, idx_base, k, q_raw + static_cast<size_t>(q) * d, a1, a0,
                   out + static_cast<size_t>(q) * d, threadIdx.x, kThreads);
+#ifdef ALIVE_FINISH_TIMING
+  __syncthreads();
+  ALIVE_FT(8);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -992,13 +1071,12 @@ extern "C" int alive_knn_merge(const float* scores, const int64_t* idx, int32_t 
   return 0;
 }
 
-extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
-                                const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
-                                const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
-                                int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx,
-                                int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, int32_t items,
-                                alive_stream_t stream) {
-  using namespace alive;
+namespace alive {
+int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
+                const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
+                const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
+                int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx, int32_t* sel_n,
+                int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, alive_stream_t stream) {
   ALIVE_REQUIRE(cand_score && cand_idx && q_raw && q_norm && q_err && lib_raw && lib_norm && lib_stats && top_score &&
                     top_idx && sel_n && fb_list && fb_count,
                 "alive_knn_finish: NULL argument");
@@ -1010,19 +1088,21 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
   ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "alive_knn_finish: raw/out buffers must be 16-byte aligned");
   ALIVE_REQUIRE(out == nullptr || idx_base == 0, "alive_knn_finish: gather needs an unsharded library");
-  ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * items, as_stream(stream)));
+  if (zero_counts) ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * items, as_stream(stream)));
   const int entries = lists * kListLen;
   const int staged = entries <= kFinishMaxStagedEntries ? 1 : 0;
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
                       (staged ? static_cast<size_t>(entries) * 8 : 0);
   static bool attr_done = false;
-  // 0 = by batch size: 256 threads x 4 CTAs/SM finishes a small batch soonest (latency), 128 threads
-  // x 8 CTAs/SM keeps more queries in flight once the batch spans many waves (measured at T = 10k:
-  // 360 -> 286 us); ALIVE_KNN_FINISH_THREADS=128|256 forces one
+  // 0 = by batch size: 128 threads x 8 CTAs/SM keeps more queries in flight once the batch spans many
+  // waves (measured at T = 10k: 360 -> 286 us), 256 x 4 in between, 512 / 1024 threads when there are
+  // fewer queries than SMs can hold; ALIVE_KNN_FINISH_THREADS=128|256|512|1024 forces one
   static int variant = 0;
   if (!attr_done) {
     ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
     ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
     const char* v = getenv("ALIVE_KNN_FINISH_THREADS");
     if (v) variant = atoi(v);
     attr_done = true;
@@ -1033,10 +1113,33 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
   finish_kernel<TH, B><<<t, TH, smem, as_stream(stream)>>>(                                                          \
       cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1, \
       alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items)
-  const int threads = variant == 128 || variant == 256 ? variant : (t >= 4096 ? 128 : 256);
+  // a batch that does not fill the GPU is pure latency: give every query a whole SM's worth of warps
+  // (one survivor frame per warp in flight -> the rescoring is a single DRAM round trip)
+  const int threads = variant == 128 || variant == 256 || variant == 512 || variant == 1024
+                          ? variant
+                          : (t >= 4096 ? 128 : t > 296 ? 256 : t > 148 ? 512 : 1024);
   if (threads == 128) ALIVE_LAUNCH_FINISH(128, 8);
-  else ALIVE_LAUNCH_FINISH(256, 4);
+  else if (threads == 256) ALIVE_LAUNCH_FINISH(256, 4);
+  else if (threads == 512) ALIVE_LAUNCH_FINISH(512, 2);
+  else ALIVE_LAUNCH_FINISH(1024, 1);
 #undef ALIVE_LAUNCH_FINISH
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+}  // namespace alive
+
+extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
+                                const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
+                                const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
+                                int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx,
+                                int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, int32_t items,
+                                alive_stream_t stream) {
+  return alive::finish_impl(cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max,
+                            idx_base, alpha, out, top_score, top_idx, sel_n, fb_list, fb_count, items, 1, stream);
+}
+
+#ifdef ALIVE_FINISH_TIMING
+extern "C" int alive_knn_debug_finish_times(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, alive::g_finish_t, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
