@@ -38,7 +38,7 @@ class Plan(ctypes.Structure):
         ("t", ctypes.c_int32), ("n", ctypes.c_int64), ("d", ctypes.c_int32),
         ("ctas_per_unit", ctypes.c_int32), ("m_units", ctypes.c_int32), ("n_tiles", ctypes.c_int32),
         ("segments", ctypes.c_int32), ("tiles_per_segment", ctypes.c_int32), ("lists", ctypes.c_int32),
-        ("grid", ctypes.c_int32), ("items", ctypes.c_int32),
+        ("grid", ctypes.c_int32), ("items", ctypes.c_int32), ("kernel", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -160,7 +160,7 @@ def load():
             # ALIVE_KNN_LIB: an instrumented build of the same sources (tests/gpu_tools/finish_phases.py)
             lib = ctypes.CDLL(os.environ.get("ALIVE_KNN_LIB") or LIB_PATH)
             _declare(lib)
-            if lib.alive_knn_abi_version() != 2:
+            if lib.alive_knn_abi_version() != 3:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")
             _lib = lib
     return _lib

@@ -128,7 +128,9 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   }
   if (mode == 1) {
     if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
-    rc = alive_knn_search(q_packed, lib->packed, &plan, cand_score, cand_idx, stream);
+    // the search may start behind the (still running) query pack: see search_impl
+    static const bool pdl = !(getenv("ALIVE_KNN_PDL") && atoi(getenv("ALIVE_KNN_PDL")) == 0);
+    rc = search_impl(q_packed, lib->packed, &plan, cand_score, cand_idx, (pdl && !ev_search_start) ? 1 : 0, stream);
     if (rc) return rc;
     if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");

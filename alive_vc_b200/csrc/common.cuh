@@ -34,11 +34,21 @@ void set_error(const char* fmt, ...);
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
               alive_stream_t stream);
+// `after_query_pack`: the launch directly follows the query pack of the same call in `stream`; kernels
+// that can use it start early (programmatic dependent launch) and wait for the pack on the device
+int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,
+                int32_t* cand_idx, int after_query_pack, alive_stream_t stream);
 int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists, int32_t k,
                 const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
                 const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
                 int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx, int32_t* sel_n,
                 int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, alive_stream_t stream);
+
+// programmatic dependent launch (sm_90+): `launch_dependents` lets the next kernel of the stream be
+// scheduled while this one still runs, `wait` blocks until the kernels it depends on have completed and
+// their writes are visible.  Both are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 static inline cudaStream_t as_stream(alive_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -33,6 +33,7 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
             float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
             float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
   extern __shared__ float tile[];          // [d][kFrames + 1]
+  pdl_launch_dependents();                 // a search launched behind this pack may start streaming the library
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
   const int ld = kFrames + 1;
@@ -105,6 +106,7 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long str
                   float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
                   float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
   __shared__ double red[kPackThreads / 32];
+  pdl_launch_dependents();                 // a search launched behind this pack may start streaming the library
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
   __shared__ int fin[kPackThreads / 32];

@@ -554,6 +554,225 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// "skinny" kernel: at most 32 query frames (one realtime chunk, BASELINE cfg2).  The library streams
+// through ONCE and nothing else is worth staging, so the roles of the operands are swapped:
+//   A (M = 128) = a 128-frame library tile, 16 KB per 64-channel block, a deep TMA ring of its own;
+//   B (N = 32)  = the query chunk, resident in shared memory for the whole launch (d/64 x 4 KB).
+// Every byte of the ring is library data (the tiled kernel re-fetches a 16 KB query tile with every
+// 32 KB of library), so ~25% more HBM traffic is in flight per SM - this regime is bound by exactly that.
+// The accumulator is [128 frames (TMEM lanes) x 32 queries (columns)]: 16 of them fit in TMEM, the
+// MMA warp runs up to 16 tiles ahead.  An epilogue warp reads its 32-lane quarter (thread = frame),
+// transposes the 32 x 32 block through shared memory (thread = query) and folds it into the
+// per-query top list it keeps in registers; the four warps' lists are merged at the end, so the
+// launch leaves ONE list per CTA and query: lists = grid.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSkinnyQ = 32;                                   // query rows (MMA N)
+constexpr int kSkinnyThreads = 256;                            // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 epilogue
+constexpr int kSkinnySlots = 16;                               // accumulators of 32 TMEM columns
+constexpr uint32_t kSkinnyQBytes = kSkinnyQ * kBlockK * 2;     // 4 KB per channel block
+constexpr uint32_t kSkinnyTbFloats = 32 * 33;                  // transpose buffer per epilogue warp
+constexpr uint32_t kSkinnySmemMax = 227 * 1024;
+
+struct SkinnyParams {
+  int t, n, k_blocks, n_tiles, stages, lists, contig;
+  float* cand_score;
+  int* cand_idx;
+};
+
+__host__ __device__ inline uint32_t skinny_fixed_bytes(int k_blocks) {
+  return static_cast<uint32_t>(k_blocks) * kSkinnyQBytes + 4 * kSkinnyTbFloats * 4 + 1024 /*align slack*/ + 1024 /*barriers*/;
+}
+
+__global__ void __launch_bounds__(kSkinnyThreads, 1)
+knn_search_skinny_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_lib,
+                         const SkinnyParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_q = smem_base;                                              // [k_blocks][32 x 128 B]
+  const uint32_t smem_a = smem_q + static_cast<uint32_t>(p.k_blocks) * kSkinnyQBytes;   // [stages][128 x 128 B]
+  const uint32_t tb_off = static_cast<uint32_t>(p.k_blocks) * kSkinnyQBytes + static_cast<uint32_t>(p.stages) * kABytes;
+  const uint32_t bars = smem_base + tb_off + 4 * kSkinnyTbFloats * 4;
+  const uint32_t bar_full = bars;                                   // stages x 8 B
+  const uint32_t bar_empty = bars + 8 * p.stages;                   // stages x 8 B
+  const uint32_t bar_tfull = bars + 16 * p.stages;                  // 16 x 8 B
+  const uint32_t bar_tempty = bar_tfull + 8 * kSkinnySlots;         // 16 x 8 B
+  const uint32_t bar_q = bar_tempty + 8 * kSkinnySlots;             // 8 B
+  const uint32_t tmem_slot = bar_q + 8;                             // 4 B
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_lib);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < kSkinnySlots; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);      // one tcgen05.commit
+      mbar_init(bar_tempty + 8 * a, 4);     // one arrive per epilogue warp
+    }
+    mbar_init(bar_q, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, kTmemCols);
+    tmem_relinquish<1>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    // the library does not depend on the query pack that may still be running in front of this launch
+    // (programmatic dependent launch): start streaming right away
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(bar_full + 8 * stage, kABytes);
+          if (p.contig)
+            tma_load_2d<1>(smem_a + stage * kABytes, &tmap_lib, bar_full + 8 * stage, 0, (tile * p.k_blocks + kb) * kBlockM,
+                           kL2EvictFirst);
+          else
+            tma_load_2d<1>(smem_a + stage * kABytes, &tmap_lib, bar_full + 8 * stage, kb * kBlockK, tile * kBlockM,
+                           kL2EvictFirst);
+        }
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(p.stages)) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc = make_idesc(kBlockM, kSkinnyQ);
+    mbar_wait(bar_q, 0);
+    tcgen05_fence_after();
+    uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * slot, slot_phase ^ 1u);   // the epilogue drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + slot * kSkinnyQ;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t adesc = make_smem_desc(smem_a + stage * kABytes);
+          const uint64_t bdesc = make_smem_desc(smem_q + kb * kSkinnyQBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16<1>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit<1>(bar_empty + 8 * stage);
+          if (kb == p.k_blocks - 1) umma_commit<1>(bar_tfull + 8 * slot);
+        }
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(p.stages)) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++slot == kSkinnySlots) {
+        slot = 0;
+        slot_phase ^= 1u;
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ query chunk (resident B operand) ================================
+    pdl_wait();                                                     // the query pack of this call has finished
+    if (elect_one_sync()) {
+      mbar_expect_tx(bar_q, static_cast<uint32_t>(p.k_blocks) * kSkinnyQBytes);
+      for (int kb = 0; kb < p.k_blocks; ++kb)
+        tma_load_2d<1>(smem_q + kb * kSkinnyQBytes, &tmap_q, bar_q, kb * kBlockK, 0, kL2EvictNormal);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31
+    float* tb = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + tb_off) + quarter * kSkinnyTbFloats;
+    const bool q_valid = lane < p.t;                                // lane = query once transposed
+    float s[kListLen];
+    uint32_t id[kListLen];
+#pragma unroll
+    for (int i = 0; i < kListLen; ++i) {
+      s[i] = q_valid ? -INFINITY : INFINITY;                        // padded queries never insert
+      id[i] = 0xFFFFFFFFu;
+    }
+    uint32_t slot = 0, slot_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tfull + 8 * slot, slot_phase);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * kSkinnyQ, v);
+      tmem_ld_wait(v);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+      if (++slot == kSkinnySlots) {
+        slot = 0;
+        slot_phase ^= 1u;
+      }
+      // thread = frame (32*quarter + lane of this tile) -> thread = query
+      const int row0 = tile * kBlockM + quarter * 32;
+      const bool row_ok = row0 + lane < p.n;                        // ragged last tile: TMA zero fill
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = row_ok ? __uint_as_float(v[j]) : -INFINITY;
+      __syncwarp();
+      float m = tb[lane];
+#pragma unroll
+      for (int r = 1; r < 32; ++r) m = fmaxf(m, tb[r * 33 + lane]);
+      if (m > s[kListLen - 1]) {
+#pragma unroll 1
+        for (int r = 0; r < 32; ++r) {
+          const float x = tb[r * 33 + lane];
+          if (x > s[kListLen - 1]) list_insert(s, id, x, static_cast<uint32_t>(row0 + r));
+        }
+      }
+      __syncwarp();
+    }
+    // ---- merge the four quarters' lists: every warp parks its lists, warp 4 folds them ----
+    // (named barrier 1 over the 128 epilogue threads; the transpose buffers are free now)
+    float* park_s = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + tb_off);   // [4][8][32]
+    uint32_t* park_i = reinterpret_cast<uint32_t*>(park_s + 4 * kListLen * 32);                            // [4][8][32]
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < kListLen; ++i) {
+      park_s[(quarter * kListLen + i) * 32 + lane] = s[i];
+      park_i[(quarter * kListLen + i) * 32 + lane] = id[i];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (quarter == 0 && q_valid) {
+      pdl_wait();      // (already satisfied: the accumulators needed the query chunk) orders the list stores
+#pragma unroll 1
+      for (int e = kListLen; e < 4 * kListLen; ++e) {
+        const float x = park_s[e * 32 + lane];
+        if (x > s[kListLen - 1]) list_insert(s, id, x, park_i[e * 32 + lane]);
+      }
+      const size_t o = (static_cast<size_t>(lane) * p.lists + blockIdx.x) * kListLen;
+      float4* ps = reinterpret_cast<float4*>(p.cand_score + o);
+      int4* pi = reinterpret_cast<int4*>(p.cand_idx + o);
+      ps[0] = make_float4(s[0], s[1], s[2], s[3]);
+      ps[1] = make_float4(s[4], s[5], s[6], s[7]);
+      pi[0] = make_int4(static_cast<int>(id[0]), static_cast<int>(id[1]), static_cast<int>(id[2]), static_cast<int>(id[3]));
+      pi[1] = make_int4(static_cast<int>(id[4]), static_cast<int>(id[5]), static_cast<int>(id[6]), static_cast<int>(id[7]));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -682,6 +901,61 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   return 0;
 }
 
+int launch_skinny(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t& plan, float* cand_score,
+                  int32_t* cand_idx, int after_query_pack, cudaStream_t stream) {
+  ALIVE_REQUIRE(plan.items == 1 && plan.t >= 1 && plan.t <= kSkinnyQ && plan.grid >= 1 && plan.lists == plan.grid &&
+                    plan.n_tiles == static_cast<int32_t>((plan.n + kBlockM - 1) / kBlockM) && plan.grid <= plan.n_tiles,
+                "alive_knn_search: bad skinny plan");
+  CUtensorMap mq, ml;
+  int rc = make_map(&mq, q, static_cast<uint64_t>(plan.t), static_cast<uint64_t>(plan.d), kSkinnyQ);
+  if (rc) return rc;
+  rc = make_map(&ml, lib, static_cast<uint64_t>(plan.n), static_cast<uint64_t>(plan.d), kBlockM);
+  if (rc) return rc;
+  const char* contig = getenv("ALIVE_KNN_SKINNY_CONTIG");   // timing experiment only (results are garbage):
+  const bool contig_exp = contig && atoi(contig) == 1;      // every 16 KB stage is ONE contiguous chunk of HBM
+  if (contig_exp) {
+    rc = make_map(&ml, lib, static_cast<uint64_t>(plan.n) * (plan.d / kBlockK), kBlockK, kBlockM);
+    if (rc) return rc;
+  }
+  SkinnyParams p;
+  p.contig = contig_exp ? 1 : 0;
+  p.t = plan.t;
+  p.n = static_cast<int>(plan.n);
+  p.k_blocks = plan.d / kBlockK;
+  p.n_tiles = plan.n_tiles;
+  p.lists = plan.lists;
+  p.cand_score = cand_score;
+  p.cand_idx = cand_idx;
+  const uint32_t fixed = skinny_fixed_bytes(p.k_blocks);
+  ALIVE_REQUIRE(fixed + 4 * kABytes <= kSkinnySmemMax, "alive_knn_search: d = %d is too wide for the skinny kernel", plan.d);
+  int stages = static_cast<int>((kSkinnySmemMax - fixed) / kABytes);
+  if (stages > 16) stages = 16;
+  {
+    const char* st = getenv("ALIVE_KNN_SKINNY_STAGES");   // experiments: shallower ring
+    if (st && atoi(st) >= 2 && atoi(st) < stages) stages = atoi(st);
+  }
+  p.stages = stages;
+  const size_t smem = fixed + static_cast<size_t>(stages) * kABytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(knn_search_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(kSkinnySmemMax)));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
+  cfg.blockDim = dim3(kSkinnyThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = after_query_pack ? 1 : 0;
+  ALIVE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_search_skinny_kernel, mq, ml, p));
+  return 0;
+}
+
 }  // namespace
 }  // namespace alive
 
@@ -699,8 +973,31 @@ extern "C" int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32
   // default: the CTA-pair kernel (cta_group::2) once there is more than one 128-query tile - it
   // moves a third less operand data per flop and is ~10% faster under the power cap; a single
   // tile (streaming chunks) runs on one CTA per unit
-  if (variant == 0) variant = (t > kBlockM) ? 2 : 1;
-  ALIVE_REQUIRE(variant == 1 || variant == 2, "alive_knn_plan: variant must be 0, 1 or 2");
+  const int skinny_stages = static_cast<int>((kSkinnySmemMax - skinny_fixed_bytes(d / kBlockK)) / kABytes);
+  const bool skinny_ok = items == 1 && t <= kSkinnyQ && skinny_stages >= 4;
+  if (variant == 0) {
+    const char* sk = getenv("ALIVE_KNN_SKINNY");      // A/B switch: 0 keeps the tiled kernel for small chunks
+    variant = (skinny_ok && !(sk && atoi(sk) == 0)) ? 3 : (t > kBlockM) ? 2 : 1;
+  }
+  ALIVE_REQUIRE(variant >= 1 && variant <= 3, "alive_knn_plan: variant must be 0, 1, 2 or 3");
+  plan->kernel = 0;
+  if (variant == 3) {
+    ALIVE_REQUIRE(skinny_ok, "alive_knn_plan: the skinny kernel needs one item, t <= %d and d <= %d (got t=%d d=%d items=%d)",
+                  kSkinnyQ, 2048, t, d, items);
+    plan->t = t;
+    plan->n = n;
+    plan->d = d;
+    plan->items = 1;
+    plan->kernel = 1;
+    plan->ctas_per_unit = 1;
+    plan->m_units = 1;
+    plan->n_tiles = static_cast<int32_t>((n + kBlockM - 1) / kBlockM);
+    plan->grid = plan->n_tiles < num_sms ? plan->n_tiles : num_sms;
+    plan->segments = plan->grid;
+    plan->tiles_per_segment = (plan->n_tiles + plan->grid - 1) / plan->grid;
+    plan->lists = plan->grid;
+    return 0;
+  }
   const int ctas = variant;
   const int slots = num_sms / ctas;   // units that run concurrently
   plan->t = t;
@@ -749,18 +1046,26 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
   return alive_knn_plan_batched(1, t, n, d, num_sms, variant, plan);
 }
 
-extern "C" int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,
-                                const alive_knn_plan_t* plan, float* cand_score, int32_t* cand_idx,
-                                alive_stream_t stream) {
-  using namespace alive;
+namespace alive {
+int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,
+                int32_t* cand_idx, int after_query_pack, alive_stream_t stream) {
   ALIVE_REQUIRE(plan && q_packed && lib_packed && cand_score && cand_idx, "alive_knn_search: NULL argument");
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(q_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(lib_packed) & 15) == 0,
                 "alive_knn_search: packed operands must be 16-byte aligned");
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(cand_score) & 15) == 0 && (reinterpret_cast<uintptr_t>(cand_idx) & 15) == 0,
                 "alive_knn_search: candidate buffers must be 16-byte aligned");
   ALIVE_REQUIRE(plan->d % 64 == 0 && plan->grid > 0 && plan->grid % plan->ctas_per_unit == 0, "alive_knn_search: bad plan");
+  if (plan->kernel == 1) return launch_skinny(q_packed, lib_packed, *plan, cand_score, cand_idx, after_query_pack, as_stream(stream));
+  ALIVE_REQUIRE(plan->kernel == 0, "alive_knn_search: unknown plan kernel %d", plan->kernel);
   if (plan->ctas_per_unit == 1) return launch_search<1>(q_packed, lib_packed, *plan, cand_score, cand_idx, as_stream(stream));
   if (plan->ctas_per_unit == 2) return launch_search<2>(q_packed, lib_packed, *plan, cand_score, cand_idx, as_stream(stream));
   set_error("alive_knn_search: ctas_per_unit must be 1 or 2");
   return -1;
+}
+}  // namespace alive
+
+extern "C" int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,
+                                const alive_knn_plan_t* plan, float* cand_score, int32_t* cand_idx,
+                                alive_stream_t stream) {
+  return alive::search_impl(q_packed, lib_packed, plan, cand_score, cand_idx, 0, stream);
 }

@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* alive_stream_t; /* cudaStream_t */
 
-#define ALIVE_KNN_ABI_VERSION 2
+#define ALIVE_KNN_ABI_VERSION 3
 #define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
 #define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
 #define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
@@ -52,6 +52,12 @@ typedef struct alive_knn_plan {
   int32_t lists;             /* running lists per query = 2 * segments */
   int32_t grid;              /* CTAs launched (multiple of ctas_per_unit) */
   int32_t items;             /* independent (query batch, library) pairs laid out back to back; 1 = plain */
+  int32_t kernel;            /* 0: tiled kernel (fields as described above)
+                              * 1: "skinny" kernel for t <= 32 (one realtime chunk): 128-frame library tiles on
+                              *    the M side of the MMA, the query chunk resident in shared memory; n_tiles =
+                              *    ceil(n / 128), CTA c takes tiles c, c + grid, ... (segments = grid,
+                              *    tiles_per_segment = ceil(n_tiles / grid)) and leaves ONE list per query:
+                              *    lists = grid */
 } alive_knn_plan_t;
 
 /* Library statistics produced by alive_knn_pack (2 x uint32 on the device):
@@ -79,7 +85,8 @@ int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64
                    alive_stream_t stream);
 
 /* Fill `plan` for t queries against n library frames on a device with
- * `num_sms` SMs.  variant: 1 or 2 CTAs per unit (0 = library default). Host only. */
+ * `num_sms` SMs.  variant: 1 or 2 CTAs per unit, 3 = the skinny kernel (t <= 32, single item);
+ * 0 = library default (skinny when it applies, else CTA pairs once t > 128). Host only. */
 int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, int32_t variant,
                    alive_knn_plan_t* plan_host);
 /* Batched form (BASELINE cfg5, train_decoder.py:134-135): `items` independent problems of t

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     assert sorted(_cabi.EXPORTS) == declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in alive_knn.h but not exported"
-    assert lib.alive_knn_abi_version() == 2
+    assert lib.alive_knn_abi_version() == 3
 
 
 def test_sass_is_blackwell_native():
@@ -64,13 +64,30 @@ def test_plan_covers_the_problem(lib, t, n, variant):
         assert waves * p.tiles_per_segment * slots <= 1.15 * p.m_units * p.n_tiles + slots
 
 
+@pytest.mark.parametrize("t,n", [(1, 1), (24, 3512), (32, 200000), (32, 128 * 148), (7, 128 * 148 + 1), (32, 10_000_000)])
+def test_skinny_plan(lib, t, n):
+    """variant 3 / the default for t <= 32: 128-frame tiles dealt round-robin to the CTAs, one list per CTA."""
+    for variant in (3, 0):
+        p = _cabi.Plan()
+        assert lib.alive_knn_plan(t, n, 768, 148, variant, ctypes.byref(p)) == 0
+        assert p.kernel == 1 and p.items == 1 and p.m_units == 1 and p.ctas_per_unit == 1
+        assert p.n_tiles * 128 >= n > (p.n_tiles - 1) * 128
+        assert p.grid == min(148, p.n_tiles) and p.lists == p.grid == p.segments
+        assert p.tiles_per_segment == -(-p.n_tiles // p.grid)
+    p = _cabi.Plan()
+    assert lib.alive_knn_plan(33, n, 768, 148, 0, ctypes.byref(p)) == 0 and p.kernel == 0      # too many queries
+    assert lib.alive_knn_plan(33, n, 768, 148, 3, ctypes.byref(p)) != 0
+    assert lib.alive_knn_plan_batched(2, t, n, 768, 148, 3, ctypes.byref(p)) != 0               # single item only
+    assert lib.alive_knn_plan_batched(2, t, n, 768, 148, 0, ctypes.byref(p)) == 0 and p.kernel == 0
+
+
 def test_plan_rejects_bad_arguments(lib):
     p = _cabi.Plan()
     assert lib.alive_knn_plan(0, 10, 768, 148, 1, ctypes.byref(p)) != 0
     assert b"t must be" in lib.alive_knn_last_error()
     assert lib.alive_knn_plan(4, 10, 100, 148, 1, ctypes.byref(p)) != 0
     assert b"multiple of 64" in lib.alive_knn_last_error()
-    assert lib.alive_knn_plan(4, 10, 768, 148, 3, ctypes.byref(p)) != 0
+    assert lib.alive_knn_plan(4, 10, 768, 148, 4, ctypes.byref(p)) != 0
     assert lib.alive_knn_plan(4, 2 ** 31, 768, 148, 1, ctypes.byref(p)) != 0
 
 

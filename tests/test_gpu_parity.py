@@ -206,6 +206,34 @@ def test_search_lists_match_bf16_matmul():
                 assert (ci[:, lst, kk:] == -1).all()
 
 
+@pytest.mark.parametrize("T,N,D", [(32, 5000, 768), (24, 3512, 768), (1, 128, 768), (7, 129, 768), (32, 70001, 768),
+                                   (32, 2000, 64), (13, 4000, 1024), (32, 200000, 768)])
+def test_skinny_search_lists_match_bf16_matmul(T, N, D):
+    """The skinny kernel (t <= 32): list c holds the top-8 of the 128-frame tiles c, c+grid, ... ."""
+    g = torch.Generator(device="cuda").manual_seed(T + N)
+    q = M.pack_frames(torch.randn(D, T, device="cuda", generator=g))
+    lib = M.pack_frames(torch.randn(D, N, device="cuda", generator=g))
+    plan = M.make_plan(T, N, D, q.device, 3)
+    assert plan.kernel == 1
+    cs = torch.full((T, plan.lists, 8), float("nan"), device="cuda")
+    ci = torch.full((T, plan.lists, 8), -7, dtype=torch.int32, device="cuda")
+    rc = _cabi.load().alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
+                                       cs.data_ptr(), ci.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "search")
+    ref = q.packed.float() @ lib.packed.float().t()
+    for c in range(plan.grid):
+        cols = torch.cat([torch.arange(t * 128, min(t * 128 + 128, N), device="cuda")
+                          for t in range(c, plan.n_tiles, plan.grid)])
+        kk = min(8, cols.numel())
+        want_s, _ = ref[:, cols].topk(kk, dim=1)
+        assert (cs[:, c, :kk] - want_s).abs().max().item() < 2e-4
+        got_idx = ci[:, c, :kk].long()
+        assert torch.isin(got_idx, cols).all()                       # only frames of this CTA's tiles
+        assert (ref.gather(1, got_idx) - cs[:, c, :kk]).abs().max().item() < 2e-4
+        assert (ci[:, c, kk:] == -1).all()
+        assert (cs[:, c, :-1] >= cs[:, c, 1:]).all()                 # descending, -inf padded
+
+
 def test_pack_cache_invalidation_on_inplace_update():
     """fine_tune.py:170 updates VL.tokens in place every step: the packed copy must follow."""
     vl = A.VoiceLibrary(num_tokens=600).cuda()
