@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "alive_knn.h"
 
@@ -49,6 +52,30 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
 // their writes are visible.  Both are no-ops when the launch carries no programmatic dependency.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may be scheduled while its
+// predecessor in the stream still runs.  Every kernel launched this way executes pdl_wait() before it
+// touches global memory, so ordering is unchanged - only launch latency is hidden.  ALIVE_KNN_PDL=0
+// turns the attribute off (A/B runs).
+inline bool chain_pdl_enabled() {
+  static const bool on = !(getenv("ALIVE_KNN_PDL") && atoi(getenv("ALIVE_KNN_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = chain_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 static inline cudaStream_t as_stream(alive_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -354,6 +354,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const int first_unit = blockIdx.x / kCtas;
   const int units_per_item = p.m_units * p.segments;
   const int total_units = units_per_item * p.items;
+  pdl_launch_dependents();        // the finish kernel may be scheduled now; it waits for this grid on the device
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -601,6 +602,7 @@ knn_search_skinny_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();        // the finish kernel may be scheduled now; it waits for this grid on the device
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);

@@ -309,6 +309,8 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   __shared__ unsigned s_tau[kWarps];
   __shared__ unsigned s_wbest[kWarps * kListLen];
   __shared__ long long s_top[kMaxK];
+  pdl_wait();                    // launched behind the search (launch_chained): its lists are complete now
+  pdl_launch_dependents();
   ALIVE_FT(0);
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -515,6 +517,8 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
                      float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item, int few) {
   // blockIdx.y = item: its queries are q_list[item][..] (or [item*t_item, (item+1)*t_item) when no
   // list is given) and its frames are rows [item*n, (item+1)*n) of lib_raw; t = queries PER ITEM
+  pdl_wait();
+  pdl_launch_dependents();
   const int item = blockIdx.y;
   if (q_list) q_list += static_cast<size_t>(item) * t_item;
   if (q_count) q_count += item;
@@ -719,6 +723,8 @@ exact_rows_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_n
                   const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
                   int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
                   float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item, int few) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int item = blockIdx.y;
   if (q_list) q_list += static_cast<size_t>(item) * t_item;
   if (q_count) q_count += item;
@@ -887,6 +893,7 @@ exact_final_kernel(int t, int k, const int* __restrict__ q_list, const int* __re
                    const float* __restrict__ lib_raw, long long n, int d, const float* __restrict__ q_raw,
                    float a1, float a0, float* __restrict__ out, int t_item) {
   // blockIdx.y = item; t = queries PER ITEM; n = frames of ALL items (gather reads global indices)
+  pdl_wait();
   const int item = blockIdx.y;
   const int nq = q_count ? q_count[item] : t;
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1027,10 +1034,9 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
   // q_count); its per-lane lists only fit in shared memory for moderate k
   const size_t rsmem = rows_query_bytes(d, k) + static_cast<size_t>(8) * 32 * k * 12;
   const int few = rsmem <= 200 * 1024 ? kFewQueries : 0;
-  exact_partial_kernel<<<pgrid, kEThreads, smem, as_stream(stream)>>>(q_raw, q_norm, t_item, lib_raw, lib_norm, n, d, k,
-                                                                     q_list, q_count, splits, part_score, part_idx, t_item,
-                                                                     few);
-  ALIVE_CHECK_CUDA(cudaGetLastError());
+  ALIVE_CHECK_CUDA(launch_chained(exact_partial_kernel, pgrid, dim3(kEThreads), smem, as_stream(stream), q_raw, q_norm, t_item,
+                                  lib_raw, lib_norm, static_cast<long long>(n), d, k, q_list, q_count, splits, part_score,
+                                  part_idx, t_item, few));
   if (few > 0) {
     static bool rattr_done = false;
     if (!rattr_done) {
@@ -1042,18 +1048,18 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
     if (rgx > rwork) rgx = rwork;
     if (rgx < 1) rgx = 1;
     dim3 rgrid(static_cast<unsigned>(rgx), static_cast<unsigned>(items));
-    exact_rows_kernel<<<rgrid, 256, rsmem, as_stream(stream)>>>(q_raw, q_norm, t_item, lib_raw, lib_norm, n, d, k, q_list,
-                                                               q_count, splits, part_score, part_idx, t_item, few);
-    ALIVE_CHECK_CUDA(cudaGetLastError());
+    ALIVE_CHECK_CUDA(launch_chained(exact_rows_kernel, rgrid, dim3(256), rsmem, as_stream(stream), q_raw, q_norm, t_item,
+                                    lib_raw, lib_norm, static_cast<long long>(n), d, k, q_list, q_count, splits, part_score,
+                                    part_idx, t_item, few));
   }
   ALIVE_REQUIRE(out == nullptr || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && idx_base == 0),
                 "alive_knn_exact: gather needs a 16-byte aligned `out` and an unsharded library");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
   dim3 fgrid(static_cast<unsigned>((t_item + 3) / 4), static_cast<unsigned>(items));
-  exact_final_kernel<<<fgrid, 128, 0, as_stream(stream)>>>(t_item, k, q_list, q_count, splits, part_score, part_idx, idx_base,
-                                                           top_score, reinterpret_cast<long long*>(top_idx), lib_raw,
-                                                           n * items, d, q_raw, a1, alpha, out, t_item);
-  ALIVE_CHECK_CUDA(cudaGetLastError());
+  ALIVE_CHECK_CUDA(launch_chained(exact_final_kernel, fgrid, dim3(128), 0, as_stream(stream), t_item, k, q_list, q_count,
+                                  splits, part_score, part_idx, static_cast<long long>(idx_base), top_score,
+                                  reinterpret_cast<long long*>(top_idx), lib_raw, static_cast<long long>(n * items), d,
+                                  q_raw, a1, alpha, out, t_item));
   return 0;
 }
 
@@ -1110,9 +1116,10 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
   ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
 #define ALIVE_LAUNCH_FINISH(TH, B)                                                                                   \
-  finish_kernel<TH, B><<<t, TH, smem, as_stream(stream)>>>(                                                          \
-      cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max, idx_base, a1, \
-      alpha, out, top_score, reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items)
+  ALIVE_CHECK_CUDA(launch_chained(finish_kernel<TH, B>, dim3(t), dim3(TH), smem, as_stream(stream), cand_score, cand_idx, t,   \
+                                  lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, static_cast<long long>(n), d,   \
+                                  r_max, static_cast<long long>(idx_base), a1, alpha, out, top_score,                           \
+                                  reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items))
   // a batch that does not fill the GPU is pure latency: give every query a whole SM's worth of warps
   // (one survivor frame per warp in flight -> the rescoring is a single DRAM round trip)
   const int threads = variant == 128 || variant == 256 || variant == 512 || variant == 1024
