@@ -385,6 +385,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================================== TMA producer =====================================
     // the whole warp walks the loop (warp-uniform control flow), one elected lane issues
     {
+      pdl_wait();   // launched behind the query pack of the same call: its output is complete from here on
       const uint32_t full0 = (kCtas == 1) ? bar_full : map_to_cta(bar_full, 0);   // barrier lives in the leader
       uint32_t it = 0;
       int my_tiles = 0, epoch = 0;
@@ -830,7 +831,7 @@ unsigned int* pacing_slot(cudaStream_t stream) {
 
 template <int kCtas>
 int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t& plan, float* cand_score,
-                  int32_t* cand_idx, cudaStream_t stream) {
+                  int32_t* cand_idx, int after_query_pack, cudaStream_t stream) {
   using C = Cfg<kCtas>;
   CUtensorMap mq, ml;
   const uint64_t items = static_cast<uint64_t>(plan.items < 1 ? 1 : plan.items);
@@ -892,13 +893,15 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = after_query_pack ? 2 : 1;
   ALIVE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_search_kernel<kCtas>, mq, ml, p));
   return 0;
 }
@@ -1059,8 +1062,8 @@ int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const aliv
   ALIVE_REQUIRE(plan->d % 64 == 0 && plan->grid > 0 && plan->grid % plan->ctas_per_unit == 0, "alive_knn_search: bad plan");
   if (plan->kernel == 1) return launch_skinny(q_packed, lib_packed, *plan, cand_score, cand_idx, after_query_pack, as_stream(stream));
   ALIVE_REQUIRE(plan->kernel == 0, "alive_knn_search: unknown plan kernel %d", plan->kernel);
-  if (plan->ctas_per_unit == 1) return launch_search<1>(q_packed, lib_packed, *plan, cand_score, cand_idx, as_stream(stream));
-  if (plan->ctas_per_unit == 2) return launch_search<2>(q_packed, lib_packed, *plan, cand_score, cand_idx, as_stream(stream));
+  if (plan->ctas_per_unit == 1) return launch_search<1>(q_packed, lib_packed, *plan, cand_score, cand_idx, after_query_pack, as_stream(stream));
+  if (plan->ctas_per_unit == 2) return launch_search<2>(q_packed, lib_packed, *plan, cand_score, cand_idx, after_query_pack, as_stream(stream));
   set_error("alive_knn_search: ctas_per_unit must be 1 or 2");
   return -1;
 }

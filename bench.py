@@ -435,12 +435,17 @@ def gpu_arm(args):
         else:
             flops_per_launch = 2.0 * B * T * n_local * D
         avg_search_ms = sum(search_ms) / max(1, len(search_ms))
+        if args.workload == "cfg5":
+            search_kernel = "knn_search_kernel"
+        else:
+            _plan = M.make_plan(B * T, n_local, D, dev, variant)
+            search_kernel = "knn_search_skinny_kernel" if _plan.kernel == 1 else "knn_search_kernel"
         if latency_workload:
             bytes_per_launch = float(n_local) * D * 2
             achieved = bytes_per_launch / (avg_search_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(args.workload, world),
-                    "kernel": "knn_search_kernel", "avg_kernel_ms": avg_search_ms, "peak_source": peaks["source"]}
+                    "kernel": search_kernel, "avg_kernel_ms": avg_search_ms, "peak_source": peaks["source"]}
         else:
             achieved = flops_per_launch / (avg_search_ms * 1e-3) / 1e12
             # conservative denominator: the burst cuBLAS figure, even though the kernel runs
@@ -448,7 +453,7 @@ def gpu_arm(args):
             sustained = False
             peak = peaks["bf16_burst"]
             roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": load_traffic(args.workload, world), "kernel": "knn_search_kernel",
+                    "frac": achieved / peak, "traffic": load_traffic(args.workload, world), "kernel": search_kernel,
                     "avg_kernel_ms": avg_search_ms,
                     "kernel_share_of_step": avg_search_ms / ms_per_step,
                     "peak_kind": "sustained" if sustained else "burst", "peak_source": peaks["source"],

@@ -99,7 +99,10 @@ int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32_t d, int32
  * common.py:104 and the first pass of torch.topk :105 WITHOUT materialising
  * the [T,N] score matrix: TMA-fed tcgen05 bf16 MMAs accumulate 128x256 score
  * tiles in TMEM; epilogue warps keep, per query and per list, the
- * ALIVE_KNN_LIST_LEN best (score, frame) pairs.
+ * ALIVE_KNN_LIST_LEN best (score, frame) pairs.  plan.kernel == 1 (one realtime chunk,
+ * t <= 32; realtime_inference.py:165): the operands are swapped - 128-frame library tiles
+ * stream through a deep TMA ring as the M side of the MMA, the query chunk stays resident
+ * in shared memory - and every CTA leaves one list per query.
  *   q_packed [items*t,d] bf16, lib_packed [items*n,d] bf16 (from alive_knn_pack)
  *   cand_score [items*t, plan.lists, 8] float32 (descending, -inf padded)
  *   cand_idx   [items*t, plan.lists, 8] int32   (-1 padded; frame index inside [items*n]) */
