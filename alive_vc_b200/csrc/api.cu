@@ -28,7 +28,7 @@ namespace alive {
 namespace {
 
 constexpr int kOffQRaw = 0, kOffQNorm = 1, kOffQPacked = 2, kOffQErr = 3, kOffCandScore = 4, kOffCandIdx = 5,
-              kOffSelIdx = 6, kOffSelN = 7, kOffFbList = 8, kOffFbCount = 9, kOffExact = 10, kOffTotal = 11;
+              kOffCollect = 6, kOffSelN = 7, kOffFbList = 8, kOffFbCount = 9, kOffExact = 10, kOffTotal = 11;
 
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -38,8 +38,46 @@ int resolve_mode(int mode, int64_t n, int d, int k) {
   return mode;
 }
 
+// Second screen pass for uncertified queries (single item, tiled screen, enough work for the
+// exhaustive scan to hurt): at most kCollectRows queries get a slot and a buffer of kCollectCap
+// candidate frames each.  Area layout: fb2_list [rows] | qc_packed [rows_c, d] bf16 | cut [rows_c] |
+// cnt [rows_c] | idx [rows_c, cap]; fb2_count is the word after the per-item fallback counters.
+constexpr int kCollectRows = 2048;
+constexpr int kCollectCap = 2048;
+struct CollectLayout {
+  bool on;
+  int rows_c;
+  alive_knn_plan_t plan;
+  size_t fb2_list, qc, cut, cnt, idx, bytes;
+};
+
+int collect_layout(int32_t rows, int64_t n, int32_t d, int32_t num_sms, int mode, int32_t items,
+                   const alive_knn_plan_t& screen_plan, CollectLayout* cl) {
+  static const bool enabled = !(getenv("ALIVE_KNN_COLLECT") && atoi(getenv("ALIVE_KNN_COLLECT")) == 0);
+  cl->on = enabled && mode == 1 && items == 1 && screen_plan.kernel == 0 && d % 64 == 0 &&
+           static_cast<double>(rows) * static_cast<double>(n) >= 16777216.0;
+  cl->bytes = 0;
+  if (!cl->on) return 0;
+  cl->rows_c = rows < kCollectRows ? rows : kCollectRows;
+  int rc = alive_knn_plan(cl->rows_c, n, d, num_sms, cl->rows_c > ALIVE_KNN_TILE_M ? 2 : 1, &cl->plan);
+  if (rc) return rc;
+  size_t cur = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = cur;
+    cur += align256(bytes);
+    return at;
+  };
+  cl->fb2_list = take(static_cast<size_t>(rows) * 4);
+  cl->qc = take(static_cast<size_t>(cl->rows_c) * d * 2);
+  cl->cut = take(static_cast<size_t>(cl->rows_c) * 4);
+  cl->cnt = take(static_cast<size_t>(cl->rows_c) * 4);
+  cl->idx = take(static_cast<size_t>(cl->rows_c) * kCollectCap * 4);
+  cl->bytes = cur;
+  return 0;
+}
+
 int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t num_sms, int32_t variant, int mode,
-           int32_t items, alive_knn_plan_t* plan, int64_t* off) {
+           int32_t items, alive_knn_plan_t* plan, int64_t* off, CollectLayout* cl) {
   size_t cur = 0;
   auto take = [&](int slot, size_t bytes) {
     off[slot] = static_cast<int64_t>(cur);
@@ -57,10 +95,21 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
   }
   take(kOffCandScore, static_cast<size_t>(rows) * lists * ALIVE_KNN_LIST_LEN * 4);
   take(kOffCandIdx, static_cast<size_t>(rows) * lists * ALIVE_KNN_LIST_LEN * 4);
-  take(kOffSelIdx, 0);   // survivors stay in finish_kernel's shared memory (slot kept for ABI stability)
+  {
+    CollectLayout local;
+    CollectLayout* c = cl ? cl : &local;
+    if (mode == 1) {
+      int rc = collect_layout(rows, n, d, num_sms, mode, items, *plan, c);
+      if (rc) return rc;
+    } else {
+      c->on = false;
+      c->bytes = 0;
+    }
+    take(kOffCollect, c->bytes);
+  }
   take(kOffSelN, static_cast<size_t>(rows) * 4);
   take(kOffFbList, static_cast<size_t>(rows) * 4);
-  take(kOffFbCount, static_cast<size_t>(items) * 4);
+  take(kOffFbCount, static_cast<size_t>(items + 1) * 4);   // per-item counters + the collect pass's fb2 counter
   take(kOffExact, alive_knn_exact_workspace_bytes(rows, n, k, items));
   off[kOffTotal] = static_cast<int64_t>(cur);
   return 0;
@@ -76,7 +125,7 @@ extern "C" int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_
   ALIVE_REQUIRE(rows >= 1 && n >= 1 && k >= 1 && k <= ALIVE_KNN_MAX_K, "alive_knn_match_layout: bad sizes");
   ALIVE_REQUIRE(items >= 1 && rows % items == 0, "alive_knn_match_layout: rows must be a multiple of items");
   alive_knn_plan_t plan;
-  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets12);
+  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets12, nullptr);
 }
 
 extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
@@ -101,7 +150,8 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   ALIVE_REQUIRE(mode == 2 || k <= ALIVE_KNN_LIST_LEN, "alive_knn_match: the screened path needs k <= %d", ALIVE_KNN_LIST_LEN);
   alive_knn_plan_t plan;
   int64_t off[12];
-  int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, items, &plan, off);
+  CollectLayout cl;
+  int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, items, &plan, off, &cl);
   if (rc) return rc;
   ALIVE_REQUIRE(static_cast<size_t>(off[kOffTotal]) <= workspace_bytes,
                 "alive_knn_match: workspace too small (%zu < %lld)", workspace_bytes, static_cast<long long>(off[kOffTotal]));
@@ -122,7 +172,7 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
     const size_t r0 = static_cast<size_t>(b) * t;
     // the first pack launch also zeroes the per-item fallback counters (no separate memset node)
     rc = pack_impl(source + static_cast<int64_t>(b) * stride_b, t, d, stride_t, stride_d, q_raw + r0 * d,
-                   q_norm + r0, q_packed + r0 * d, q_err + r0, nullptr, b == 0 ? fb_count : nullptr, b == 0 ? items : 0,
+                   q_norm + r0, q_packed + r0 * d, q_err + r0, nullptr, b == 0 ? fb_count : nullptr, b == 0 ? items + 1 : 0,
                    stream);
     if (rc) return rc;
   }
@@ -134,11 +184,32 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
     if (rc) return rc;
     if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
+    char* ca = ws + off[kOffCollect];
+    uint16_t* qc = cl.on ? reinterpret_cast<uint16_t*>(ca + cl.qc) : nullptr;
+    float* c_cut = cl.on ? reinterpret_cast<float*>(ca + cl.cut) : nullptr;
+    int32_t* c_cnt = cl.on ? reinterpret_cast<int32_t*>(ca + cl.cnt) : nullptr;
     rc = finish_impl(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
                      lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
-                     fb_count, items, 0, stream);
+                     fb_count, items, 0, q_packed, qc, c_cut, c_cnt, cl.on ? cl.rows_c : 0, stream);
     if (rc) return rc;
-    rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, fb_list, fb_count, lib->row_base,
+    const int32_t* x_list = fb_list;
+    const int32_t* x_count = fb_count;
+    if (cl.on) {
+      // uncertified queries: a second tensor-core pass collects every frame that reaches the query's
+      // cut, those are rescored exactly; only buffer overflows go on to the exhaustive scan
+      int32_t* c_idx = reinterpret_cast<int32_t*>(ca + cl.idx);
+      int32_t* fb2_list = reinterpret_cast<int32_t*>(ca + cl.fb2_list);
+      int32_t* fb2_count = fb_count + items;
+      rc = collect_impl(qc, lib->packed, &cl.plan, fb_count, c_cut, c_cnt, c_idx, kCollectCap, stream);
+      if (rc) return rc;
+      rc = collect_rescore_impl(fb_list, fb_count, rows, cl.rows_c, c_cnt, c_idx, kCollectCap, k, q_raw, q_norm, lib->raw,
+                                lib->norms, lib->n, d, alpha, out, top_score, top_idx, lib->row_base, fb2_list, fb2_count,
+                                stream);
+      if (rc) return rc;
+      x_list = fb2_list;
+      x_count = fb2_count;
+    }
+    rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, x_list, x_count, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;
   } else {

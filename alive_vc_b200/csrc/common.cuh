@@ -45,7 +45,17 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
                 const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
                 const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
                 int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx, int32_t* sel_n,
-                int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, alive_stream_t stream);
+                int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, const uint16_t* q_packed,
+                uint16_t* qc_packed, float* c_cut, int32_t* c_cnt, int32_t rows_c, alive_stream_t stream);
+// second screen pass for uncertified queries (search_sm100.cu, select.cu; driven by api.cu)
+int collect_impl(const uint16_t* qc_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan,
+                 const int32_t* active_rows, const float* cut, int32_t* cnt, int32_t* idx, int32_t cap,
+                 alive_stream_t stream);
+int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_t t, int32_t rows_c, const int32_t* c_cnt,
+                         const int32_t* c_idx, int32_t c_cap, int32_t k, const float* q_raw, const float* q_norm,
+                         const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, float alpha, float* out,
+                         float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list, int32_t* fb2_count,
+                         alive_stream_t stream);
 
 // programmatic dependent launch (sm_90+): `launch_dependents` lets the next kernel of the stream be
 // scheduled while this one still runs, `wait` blocks until the kernels it depends on have completed and

@@ -75,6 +75,13 @@ struct SearchParams {
   unsigned int* sync_ctr;        // grid-wide pacing counter (zeroed before the launch), or NULL
   int sync_every;                // producers re-align every this many tiles ...
   int sync_rounds;               // ... for this many epochs (every CTA reaches them)
+  // collect mode (knn_search_kernel<kCtas, true>): instead of running top lists, EVERY frame whose
+  // screened score is not below the row's cut is appended to the row's candidate buffer
+  const int* c_active;           // device: number of live query rows (rows beyond it are skipped)
+  const float* c_cut;            // [t] per-row cut (S_k - 2 eps from the first pass)
+  int* c_cnt;                    // [t] candidates found (may exceed c_cap: overflow)
+  int* c_idx;                    // [t, c_cap] frame indices
+  int c_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -327,12 +334,20 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_ba
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int kCtas>
+template <int kCtas, bool kCollect>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_lib,
                   const SearchParams p) {
   using C = Cfg<kCtas>;
   constexpr int kStages = C::kStages;
+  // collect mode: only the query units that hold live rows do any work (the count lives on the device)
+  int m_active = p.m_units;
+  if constexpr (kCollect) {
+    pdl_wait();
+    const int live = min(*p.c_active, p.t);
+    m_active = (live + kBlockM * kCtas - 1) / (kBlockM * kCtas);
+    if (m_active == 0) return;               // nothing fell back: uniform exit before any setup
+  }
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024 B alignment
@@ -393,6 +408,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int item = unit / units_per_item;
         const int rem = unit - item * units_per_item;
         const int m_unit = rem % p.m_units;
+        if (kCollect && m_unit >= m_active) continue;
         const int seg = rem / p.m_units;
         const int tile0 = seg * p.tiles_per_segment;
         const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
@@ -441,6 +457,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       constexpr uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN);
       uint32_t it = 0, tile_count = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        if (kCollect && (unit % units_per_item) % p.m_units >= m_active) continue;
         const int seg = (unit % units_per_item) / p.m_units;
         const int tile0 = seg * p.tiles_per_segment;
         const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
@@ -484,11 +501,12 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const int item = unit / units_per_item;
       const int rem = unit - item * units_per_item;
       const int m_unit = rem % p.m_units;
+      if (kCollect && m_unit >= m_active) continue;
       const int seg = rem / p.m_units;
       const int tile0 = seg * p.tiles_per_segment;
       const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
       const int row_in_item = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
-      const bool row_valid = row_in_item < p.t;
+      const bool row_valid = row_in_item < (kCollect ? min(*p.c_active, p.t) : p.t);
       const int row = item * p.t + row_in_item;          // global query index
       const int col_item0 = item * p.n;                  // frame indices are global: item*n + frame
       const int n_valid = col_item0 + p.n;
@@ -499,6 +517,15 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int i = 0; i < kListLen; ++i) {
         s[i] = row_valid ? -INFINITY : INFINITY;   // padded query rows never insert
         id[i] = 0xFFFFFFFFu;
+      }
+      // collect mode: this row's cut; a row that has overflowed its buffer stops collecting
+      float c_cut = INFINITY;
+      bool c_live = false;
+      if constexpr (kCollect) {
+        if (row_valid) {
+          c_cut = p.c_cut[row];
+          c_live = true;
+        }
       }
 
       for (int tile = tile0; tile < tile1; ++tile, ++tile_count) {
@@ -531,12 +558,30 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               else mbar_arrive_cluster(tempty0 + 8 * acc);
             }
           }
-          if (p.debug == 0 || p.debug == 3) scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
-          else s[0] = fmaxf(s[0], __uint_as_float(v[0] ^ v[13] ^ v[31]));
+          if constexpr (kCollect) {
+            if (c_live) {
+              uint32_t mask = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)     // NaN scores are collected too (they rank first)
+                mask |= (!(__uint_as_float(v[j]) < c_cut) && col0 + 32 * c + j < n_valid) ? (1u << j) : 0u;
+              if (mask) {
+                int at = atomicAdd(p.c_cnt + row, __popc(mask));
+                if (at >= p.c_cap) c_live = false;
+                while (mask && at < p.c_cap) {
+                  const int j = __ffs(static_cast<int>(mask)) - 1;
+                  mask &= mask - 1;
+                  p.c_idx[static_cast<size_t>(row) * p.c_cap + at++] = col0 + 32 * c + j;
+                }
+              }
+            }
+          } else {
+            if (p.debug == 0 || p.debug == 3) scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
+            else s[0] = fmaxf(s[0], __uint_as_float(v[0] ^ v[13] ^ v[31]));
+          }
         }
       }
 
-      if (row_valid) {
+      if (!kCollect && row_valid) {
         const size_t o = (static_cast<size_t>(row) * p.lists + static_cast<size_t>(seg * 2 + half)) * kListLen;
         float4* ps = reinterpret_cast<float4*>(p.cand_score + o);
         int4* pi = reinterpret_cast<int4*>(p.cand_idx + o);
@@ -829,9 +874,17 @@ unsigned int* pacing_slot(cudaStream_t stream) {
   return slot;
 }
 
-template <int kCtas>
+struct CollectArgs {
+  const int* active;
+  const float* cut;
+  int* cnt;
+  int* idx;
+  int cap;
+};
+
+template <int kCtas, bool kCollect = false>
 int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t& plan, float* cand_score,
-                  int32_t* cand_idx, int after_query_pack, cudaStream_t stream) {
+                  int32_t* cand_idx, int after_query_pack, cudaStream_t stream, const CollectArgs* ca = nullptr) {
   using C = Cfg<kCtas>;
   CUtensorMap mq, ml;
   const uint64_t items = static_cast<uint64_t>(plan.items < 1 ? 1 : plan.items);
@@ -875,7 +928,20 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
     const long long clusters = plan.grid / kCtas;
     const int last_seg_tiles = plan.n_tiles - (plan.segments - 1) * plan.tiles_per_segment;
     const long long min_tiles = (total_units / clusters) * (last_seg_tiles < plan.tiles_per_segment ? last_seg_tiles : plan.tiles_per_segment);
-    if (p.sync_every > 0 && (plan.m_units > 1 || items > 1) && min_tiles / p.sync_every >= 1) {
+    p.c_active = nullptr;
+    p.c_cut = nullptr;
+    p.c_cnt = nullptr;
+    p.c_idx = nullptr;
+    p.c_cap = 0;
+    if constexpr (kCollect) {
+      p.c_active = ca->active;
+      p.c_cut = ca->cut;
+      p.c_cnt = ca->cnt;
+      p.c_idx = ca->idx;
+      p.c_cap = ca->cap;
+    }
+    // (no pacing in collect mode: units are skipped by a device-side count, CTAs would wait for absentees)
+    if (!kCollect && p.sync_every > 0 && (plan.m_units > 1 || items > 1) && min_tiles / p.sync_every >= 1) {
       p.sync_ctr = pacing_slot(stream);
       p.sync_rounds = static_cast<int>(min_tiles / p.sync_every);
       if ((static_cast<long long>(p.sync_rounds) + 1) * plan.grid >= (1ll << 32)) p.sync_ctr = nullptr;
@@ -884,8 +950,8 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
 
   static bool attr_done = false;
   if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(knn_search_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(C::kSmemBytes)));
+    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(knn_search_kernel<kCtas, kCollect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(C::kSmemBytes))));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -902,7 +968,7 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = after_query_pack ? 2 : 1;
-  ALIVE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_search_kernel<kCtas>, mq, ml, p));
+  ALIVE_CHECK_CUDA((cudaLaunchKernelEx(&cfg, knn_search_kernel<kCtas, kCollect>, mq, ml, p)));
   return 0;
 }
 
@@ -1052,6 +1118,17 @@ extern "C" int alive_knn_plan(int32_t t, int64_t n, int32_t d, int32_t num_sms, 
 }
 
 namespace alive {
+// second screen pass of the one-call pipeline: see SearchParams (collect mode) and select.cu
+int collect_impl(const uint16_t* qc_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan,
+                 const int32_t* active_rows, const float* cut, int32_t* cnt, int32_t* idx, int32_t cap,
+                 alive_stream_t stream) {
+  ALIVE_REQUIRE(plan && plan->kernel == 0 && plan->items == 1, "collect pass: needs a tiled single-item plan");
+  CollectArgs ca{active_rows, cut, cnt, idx, cap};
+  if (plan->ctas_per_unit == 1)
+    return launch_search<1, true>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
+  return launch_search<2, true>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
+}
+
 int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,
                 int32_t* cand_idx, int after_query_pack, alive_stream_t stream) {
   ALIVE_REQUIRE(plan && q_packed && lib_packed && cand_score && cand_idx, "alive_knn_search: NULL argument");

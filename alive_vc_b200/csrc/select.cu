@@ -271,8 +271,20 @@ __device__ unsigned long long g_finish_t[16];
 #else
 #define ALIVE_FT(i)
 #endif
-constexpr int kFinishThreads = 256;
 constexpr int kFinishMaxStagedEntries = 6144;   // lists*8 entries staged in shared memory (48 KB) when they fit
+
+// Second screen pass for uncertified queries (one-call pipeline, single item): finish_kernel moves
+// the query to slot `fb slot` of a compact query matrix, the tiled search kernel in collect mode
+// appends every frame whose screened score reaches the query's cut, collect_rescore_kernel below
+// rescores exactly those.  Queries whose buffer overflowed, or that did not get a slot, go on to the
+// exhaustive scan through fb2_list.
+struct CollectStage {
+  const uint16_t* q_packed;   // [t, d] bf16 packed queries of this call
+  uint16_t* qc_packed;        // [rows_c, d] compact copy (NULL: stage disabled)
+  float* c_cut;               // [rows_c]
+  int* c_cnt;                 // [rows_c]
+  int rows_c;
+};
 
 // monotone map score -> uint32 (larger score = larger key, -0 == +0, NaN above everything, 0 is
 // below every score): lets the selections below run on redux.sync instead of shuffle trees
@@ -294,7 +306,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
               const unsigned int* __restrict__ lib_stats, long long n, int d, int r_max, long long idx_base,
               float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
               long long* __restrict__ top_idx, int* __restrict__ sel_n, int* __restrict__ fb_list,
-              int* __restrict__ fb_count, int staged, int t_item) {
+              int* __restrict__ fb_count, int staged, int t_item, CollectStage cs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qh = reinterpret_cast<float*>(smem_raw);                         // [d]
   long long* cid = reinterpret_cast<long long*>(qh + d);                  // [r_max] (layout shared with rescore_kernel)
@@ -306,6 +318,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   __shared__ int s_total;
   __shared__ int s_fb;
   __shared__ float s_cut;
+  __shared__ float s_ccut;
   __shared__ unsigned s_tau[kWarps];
   __shared__ unsigned s_wbest[kWarps * kListLen];
   __shared__ long long s_top[kMaxK];
@@ -414,6 +427,8 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
       const bool fb = lib_bad != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > t2);
       s_cut = cut;
       s_fb = fb ? 1 : 0;
+      // what the collect pass may use as this query's cut (+inf: nothing is known about the screen)
+      s_ccut = (lib_bad == 0u && qn > 0.f && isfinite(qn) && sk > -INFINITY && cut > -INFINITY) ? cut : INFINITY;
     }
   }
   __syncthreads();
@@ -444,10 +459,21 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
     sel_n[q] = n_sel;
     if (n_sel < 0) {
       const int item = q / t_item;                      // uncertified queries are listed per item
-      fb_list[static_cast<size_t>(item) * t_item + atomicAdd(&fb_count[item], 1)] = q;
+      const int slot = atomicAdd(&fb_count[item], 1);
+      fb_list[static_cast<size_t>(item) * t_item + slot] = q;
+      // collect pass: the query's packed row moves to its slot of the compact query matrix, next to
+      // the cut.  One thread copies the 1.5 KB: anything heavier between here and the bare `return`
+      // below (a block-wide copy behind a barrier was tried) costs the COMMON path 40% - measured.
+      if (cs.qc_packed != nullptr && slot < cs.rows_c) {
+        const uint4* src = reinterpret_cast<const uint4*>(cs.q_packed + static_cast<size_t>(q) * d);
+        uint4* dst = reinterpret_cast<uint4*>(cs.qc_packed + static_cast<size_t>(slot) * d);
+        for (int j = 0; j < d / 8; ++j) dst[j] = src[j];
+        cs.c_cut[slot] = s_ccut;
+        cs.c_cnt[slot] = 0;
+      }
     }
   }
-  if (n_sel < 0) return;   // the exact scan (and its gather) handle this query
+  if (n_sel < 0) return;   // the collect pass / the exact scan (and their gather) handle this query
   for (int c = warp; c < n_sel; c += kWarps) {
     const int idx = sel[c];
     const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
@@ -493,6 +519,81 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   __syncthreads();
   ALIVE_FT(8);
 #endif
+}
+
+// One CTA per fallback slot: exact rescoring of the collected candidates, top-k, gather.
+constexpr int kCollectThreads = 512;
+__global__ void __launch_bounds__(kCollectThreads, 2)
+collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, int rows_c,
+                       const int* __restrict__ c_cnt, const int* __restrict__ c_idx, int c_cap, int k,
+                       const float* __restrict__ q_raw, const float* __restrict__ q_norm,
+                       const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
+                       float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
+                       long long* __restrict__ top_idx, long long idx_base, int* __restrict__ fb2_list,
+                       int* __restrict__ fb2_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qh = reinterpret_cast<float*>(smem_raw);          // [d]
+  float* csc = qh + d;                                      // [c_cap]
+  __shared__ long long s_top[kMaxK];
+  constexpr int kWarps = kCollectThreads / 32;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int n_fb = *fb_count;
+  const int slot = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // uncertified queries beyond the compact matrix go straight to the exhaustive scan
+  if (threadIdx.x == 0)
+    for (int sl = rows_c + slot; sl < n_fb; sl += gridDim.x) fb2_list[atomicAdd(fb2_count, 1)] = fb_list[sl];
+  if (slot >= n_fb || slot >= rows_c) return;
+  const int q = fb_list[slot];
+  const int cnt = c_cnt[slot];
+  if (cnt > c_cap || cnt < k) {                             // overflow, or no usable cut: exhaustive scan
+    if (threadIdx.x == 0) fb2_list[atomicAdd(fb2_count, 1)] = q;
+    return;
+  }
+  const float qn = q_norm[q];
+  for (int j = threadIdx.x; j < d; j += kCollectThreads) qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
+  __syncthreads();
+  const int* cand = c_idx + static_cast<size_t>(slot) * c_cap;
+  for (int c = warp; c < cnt; c += kWarps) {
+    const int idx = cand[c];
+    const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
+    if (lane == 0) csc[c] = static_cast<float>(acc);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // k rounds of (max score key, min index) over the not yet taken candidates; `prev` = last winner
+    unsigned pk = 0xFFFFFFFFu;
+    int pi = -1;
+    for (int r = 0; r < k; ++r) {
+      unsigned bk = 0u;
+      int bi = 0x7fffffff;
+      bool have = false;
+      for (int c = lane; c < cnt; c += 32) {
+        const unsigned key = score_key(csc[c]);
+        const int idx = cand[c];
+        const bool after = r == 0 || key < pk || (key == pk && idx > pi);   // strictly after the previous winner
+        if (after && (!have || key > bk || (key == bk && idx < bi))) {
+          bk = key;
+          bi = idx;
+          have = true;
+        }
+      }
+      const unsigned m = __reduce_max_sync(0xffffffffu, have ? bk : 0u);
+      const int wi = __reduce_min_sync(0xffffffffu, (have && bk == m) ? bi : 0x7fffffff);
+      pk = m;
+      pi = wi;
+      if (lane == 0) {
+        s_top[r] = wi;
+        top_score[static_cast<size_t>(q) * k + r] = key_score(m);
+        top_idx[static_cast<size_t>(q) * k + r] = wi + idx_base;
+      }
+    }
+  }
+  if (out == nullptr) return;
+  __syncthreads();
+  gather_mean_row(lib_raw, n, d, s_top, 0, k, q_raw + static_cast<size_t>(q) * d, a1, a0, out + static_cast<size_t>(q) * d,
+                  threadIdx.x, kCollectThreads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1082,7 +1183,8 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
                 const float* q_raw, const float* q_norm, const float* q_err, const float* lib_raw,
                 const float* lib_norm, const uint32_t* lib_stats, int64_t n, int32_t d, int32_t r_max,
                 int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx, int32_t* sel_n,
-                int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, alive_stream_t stream) {
+                int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, const uint16_t* q_packed,
+                uint16_t* qc_packed, float* c_cut, int32_t* c_cnt, int32_t rows_c, alive_stream_t stream) {
   ALIVE_REQUIRE(cand_score && cand_idx && q_raw && q_norm && q_err && lib_raw && lib_norm && lib_stats && top_score &&
                     top_idx && sel_n && fb_list && fb_count,
                 "alive_knn_finish: NULL argument");
@@ -1115,11 +1217,14 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
   }
   ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
+  ALIVE_REQUIRE(qc_packed == nullptr || (items == 1 && q_packed && c_cut && c_cnt && rows_c >= 1 && d % 8 == 0),
+                "alive_knn_finish: bad collect stage");
+  CollectStage cs{q_packed, qc_packed, c_cut, c_cnt, rows_c};
 #define ALIVE_LAUNCH_FINISH(TH, B)                                                                                   \
   ALIVE_CHECK_CUDA(launch_chained(finish_kernel<TH, B>, dim3(t), dim3(TH), smem, as_stream(stream), cand_score, cand_idx, t,   \
                                   lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, static_cast<long long>(n), d,   \
                                   r_max, static_cast<long long>(idx_base), a1, alpha, out, top_score,                           \
-                                  reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items))
+                                  reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items, cs))
   // a batch that does not fill the GPU is pure latency: give every query a whole SM's worth of warps
   // (one survivor frame per warp in flight -> the rescoring is a single DRAM round trip)
   const int threads = variant == 128 || variant == 256 || variant == 512 || variant == 1024
@@ -1142,8 +1247,33 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
                                 int32_t* sel_n, int32_t* fb_list, int32_t* fb_count, int32_t items,
                                 alive_stream_t stream) {
   return alive::finish_impl(cand_score, cand_idx, t, lists, k, q_raw, q_norm, q_err, lib_raw, lib_norm, lib_stats, n, d, r_max,
-                            idx_base, alpha, out, top_score, top_idx, sel_n, fb_list, fb_count, items, 1, stream);
+                            idx_base, alpha, out, top_score, top_idx, sel_n, fb_list, fb_count, items, 1, nullptr, nullptr,
+                            nullptr, nullptr, 0, stream);
 }
+
+namespace alive {
+int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_t t, int32_t rows_c, const int32_t* c_cnt,
+                         const int32_t* c_idx, int32_t c_cap, int32_t k, const float* q_raw, const float* q_norm,
+                         const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, float alpha, float* out,
+                         float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list, int32_t* fb2_count,
+                         alive_stream_t stream) {
+  const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(c_cap) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(collect_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_done = true;
+  }
+  ALIVE_REQUIRE(smem <= 64 * 1024, "collect pass: candidate buffer too large for shared memory");
+  const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
+  (void)t;
+  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c), dim3(kCollectThreads), smem, as_stream(stream), fb_list,
+                                  fb_count, rows_c, c_cnt, c_idx, c_cap, k, q_raw, q_norm, lib_raw, lib_norm,
+                                  static_cast<long long>(n), d, a1, alpha, out, top_score,
+                                  reinterpret_cast<long long*>(top_idx), static_cast<long long>(idx_base), fb2_list,
+                                  fb2_count));
+  return 0;
+}
+}  // namespace alive
 
 #ifdef ALIVE_FINISH_TIMING
 extern "C" int alive_knn_debug_finish_times(unsigned long long* host16) {

@@ -267,12 +267,19 @@ class SearchInfo:
     """Per-call bookkeeping (device tensors; reading them synchronises)."""
     mode: str
     plan: Optional[dict] = None
-    fb_count: Optional[torch.Tensor] = None     # [1] int32: queries sent to the exact scan
+    fb_count: Optional[torch.Tensor] = None     # [items] int32: queries the first screen could not certify
+    exact_count: Optional[torch.Tensor] = None  # [1] int32: of those, queries that needed the exhaustive scan
+    collect: bool = False                       # a collect pass ran between the two (alive_knn_match, off[6] area)
     sel_n: Optional[torch.Tensor] = None        # [T] int32: survivors rescored per query (-1 = exact scan)
     launches: int = 0
 
     def fallback_queries(self) -> int:
         return int(self.fb_count.sum().item()) if self.fb_count is not None else 0
+
+    def exact_scan_queries(self) -> int:
+        if self.exact_count is None or not self.collect:
+            return self.fallback_queries()
+        return int(self.exact_count.sum().item())
 
 
 last_info: Optional[SearchInfo] = None
@@ -455,11 +462,13 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
                            ev0.cuda_event if ev0 is not None else None,
                            ev1.cuda_event if ev1 is not None else None, _stream_ptr())
     _cabi.check(rc, "alive_knn_match")
-    _count(B + (4 if m == 1 else 2))
+    _count(B + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
                            fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
+                           exact_count=workspace[off[9] + 4 * lib.items:off[9] + 4 * lib.items + 4].view(torch.int32),
+                           collect=m == 1 and off[7] > off[6],
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
-                           launches=B + (4 if m == 1 else 2))
+                           launches=B + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info._workspace = workspace
     return (out if want_out else None), top_idx, top_score
 

@@ -38,6 +38,25 @@ def main():
     out, idx = A.match_features(torch.from_numpy(base[:, :, :10].copy()).cuda(), torch.from_numpy(ref).cuda(), 3, 0.0,
                                 return_indices=True, mode="screen")
     torch.cuda.synchronize()
+    # one realtime chunk: the skinny kernel (operands swapped, resident query chunk)
+    src = rng.standard_normal((1, 768, 24), dtype=np.float32)
+    ref = rng.standard_normal((1, 768, 3512), dtype=np.float32)
+    out, idx = A.match_features(torch.from_numpy(src).cuda(), torch.from_numpy(ref).cuda(), 4, 0.0, return_indices=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), O.match_features_np(src, ref, 4, 0.0, True)[1])
+    print("ok skinny chunk", flush=True)
+    # tight clusters on a library big enough for the collect pass (second tensor-core pass + rescoring)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    cent = torch.randn(768, 40, device="cuda", generator=g)
+    refc = (cent[:, torch.randint(0, 40, (70_000,), device="cuda", generator=g)] +
+            0.2 * torch.randn(768, 70_000, device="cuda", generator=g))[None]
+    srcc = (cent[:, torch.randint(0, 40, (260,), device="cuda", generator=g)] +
+            0.2 * torch.randn(768, 260, device="cuda", generator=g))[None]
+    libc = A.pack_library(refc)
+    _, idx_s, _ = M.run_match(srcc, libc, 4, 0.0, mode="screen")
+    assert M.last_info.collect and M.last_info.fallback_queries() > 0
+    torch.cuda.synchronize()
+    print("ok collect pass", M.last_info.fallback_queries(), M.last_info.exact_scan_queries(), flush=True)
     vl = A.VoiceLibrary(num_tokens=300).cuda()
     s = torch.randn(2, 768, 11, device="cuda", requires_grad=True)
     vl.match(s, alpha=0.5).sum().backward()

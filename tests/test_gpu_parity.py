@@ -475,3 +475,58 @@ def test_other_feature_dims(D, mode):
     same = (idx.cpu().numpy() == want_idx).all(axis=2)
     o = out.detach().cpu().numpy()
     assert np.array_equal(np.swapaxes(o, 1, 2)[same], np.swapaxes(want_out, 1, 2)[same])
+
+
+def _clustered(T, N, nclus, noise, seed, dev="cuda"):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    cent = torch.randn(768, nclus, device=dev, generator=g)
+    ref = (cent[:, torch.randint(0, nclus, (N,), device=dev, generator=g)] +
+           noise * torch.randn(768, N, device=dev, generator=g))[None]
+    src = (cent[:, torch.randint(0, nclus, (T,), device=dev, generator=g)] +
+           noise * torch.randn(768, T, device=dev, generator=g))[None]
+    return src, ref
+
+
+@pytest.mark.parametrize("T,N,nclus,noise,expect", [
+    (300, 60_000, 60, 0.2, "collect"),        # ~1000 frames inside every query's band: collected and rescored
+    (300, 60_000, 12, 0.2, "overflow"),       # ~5000 per cluster: more than a candidate buffer holds -> exhaustive scan
+    (2500, 8_000, 8, 0.2, "no_slot"),         # more uncertified queries than slots; the rest skip the collect pass
+    (400, 50_000, 50, 0.5, "mixed"),
+])
+def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect):
+    """Tight clusters defeat the bf16 certificate; the second (collecting) tensor-core pass must give
+    exactly what the exhaustive scan gives, whichever of its exits a query takes."""
+    src, ref = _clustered(T, N, nclus, noise, seed=T + N)
+    lib = A.pack_library(ref)
+    out_s, idx_s, sc_s = M.run_match(src, lib, 4, 0.25, mode="screen")
+    info = M.last_info
+    fb, ex = info.fallback_queries(), info.exact_scan_queries()
+    assert info.collect
+    out_e, idx_e, sc_e = M.run_match(src, lib, 4, 0.25, mode="exact")
+    assert torch.equal(idx_s, idx_e)
+    assert torch.equal(out_s, out_e)
+    assert torch.equal(sc_s, sc_e)
+    if expect == "collect":
+        assert fb > T // 2 and ex == 0
+    elif expect == "overflow":
+        assert fb > T // 2 and ex > T // 2
+    elif expect == "no_slot":
+        assert fb > 2048 and ex >= fb - 2048
+    # and against the oracle on a slice (the whole batch would take the CPU too long)
+    sl = slice(0, 40)
+    _assert_parity(out_s[:, sl].transpose(1, 2), idx_s[:, sl], src[:, :, sl].cpu().numpy(), ref.cpu().numpy(), 4, 0.25)
+
+
+def test_collect_pass_with_unusable_cut():
+    """Non-finite library rows void the certificate AND the cut: every query must reach the exhaustive scan."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ref = torch.randn(1, 768, 90_000, device="cuda", generator=g)
+    ref[0, :, 777] = 0.0                                   # zero row -> NaN similarity, ranks first (torch.topk)
+    src = torch.randn(1, 768, 200, device="cuda", generator=g)
+    lib = A.pack_library(ref)
+    out_s, idx_s, _ = M.run_match(src, lib, 4, 0.0, mode="screen")
+    info = M.last_info
+    assert info.collect and info.fallback_queries() == 200 and info.exact_scan_queries() == 200
+    out_e, idx_e, _ = M.run_match(src, lib, 4, 0.0, mode="exact")
+    assert torch.equal(idx_s, idx_e)
+    assert (idx_s[..., 0] == 777).all()

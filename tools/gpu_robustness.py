@@ -64,7 +64,7 @@ def main():
         _, idx_s, _ = M.run_match(src, lib, 4, 0.0, mode="screen")
         _, idx_e, _ = M.run_match(src, lib, 4, 0.0, mode="exact")
         same = bool(torch.equal(idx_s, idx_e))
-        print(f"{name:22s}: {ms:8.3f} ms  fallback {fb:5d}/{T}  survivors mean "
+        print(f"{name:22s}: {ms:8.3f} ms  uncertified {fb:5d}/{T} (exhaustive scan {info.exact_scan_queries():4d})  survivors mean "
               f"{seln[ok].float().mean().item() if ok.any() else float('nan'):6.1f} max {seln.max().item():4d}  "
               f"screen==exact: {same}")
 
@@ -86,9 +86,10 @@ def sparse_fallback():
     src[0, :, :5] = c + 0.01 * torch.randn(768, 5, device=dev, generator=g)
     ms1 = timed(lambda: M.run_match(src, lib, 4, 0.0, mode="screen"))
     fb1 = M.last_info.fallback_queries()
+    ex1 = M.last_info.exact_scan_queries()
     _, idx_s, _ = M.run_match(src, lib, 4, 0.0, mode="screen")
     _, idx_e, _ = M.run_match(src[:, :, :16].contiguous(), lib, 4, 0.0, mode="exact")
-    print(f"no cluster queries: {ms0:.3f} ms (fallback {fb0});  5 cluster queries: {ms1:.3f} ms (fallback {fb1}); "
+    print(f"no cluster queries: {ms0:.3f} ms (fallback {fb0});  5 cluster queries: {ms1:.3f} ms (uncertified {fb1}, exhaustive scan {ex1}); "
           f"first 16 queries screen==exact: {bool(torch.equal(idx_s[:, :16], idx_e))}")
 
 
