@@ -530,3 +530,32 @@ def test_collect_pass_with_unusable_cut():
     out_e, idx_e, _ = M.run_match(src, lib, 4, 0.0, mode="exact")
     assert torch.equal(idx_s, idx_e)
     assert (idx_s[..., 0] == 777).all()
+
+
+def test_collect_pass_on_a_row_shard():
+    """The collect pass inside a row shard (multi-GPU local top-k: row_base != 0, no gather): global
+    indices, and the two shards merged must equal the unsharded answer."""
+    T, N = 500, 80_000                     # per shard T * N/2 = 2e7 >= 2^24: the collect pass is on
+    src, ref = _clustered(T, N, 40, 0.2, seed=17)
+    lib = A.pack_library(ref)
+    _, want_idx, want_sc = M.run_match(src, lib, 4, 0.0, mode="exact")
+    half = N // 2
+    tops, uncertified = [], 0
+    for lo, hi in ((0, half), (half, N)):
+        shard = M.PackedFrames(n=hi - lo, d=768, raw=lib.raw[lo:hi], norms=lib.norms[lo:hi], packed=lib.packed[lo:hi],
+                               err=lib.err[lo:hi], stats=lib.stats, row_base=lo)
+        _, i, s = M.run_match(src, shard, 4, 0.0, want_out=False)
+        assert M.last_info.collect
+        uncertified += M.last_info.fallback_queries()
+        assert M.last_info.exact_scan_queries() == 0
+        assert int(i.min()) >= lo and int(i.max()) < hi
+        tops.append((s.view(T, 4), i.view(T, 4)))
+    assert uncertified > T
+    sc = torch.stack([t[0] for t in tops]).contiguous()
+    ix = torch.stack([t[1] for t in tops]).contiguous()
+    top_s = torch.empty((T, 4), device="cuda")
+    top_i = torch.empty((T, 4), dtype=torch.int64, device="cuda")
+    rc = _cabi.load().alive_knn_merge(sc.data_ptr(), ix.data_ptr(), 2, T, 4, top_s.data_ptr(), top_i.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "merge")
+    assert torch.equal(top_i, want_idx[0]) and torch.equal(top_s, want_sc[0])

@@ -24,11 +24,16 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (B, T, N, k, alpha) in [(1, 500, 200_003, 4, 0.0), (2, 64, 50_000, 4, 0.25), (1, 33, 5, 4, 0.0), (1, 24, 50_000, 4, 0.0),
+    for (B, T, N, k, alpha) in [(1, 500, 200_003, 4, 0.0), (2, 64, 50_000, 4, 0.25), (1, 33, 5, 4, 0.0), (1, 24, 50_000, 4, 0.0), (1, 300, 160_000, 4, 0.0),
                                 (1, 2000, 1_000_000, 4, 0.0)]:
         g = torch.Generator(device=dev).manual_seed(123)
         src = torch.randn(B, 768, T, device=dev, generator=g)
         ref = torch.randn(1, 768, N, device=dev, generator=g)
+        if N == 160_000:
+            # tight clusters: nothing certifies, every shard runs its collect pass
+            cent = torch.randn(768, 40, device=dev, generator=g)
+            ref = (cent[:, torch.randint(0, 40, (N,), device=dev, generator=g)] + 0.2 * ref[0])[None]
+            src = (cent[:, torch.randint(0, 40, (T,), device=dev, generator=g)] + 0.2 * src[0])[None]
         want, widx = A.match_features(src, ref.expand(B, -1, -1), k, alpha, return_indices=True)
         same = True
         for peer in (False, True):
