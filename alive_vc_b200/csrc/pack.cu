@@ -31,7 +31,8 @@ template <int kFrames>
 __global__ void __launch_bounds__(kPackThreads)
 pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
             float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
-            float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+            float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero,
+            int async_stage) {
   extern __shared__ float tile[];          // [d][kFrames + 1]
   pdl_launch_dependents();                 // a search launched behind this pack may start streaming the library
   if (blockIdx.x == 0)
@@ -47,14 +48,38 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
     const int f = lane % kFrames, jsub = lane / kFrames;
     const bool ok = f < nf;
     const float* src = x + (f0 + f) * stride_n;
-    for (int j = warp * kRowsPerWarp + jsub; j < d; j += (kPackThreads / 32) * kRowsPerWarp)
-      tile[j * ld + f] = ok ? src[j * stride_d] : 0.f;
+    if (async_stage) {
+      // every 4-byte element of the CTA's tile is requested before anything waits (cp.async straight
+      // into shared memory, no register staging): ~d*kFrames*4 B in flight per CTA instead of a
+      // handful of loads per thread - the staging loop was latency-bound, not bandwidth-bound
+      const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
+      for (int j = warp * kRowsPerWarp + jsub; j < d; j += (kPackThreads / 32) * kRowsPerWarp) {
+        if (ok)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + 4u * (j * ld + f)),
+                       "l"(src + j * stride_d)
+                       : "memory");
+        else
+          tile[j * ld + f] = 0.f;
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+      for (int j = warp * kRowsPerWarp + jsub; j < d; j += (kPackThreads / 32) * kRowsPerWarp)
+        tile[j * ld + f] = ok ? src[j * stride_d] : 0.f;
+    }
   } else {
     // already row-major frames: lane = channel
+    const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
     for (int f = warp; f < kFrames; f += kPackThreads / 32) {
       const float* src = x + (f0 + f) * stride_n;
-      for (int j = lane; j < d; j += 32) tile[j * ld + f] = (f < nf) ? src[j] : 0.f;
+      if (async_stage && f < nf) {
+        for (int j = lane; j < d; j += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + 4u * (j * ld + f)), "l"(src + j)
+                       : "memory");
+      } else {
+        for (int j = lane; j < d; j += 32) tile[j * ld + f] = (f < nf) ? src[j] : 0.f;
+      }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
 
@@ -190,17 +215,19 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
     attr_done = true;
   }
   __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
+  // ALIVE_KNN_PACK_ASYNC=0: register-staged loads (the first version; kept for A/B runs)
+  static const int async_stage = !(getenv("ALIVE_KNN_PACK_ASYNC") && atoi(getenv("ALIVE_KNN_PACK_ASYNC")) == 0);
   if (n <= 512) {
     pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw,
                                                                                        norms, pk, err, stats, zero_words, n_zero);
   } else if (n <= 8192) {
     const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
     pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
   } else {
     const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
     pack_kernel<32><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
   }
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;

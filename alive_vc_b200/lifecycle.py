@@ -1,5 +1,6 @@
-"""Callers either side of the match (SURVEY §8(f) 1-3): building a voice library on the GPU, matching
-all overlapped windows of an utterance in one call, and the host-buffer realtime loop.
+"""Callers either side of the match (SURVEY §8(f) 1-4): building a voice library on the GPU, matching
+all overlapped windows of an utterance in one call, the host-buffer realtime loop, and the row-major
+frame format for producers that emit [T, 768] (pack_rows / match_rows).
 
 Reference call sites mirrored here (nothing below re-implements the encoders/decoder around them):
     generate_voice_library.py:30-42   512 random frames written into random slots of `tokens`, saved
@@ -158,6 +159,56 @@ def match_windows(windows, lib: M.PackedFrames, k: int = 4, alpha: float = 0.0, 
         res.append(out[:, at:at + n].transpose(1, 2))
         at += n
     return res
+
+
+def pack_rows(frames_nd: torch.Tensor) -> M.PackedFrames:
+    """Pack a library a producer already holds ROW-major: [N, D] (or [1, N, D]) float32 CUDA frames,
+    e.g. content-encoder output kept as `[T, 768]` instead of the reference's `[1, 768, T]`
+    (module/content_encoder.py:21-25 emits channel-major only because Conv1d does).  K1 reads each
+    3 KB frame as one coalesced row - no transpose pass, no channel-major staging copy."""
+    if frames_nd.dim() == 3:
+        if frames_nd.shape[0] != 1:
+            raise RuntimeError("pack_rows expects [N, D] or [1, N, D]")
+        frames_nd = frames_nd[0]
+    if frames_nd.dim() != 2:
+        raise RuntimeError("pack_rows expects [N, D] or [1, N, D]")
+    return M.pack_frames(frames_nd.t())        # a [D, N] VIEW with stride_d == 1: K1's row-major branch
+
+
+def match_rows(frames: torch.Tensor, lib, k: int = 4, alpha: float = 0.0, *, return_indices: bool = False,
+               mode: str = "auto"):
+    """The match for a producer/consumer pair that works on ROW-major frames.
+
+    `frames` is [T, D] or [B, T, D] (any strides; the natural output of a channels-last encoder),
+    `lib` a PackedFrames (pack_rows / pack_library / LibraryBuilder.packed()) or a row-major [N, D]
+    tensor.  Returns the matched features in the SAME row-major shape, contiguous - the block the
+    kernels write, handed over without the transposed view `match_features` has to return to look like
+    common.py:108.  Values and indices are bit-identical to
+    `match_features(frames.transpose(-1, -2), tokens)`; the per-call query transpose of
+    common.py:100 never happens in either direction (the C ABI takes the strides as they are).
+    """
+    squeeze = frames.dim() == 2
+    f = frames.unsqueeze(0) if squeeze else frames
+    if f.dim() != 3:
+        raise RuntimeError("match_rows expects [T, D] or [B, T, D]")
+    if not isinstance(lib, M.PackedFrames):
+        lib = M.cached_pack(lib, (lib[0] if lib.dim() == 3 else lib).t(), tag=1)
+    if f.shape[2] != lib.d:
+        raise RuntimeError(f"feature dims differ: queries {f.shape[2]}, library {lib.d}")
+    M._require_cuda(f, "frames")
+    src = f if f.dtype == torch.float32 else f.float()
+    B, T, _ = src.shape
+    if T == 0:
+        out = torch.empty((B, 0, lib.d), dtype=torch.float32, device=src.device)
+        idx = torch.empty((B, 0, k), dtype=torch.int64, device=src.device)
+    else:
+        with torch.no_grad():
+            out, idx, _ = M.match_packed(src.transpose(1, 2), lib, k, float(alpha), mode)   # a view: no copy
+    if out.dtype != frames.dtype:
+        out = out.to(frames.dtype)
+    if squeeze:
+        out, idx = out[0], idx[0]
+    return (out, idx) if return_indices else out
 
 
 class HostStreamingMatcher:

@@ -488,6 +488,31 @@ def gpu_arm(args):
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                "avg_kernel_ms": g_ms, "bytes_per_query_frame": g_bytes // rows,
                                "note": "standalone K4 on this step's indices; random 3 KB rows of the raw library"}
+        # K1 alone (once per library, generate_voice_library.py / load time): the pack kernel on a fresh
+        # channel-major [D, n] chunk far larger than L2.  Algorithmic bytes per frame: D*(4 read + 4 raw
+        # + 2 packed) + 8 (norm, err) = 7,688 B.
+        pack_roof = None
+        if world == 1:
+            pn = 250_000
+            px = torch.randn(D, pn, device=dev)
+            pdst = M.alloc_packed(pn, D, dev)
+            for _ in range(2):
+                M.pack_into(pdst, 0, px)
+            torch.cuda.synchronize()
+            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            pe0.record()
+            for _ in range(reps):
+                M.pack_into(pdst, 0, px)
+            pe1.record()
+            torch.cuda.synchronize()
+            p_ms = pe0.elapsed_time(pe1) / reps
+            p_bytes = pn * (D * 10 + 8)
+            pack_roof = {"bound": "hbm", "kernel": "pack_kernel<32>", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": p_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "avg_kernel_ms": p_ms, "bytes_per_frame": D * 10 + 8, "frames": pn,
+                         "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse)"}
+            del px, pdst
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = run_cpu_arm(args.workload, 3, 1)
@@ -517,6 +542,8 @@ def gpu_arm(args):
             line["torch_eager_gpu"] = eager
         if gather_roof is not None:
             line["roofline_gather"] = gather_roof
+        if pack_roof is not None:
+            line["roofline_pack"] = pack_roof
         if lat:
             line["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                                   "min": lat[0]}

@@ -132,3 +132,79 @@ def test_host_streaming_matcher(T, N, batch):
     hm.submit(chunk)
     want, _, _ = A.match_packed(chunk.cuda(), lib, k, alpha)
     assert torch.equal(hm.result(), want.transpose(1, 2).cpu())
+
+
+# ---- row-major producer format (SURVEY §8(f) 4) ------------------------------------------------
+@pytest.mark.parametrize("T,N", [(24, 3512), (450, 3512), (1000, 20_000), (9000, 40_000)])
+def test_match_rows_equals_match_features(T, N):
+    """[T, D] row-major frames in, [T, D] out: bit-identical to the channel-major drop-in (and to the
+    oracle) - the per-call transposes of common.py:100/108 simply do not happen."""
+    from alive_vc_b200.lifecycle import match_rows, pack_rows
+    rng = np.random.default_rng(T + N)
+    D = 768
+    q_rows = rng.standard_normal((T, D), dtype=np.float32)
+    l_rows = rng.standard_normal((N, D), dtype=np.float32)
+    lib = pack_rows(_cuda(l_rows))
+    ref_lib = A.pack_library(_cuda(l_rows.T.copy()[None]))               # the reference's [1, D, N] layout
+    for name in ("raw", "norms", "packed", "err"):
+        assert torch.equal(getattr(lib, name), getattr(ref_lib, name)), name
+    out, idx = match_rows(_cuda(q_rows), lib, 4, 0.25, return_indices=True)
+    assert tuple(out.shape) == (T, D) and out.is_contiguous()
+    w_out, w_idx = A.match_features(_cuda(q_rows.T.copy()[None]), _cuda(l_rows.T.copy()[None]), 4, 0.25,
+                                    return_indices=True)
+    assert torch.equal(idx, w_idx[0])
+    assert torch.equal(out, w_out[0].t())
+    if T * N <= 2_000_000:
+        o_out, o_idx, _ = O.match_features_np(q_rows.T[None], l_rows.T[None], 4, 0.25, True)
+        scores = O.cosine_scores_np(q_rows.T[None], l_rows.T[None])
+        ok, _, _, bad = O.indices_match_mod_ties(idx[None].cpu().numpy(), o_idx, scores, 1e-6)
+        assert ok, bad
+        np.testing.assert_allclose(out.cpu().numpy(), o_out[0].T, rtol=1e-5, atol=1e-6)
+
+
+def test_match_rows_batched_strided_and_raw_library():
+    """[B, T, D] with a non-contiguous frame stride, library handed over as a plain [N, D] tensor."""
+    from alive_vc_b200.lifecycle import match_rows
+    rng = np.random.default_rng(77)
+    D, B, T, N = 768, 3, 50, 5000
+    wide = _cuda(rng.standard_normal((B, T, 2 * D), dtype=np.float32))
+    frames = wide[:, :, :D]                                               # row stride 2*D
+    l_rows = _cuda(rng.standard_normal((N, D), dtype=np.float32))
+    out, idx = match_rows(frames, l_rows, 4, 0.0, return_indices=True)
+    assert tuple(out.shape) == (B, T, D)
+    w_out, w_idx = A.match_features(frames.transpose(1, 2).contiguous(),
+                                    l_rows.t().contiguous()[None].expand(B, D, N), 4, 0.0, return_indices=True)
+    assert torch.equal(idx, w_idx)
+    assert torch.equal(out, w_out.transpose(1, 2))
+    # empty chunk and dtype passthrough
+    e = match_rows(frames[:, :0], l_rows)
+    assert tuple(e.shape) == (B, 0, D)
+    h = match_rows(frames.half(), l_rows)
+    assert h.dtype == torch.float16
+
+
+def test_pack_async_staging_is_bit_identical(monkeypatch):
+    """K1's cp.async staging (default) writes exactly what the register-staged loop wrote:
+    channel-major and row-major inputs, ragged last CTA."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, hashlib\n"
+        "from alive_vc_b200 import matching as M\n"
+        "g = torch.Generator(device='cuda').manual_seed(3)\n"
+        "x = torch.randn(768, 20011, device='cuda', generator=g)\n"
+        "h = hashlib.sha256()\n"
+        "for v in (x, x.t().contiguous().t()):\n"
+        "    p = M.pack_frames(v)\n"
+        "    for n in ('raw', 'norms', 'packed', 'err', 'stats'):\n"
+        "        h.update(getattr(p, n).view(torch.uint8).cpu().numpy().tobytes())\n"
+        "print(h.hexdigest())\n")
+    import os
+    outs = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, ALIVE_KNN_PACK_ASYNC=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]

@@ -71,3 +71,16 @@ def test_lifecycle_host_logic_without_a_gpu():
     with pytest.raises(RuntimeError, match="CUDA"):
         LibraryBuilder(device="cpu")
     assert match_windows([], None) == []
+
+
+def test_match_rows_host_checks_without_a_gpu():
+    """Row-major entry points: shape errors first, then the loud no-CPU-path failure."""
+    from alive_vc_b200.lifecycle import match_rows, pack_rows
+    with pytest.raises(RuntimeError, match=r"\[T, D\] or \[B, T, D\]"):
+        match_rows(torch.randn(768), torch.randn(20, 768))
+    with pytest.raises(RuntimeError, match=r"\[N, D\]"):
+        pack_rows(torch.randn(2, 20, 768))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pack_rows(torch.randn(20, 768))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        match_rows(torch.randn(5, 768), torch.randn(20, 768))
