@@ -38,8 +38,9 @@ int resolve_mode(int mode, int64_t n, int d, int k) {
   return mode;
 }
 
-// Second screen pass for uncertified queries (single item, tiled screen, enough work for the
-// exhaustive scan to hurt): at most kCollectRows queries get a slot and a buffer of kCollectCap
+// Second screen pass for uncertified queries (single item; the first screen may have been the tiled
+// or the skinny kernel - the collect pass always runs the tiled one on its own compact query matrix;
+// enough work for the exhaustive scan to hurt): at most kCollectRows queries get a slot and a buffer of kCollectCap
 // candidate frames each.  Area layout: fb2_list [rows] | qc_packed [rows_c, d] bf16 | cut [rows_c] |
 // cnt [rows_c] | idx [rows_c, cap]; fb2_count is the word after the per-item fallback counters.
 constexpr int kCollectRows = 2048;
@@ -54,7 +55,7 @@ struct CollectLayout {
 int collect_layout(int32_t rows, int64_t n, int32_t d, int32_t num_sms, int mode, int32_t items,
                    const alive_knn_plan_t& screen_plan, CollectLayout* cl) {
   static const bool enabled = !(getenv("ALIVE_KNN_COLLECT") && atoi(getenv("ALIVE_KNN_COLLECT")) == 0);
-  cl->on = enabled && mode == 1 && items == 1 && screen_plan.kernel == 0 && d % 64 == 0 &&
+  cl->on = enabled && mode == 1 && items == 1 && (screen_plan.kernel == 0 || screen_plan.kernel == 1) && d % 64 == 0 &&
            static_cast<double>(rows) * static_cast<double>(n) >= 16777216.0;
   cl->bytes = 0;
   if (!cl->on) return 0;

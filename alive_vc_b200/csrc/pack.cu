@@ -124,6 +124,214 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Library-sized inputs: two layout-specific kernels.  The generic kernel above spent ~1200 warp
+// instructions per frame (ncu: issue-bound at 53 % of HBM peak; 4-byte LDGSTS at 8 cycles each, a
+// full IEEE division per element, three fp64 conversions per element); these two do the same
+// arithmetic in ~400.
+// ---------------------------------------------------------------------------------------------
+
+// x / nrm, correctly rounded, for 2^-40 <= nrm <= 2^40 and r = __frcp_rn(nrm) (correctly rounded
+// reciprocal): quotient estimate + two exact-remainder corrections (Markstein); a quotient too small
+// for the remainders to be exact (or a signed zero) takes the full IEEE division.
+__device__ __forceinline__ float div_by_norm(float x, float nrm, float r) {
+  float q = __fmul_rn(x, r);
+  float e = __fmaf_rn(-q, nrm, x);
+  q = __fmaf_rn(e, r, q);
+  e = __fmaf_rn(-q, nrm, x);
+  q = __fmaf_rn(e, r, q);
+  return (fabsf(q) >= 0x1p-40f) ? q : __fdiv_rn(x, nrm);
+}
+__device__ __forceinline__ bool norm_is_tame(float nrm) { return nrm >= 0x1p-40f && nrm <= 0x1p40f; }
+
+__device__ __forceinline__ void finish_frame(long long row, float nrm, float e2, bool finite, float* __restrict__ norms,
+                                             float* __restrict__ err, unsigned int* __restrict__ stats) {
+  norms[row] = nrm;
+  // round the error norm UP a little: it feeds a bound that must not be under-estimated (the fp32 sum of
+  // d squares is within 2e-6 relative of the exact one)
+  const float e = finite ? sqrtf(e2) * 1.0001f + 1e-9f : 0.f;
+  if (err) err[row] = e;
+  if (stats) {
+    if (finite) atomicMax(&stats[0], __float_as_uint(e));
+    else atomicAdd(&stats[1], 1u);
+  }
+}
+
+// Channel-major input (the reference's [D, N], stride_n == 1, 16-byte aligned rows): a CTA owns 32
+// frames; 16-byte cp.async copies (4 frames of one channel) fill a [d][36] tile, every warp then owns
+// 4 frames and reads them back as float4 (conflict-free: quarter-warp rows are 144 B apart).
+constexpr int kCmLd = 36;
+__global__ void __launch_bounds__(kPackThreads)
+pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride_d, float* __restrict__ raw,
+               float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
+               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+  extern __shared__ __align__(16) float tile[];   // [d][36]
+  pdl_launch_dependents();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long f0 = static_cast<long long>(blockIdx.x) * 32;
+  const int nf = static_cast<int>(min(32ll, n - f0));
+  const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
+  if (nf == 32) {
+    const int g4 = threadIdx.x & 7, jsub = threadIdx.x >> 3;          // 8 groups of 4 frames x 32 channel rows
+    const float* src = x + f0 + 4 * g4 + static_cast<long long>(jsub) * stride_d;
+    unsigned dst = tile_s + 4u * (jsub * kCmLd + 4 * g4);
+    const long long src_step = 32 * stride_d;
+#pragma unroll 4
+    for (int j = jsub; j < d; j += 32) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      src += src_step;
+      dst += 4u * 32 * kCmLd;
+    }
+  } else {
+    // ragged last CTA: element-wise, missing frames read as zeros
+    const bool ok = lane < nf;
+    const float* src = x + f0 + lane;
+    for (int j = warp; j < d; j += kPackThreads / 32) {
+      if (ok)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + 4u * (j * kCmLd + lane)),
+                     "l"(src + j * stride_d)
+                     : "memory");
+      else
+        tile[j * kCmLd + lane] = 0.f;
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  // warp w: frames 4w..4w+3, lane: channels lane, lane+32, ...
+  const int fw = 4 * warp;
+  const long long row0 = f0 + fw;
+  const int nv = max(0, min(4, nf - fw));
+  if (nv == 0) return;
+  const float4* t4 = reinterpret_cast<const float4*>(tile) + warp;     // tile[j*36 + 4w] = t4[j*9]
+  double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
+#pragma unroll 4
+  for (int j = lane; j < d; j += 32) {
+    const float4 v = t4[j * (kCmLd / 4)];
+    raw[row0 * d + j] = v.x;
+    if (nv > 1) raw[(row0 + 1) * d + j] = v.y;
+    if (nv > 2) raw[(row0 + 2) * d + j] = v.z;
+    if (nv > 3) raw[(row0 + 3) * d + j] = v.w;
+    ss0 += static_cast<double>(v.x) * static_cast<double>(v.x);
+    ss1 += static_cast<double>(v.y) * static_cast<double>(v.y);
+    ss2 += static_cast<double>(v.z) * static_cast<double>(v.z);
+    ss3 += static_cast<double>(v.w) * static_cast<double>(v.w);
+  }
+  float nrm[4];
+  nrm[0] = static_cast<float>(sqrt(warp_sum_f64(ss0)));
+  nrm[1] = static_cast<float>(sqrt(warp_sum_f64(ss1)));
+  nrm[2] = static_cast<float>(sqrt(warp_sum_f64(ss2)));
+  nrm[3] = static_cast<float>(sqrt(warp_sum_f64(ss3)));
+  bool tame[4], finite[4];
+  float rinv[4], e2[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tame[c] = norm_is_tame(nrm[c]);
+    rinv[c] = tame[c] ? __frcp_rn(nrm[c]) : 0.f;
+    finite[c] = true;
+    e2[c] = 0.f;
+  }
+  unsigned short* pk16 = reinterpret_cast<unsigned short*>(packed);
+#pragma unroll 2
+  for (int j = lane; j < d; j += 32) {
+    const float4 v = t4[j * (kCmLd / 4)];
+    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float a;
+      if (tame[c]) {
+        a = div_by_norm(xs[c], nrm[c], rinv[c]);
+      } else {
+        a = __fdiv_rn(xs[c], nrm[c]);
+        finite[c] = finite[c] && isfinite(a);
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(a);
+      const float da = __bfloat162float(h) - a;
+      e2[c] = fmaf(da, da, e2[c]);
+      if (c < nv) pk16[(row0 + c) * d + j] = __bfloat16_as_ushort(h);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e2[c] += __shfl_xor_sync(0xffffffffu, e2[c], o);
+    finite[c] = __all_sync(0xffffffffu, finite[c]);
+    if (lane == 0 && c < nv) finish_frame(row0 + c, nrm[c], e2[c], finite[c], norms, err, stats);
+  }
+}
+
+// Row-major input (a producer's [n, D]: stride_d == 1, 16-byte aligned rows, d % 4 == 0): nothing to
+// transpose - one warp per frame, the 3 KB row lives in registers between the norm and the division.
+constexpr int kRmMaxV = 12;                         // float4 per lane: d <= 1536
+__global__ void __launch_bounds__(kPackThreads)
+pack_rm_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, float* __restrict__ raw,
+               float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
+               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+  pdl_launch_dependents();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (kPackThreads / 32) + warp;
+  if (row >= n) return;
+  const int d4 = d >> 2;
+  const float4* src = reinterpret_cast<const float4*>(x + row * stride_n);
+  float4* dst_raw = reinterpret_cast<float4*>(raw + row * d);
+  float4 v[kRmMaxV];
+#pragma unroll
+  for (int i = 0; i < kRmMaxV; ++i) {
+    const int q = lane + 32 * i;
+    v[i] = (q < d4) ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  double ss = 0.0;
+#pragma unroll
+  for (int i = 0; i < kRmMaxV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < d4) {
+      dst_raw[q] = v[i];
+      ss += static_cast<double>(v[i].x) * static_cast<double>(v[i].x);
+      ss += static_cast<double>(v[i].y) * static_cast<double>(v[i].y);
+      ss += static_cast<double>(v[i].z) * static_cast<double>(v[i].z);
+      ss += static_cast<double>(v[i].w) * static_cast<double>(v[i].w);
+    }
+  }
+  const float nrm = static_cast<float>(sqrt(warp_sum_f64(ss)));
+  const bool tame = norm_is_tame(nrm);
+  const float rinv = tame ? __frcp_rn(nrm) : 0.f;
+  bool finite = true;
+  float e2 = 0.f;
+  uint2* dst_pk = reinterpret_cast<uint2*>(packed + row * d);
+#pragma unroll
+  for (int i = 0; i < kRmMaxV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < d4) {
+      const float xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      unsigned short hb[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a;
+        if (tame) {
+          a = div_by_norm(xs[c], nrm, rinv);
+        } else {
+          a = __fdiv_rn(xs[c], nrm);
+          finite = finite && isfinite(a);
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(a);
+        const float da = __bfloat162float(h) - a;
+        e2 = fmaf(da, da, e2);
+        hb[c] = __bfloat16_as_ushort(h);
+      }
+      dst_pk[q] = make_uint2(static_cast<unsigned>(hb[0]) | (static_cast<unsigned>(hb[1]) << 16),
+                             static_cast<unsigned>(hb[2]) | (static_cast<unsigned>(hb[3]) << 16));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+  finite = __all_sync(0xffffffffu, finite);
+  if (lane == 0) finish_frame(row, nrm, e2, finite, norms, err, stats);
+}
+
 // Tiny batches (streaming chunks, T <= 512): one CTA per frame, three channels per thread, two
 // block reductions - one load round trip instead of a 768-row staging loop on a handful of CTAs.
 __global__ void __launch_bounds__(kPackThreads)
@@ -212,12 +420,24 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
   if (!attr_done) {
     ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
     ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4));
     attr_done = true;
   }
   __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
   // ALIVE_KNN_PACK_ASYNC=0: register-staged loads (the first version; kept for A/B runs)
   static const int async_stage = !(getenv("ALIVE_KNN_PACK_ASYNC") && atoi(getenv("ALIVE_KNN_PACK_ASYNC")) == 0);
-  if (n <= 512) {
+  // layout-specific kernels (ALIVE_KNN_PACK_FAST=0: the generic kernel everywhere, for A/B runs)
+  static const int fast = !(getenv("ALIVE_KNN_PACK_FAST") && atoi(getenv("ALIVE_KNN_PACK_FAST")) == 0);
+  const bool x16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const bool out16 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
+  if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && x16 && out16) {
+    pack_rm_kernel<<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, as_stream(stream)>>>(
+        x, n, d, stride_n, raw, norms, pk, err, stats, zero_words, n_zero);
+  } else if (fast && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
+    const size_t smem = static_cast<size_t>(d) * kCmLd * sizeof(float);
+    pack_cm_kernel<<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
+        x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+  } else if (n <= 512) {
     pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw,
                                                                                        norms, pk, err, stats, zero_words, n_zero);
   } else if (n <= 8192) {

@@ -183,28 +183,58 @@ def test_match_rows_batched_strided_and_raw_library():
     assert h.dtype == torch.float16
 
 
-def test_pack_async_staging_is_bit_identical(monkeypatch):
-    """K1's cp.async staging (default) writes exactly what the register-staged loop wrote:
-    channel-major and row-major inputs, ragged last CTA."""
+def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
+    """K1's layout-specific kernels (16-byte cp.async tile / register-resident rows, reciprocal-based
+    correctly rounded division) write exactly the frames, norms and bf16 rows the generic kernel writes
+    (full IEEE division per element); `err` is summed in fp32 instead of fp64 and may differ by 1e-5
+    relative.  Channel-major and row-major inputs, ragged last CTA, unaligned fallback, zero / huge /
+    tiny / non-finite rows, denormal and negative-zero elements."""
+    import os
     import subprocess
     import sys
     code = (
-        "import torch, hashlib\n"
+        "import sys, torch, hashlib, numpy as np\n"
         "from alive_vc_b200 import matching as M\n"
         "g = torch.Generator(device='cuda').manual_seed(3)\n"
-        "x = torch.randn(768, 20011, device='cuda', generator=g)\n"
-        "h = hashlib.sha256()\n"
-        "for v in (x, x.t().contiguous().t()):\n"
-        "    p = M.pack_frames(v)\n"
-        "    for n in ('raw', 'norms', 'packed', 'err', 'stats'):\n"
-        "        h.update(getattr(p, n).view(torch.uint8).cpu().numpy().tobytes())\n"
-        "print(h.hexdigest())\n")
-    import os
+        "res = {}\n"
+        "for n in (20000, 20012, 20011, 9001):\n"
+        "    x = torch.randn(768, n, device='cuda', generator=g)\n"
+        "    x[:, 5] = 0.0\n"
+        "    x[:, 6] *= 1e30\n"
+        "    x[:, 7] *= 1e-30\n"
+        "    x[:, 8] *= 3e-13\n"
+        "    x[:, 9] *= 2e12\n"
+        "    x[3, 10] = float('inf')\n"
+        "    x[4, 11] = float('nan')\n"
+        "    x[0:64, 12] = -0.0\n"
+        "    x[64:128, 12] = 1e-42\n"
+        "    x[128:192, 12] *= 1e-20\n"
+        "    x[:, 13] *= torch.logspace(-30, 8, 768, device='cuda')\n"
+        "    for tag, v in (('cm', x), ('rm', x.t().contiguous().t())):\n"
+        "        p = M.pack_frames(v)\n"
+        "        h = hashlib.sha256()\n"
+        "        for f in ('raw', 'norms', 'packed'):\n"
+        "            h.update(getattr(p, f).view(torch.uint8).cpu().numpy().tobytes())\n"
+        "        res[f'{tag}{n}_hash'] = np.frombuffer(h.digest(), dtype=np.uint8)\n"
+        "        res[f'{tag}{n}_err'] = p.err.cpu().numpy()\n"
+        "        res[f'{tag}{n}_stats'] = p.stats.cpu().numpy()\n"
+        "np.savez(sys.argv[1], **res)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
     for flag in ("1", "0"):
-        env = dict(os.environ, ALIVE_KNN_PACK_ASYNC=flag)
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
-                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+        path = str(tmp_path / f"pack{flag}.npz")
+        env = dict(os.environ, ALIVE_KNN_PACK_FAST=flag)
+        r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=env, cwd=root,
+                           timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(r.stdout.strip().splitlines()[-1])
-    assert outs[0] == outs[1]
+        outs.append(np.load(path))
+    fast, gen = outs
+    for key in gen.files:
+        if key.endswith("_hash"):
+            assert np.array_equal(fast[key], gen[key]), key
+        elif key.endswith("_err"):
+            np.testing.assert_allclose(fast[key], gen[key], rtol=1e-5, atol=0, err_msg=key)
+        else:
+            assert fast[key][1] == gen[key][1], key                      # count of non-finite rows
+            a, b = fast[key][:1].view(np.float32)[0], gen[key][:1].view(np.float32)[0]
+            assert abs(a - b) <= 1e-5 * b, key

@@ -130,8 +130,13 @@ def test_full_size_cfg2_against_oracle():
 
 def test_pack_kernel_layout_and_stats():
     g = torch.Generator(device="cuda").manual_seed(1)
-    for n in (1, 31, 300, 4097):
+    # (n, row_major): every kernel of K1 - per-frame, 8-frame, generic 32-frame (n % 4 != 0), the 16-byte
+    # cp.async channel-major kernel (ragged and full last CTA) and the register-resident row-major kernel
+    for n, row_major in ((1, False), (31, False), (300, False), (4097, False), (8201, False), (8204, False),
+                         (12_000 * 32, False), (600, True), (8204, True), (8201, True)):
         x = torch.randn(768, n, device="cuda", generator=g)
+        if row_major:
+            x = x.t().contiguous().t()
         p = M.pack_frames(x)
         assert torch.equal(p.raw, x.t().contiguous())
         nrm = torch.linalg.vector_norm(x.double(), dim=0).float()
@@ -492,6 +497,7 @@ def _clustered(T, N, nclus, noise, seed, dev="cuda"):
     (300, 60_000, 12, 0.2, "overflow"),       # ~5000 per cluster: more than a candidate buffer holds -> exhaustive scan
     (2500, 8_000, 8, 0.2, "no_slot"),         # more uncertified queries than slots; the rest skip the collect pass
     (400, 50_000, 50, 0.5, "mixed"),
+    (32, 600_000, 600, 0.2, "collect"),       # a realtime chunk (skinny first screen) against a clustered library
 ])
 def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect):
     """Tight clusters defeat the bf16 certificate; the second (collecting) tensor-core pass must give
