@@ -169,14 +169,10 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws + off[kOffFbCount]);
   void* exact_ws = ws + off[kOffExact];
 
-  for (int32_t b = 0; b < batch; ++b) {
-    const size_t r0 = static_cast<size_t>(b) * t;
-    // the first pack launch also zeroes the per-item fallback counters (no separate memset node)
-    rc = pack_impl(source + static_cast<int64_t>(b) * stride_b, t, d, stride_t, stride_d, q_raw + r0 * d,
-                   q_norm + r0, q_packed + r0 * d, q_err + r0, nullptr, b == 0 ? fb_count : nullptr, b == 0 ? items + 1 : 0,
-                   stream);
-    if (rc) return rc;
-  }
+  // all batch items in ONE pack launch, which also zeroes the per-item fallback counters (no separate memset node)
+  rc = pack_impl(source, rows, d, stride_t, stride_d, q_raw, q_norm, q_packed, q_err, nullptr, fb_count, items + 1, stream,
+                 t, stride_b);
+  if (rc) return rc;
   if (mode == 1) {
     if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
     // the search may start behind the (still running) query pack: see search_impl

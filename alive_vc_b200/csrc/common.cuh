@@ -34,9 +34,11 @@ void set_error(const char* fmt, ...);
 
 // internal variants of two ABI entry points used by the one-call pipeline (api.cu): the query pack also
 // zeroes the per-item fallback counters, so that alive_knn_finish needs no memset node of its own
+// (`item_frames`, `stride_b`: the n frames are n / item_frames batch items stride_b elements apart - the
+// [B, D, T] query batch of one call in ONE launch; 0 = a single item)
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
-              alive_stream_t stream);
+              alive_stream_t stream, int64_t item_frames = 0, int64_t stride_b = 0);
 // `after_query_pack`: the launch directly follows the query pack of the same call in `stream`; kernels
 // that can use it start early (programmatic dependent launch) and wait for the pack on the device
 int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,

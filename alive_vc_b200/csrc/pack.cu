@@ -52,11 +52,23 @@ __device__ __forceinline__ void cta_stats_publish(const CtaStats* cs, unsigned i
   }
 }
 
+// Query batches [B, D, T] arrive as B items of `item_frames` frames, `stride_b` elements apart (one
+// launch for all items; output rows b*item_frames + t).  A library is one item.
+struct FrameMap {
+  int item_frames;
+  long long stride_b, stride_n;
+};
+__device__ __forceinline__ const float* frame_ptr(const float* __restrict__ x, const FrameMap& m, long long f) {
+  const int fi = static_cast<int>(f);
+  const int b = fi / m.item_frames;
+  return x + b * m.stride_b + (fi - b * m.item_frames) * m.stride_n;
+}
+
 // kFrames = frames per CTA: 32 for libraries (128-byte coalesced reads of the channel-major
 // input), 8 for small query batches (more CTAs; 32-byte sectors are still fully used).
 template <int kFrames>
 __global__ void __launch_bounds__(kPackThreads)
-pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
+pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, long long stride_d,
             float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
             float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero,
             int async_stage) {
@@ -71,12 +83,12 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
   const long long f0 = static_cast<long long>(blockIdx.x) * kFrames;
   const int nf = static_cast<int>(min(static_cast<long long>(kFrames), n - f0));
 
-  if (stride_n == 1 || stride_d != 1) {
+  if (fm.stride_n == 1 || stride_d != 1) {
     // frames are the fast axis (or fully strided): lane -> (frame, channel sub-row)
     constexpr int kRowsPerWarp = 32 / kFrames;
     const int f = lane % kFrames, jsub = lane / kFrames;
     const bool ok = f < nf;
-    const float* src = x + (f0 + f) * stride_n;
+    const float* src = ok ? frame_ptr(x, fm, f0 + f) : x;
     if (async_stage) {
       // every 4-byte element of the CTA's tile is requested before anything waits (cp.async straight
       // into shared memory, no register staging): ~d*kFrames*4 B in flight per CTA instead of a
@@ -99,7 +111,7 @@ pack_kernel(const float* __restrict__ x, long long n, int d, long long stride_n,
     // already row-major frames: lane = channel
     const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
     for (int f = warp; f < kFrames; f += kPackThreads / 32) {
-      const float* src = x + (f0 + f) * stride_n;
+      const float* src = f < nf ? frame_ptr(x, fm, f0 + f) : x;
       if (async_stage && f < nf) {
         for (int j = lane; j < d; j += 32)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + 4u * (j * ld + f)), "l"(src + j)
@@ -182,23 +194,15 @@ __device__ __forceinline__ void finish_frame(long long row, float nrm, float e2,
   cta_stats_add(cta_stats, e, finite);
 }
 
-// Channel-major input (the reference's [D, N], stride_n == 1, 16-byte aligned rows): a CTA owns 32
+// Channel-major input (the reference's [D, N], stride_n == 1, 16-byte aligned rows): a tile = 32
 // frames; 16-byte cp.async copies (4 frames of one channel) fill a [d][36] tile, every warp then owns
 // 4 frames and reads them back as float4 (conflict-free: quarter-warp rows are 144 B apart).
+// Default: one CTA per tile, two CTAs per SM (one stages while the other finishes).  kDouble (opt-in
+// experiment, slower): persistent CTAs, one per SM, with TWO tiles in shared memory (d <= 768: 2 x 108 KB).
 constexpr int kCmLd = 36;
-__global__ void __launch_bounds__(kPackThreads)
-pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride_d, float* __restrict__ raw,
-               float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
-               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
-  extern __shared__ __align__(16) float tile[];   // [d][36]
-  __shared__ CtaStats cta_stats;
-  cta_stats_init(&cta_stats);
-  pdl_launch_dependents();
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long f0 = static_cast<long long>(blockIdx.x) * 32;
-  const int nf = static_cast<int>(min(32ll, n - f0));
+
+__device__ __forceinline__ void cm_stage(float* tile, const float* __restrict__ x, long long f0, int nf, int d,
+                                         long long stride_d) {
   const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
   if (nf == 32) {
     const int g4 = threadIdx.x & 7, jsub = threadIdx.x >> 3;          // 8 groups of 4 frames x 32 channel rows
@@ -212,7 +216,8 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
       dst += 4u * 32 * kCmLd;
     }
   } else {
-    // ragged last CTA: element-wise, missing frames read as zeros
+    // ragged last tile: element-wise, missing frames read as zeros
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool ok = lane < nf;
     const float* src = x + f0 + lane;
     for (int j = warp; j < d; j += kPackThreads / 32) {
@@ -224,14 +229,18 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
         tile[j * kCmLd + lane] = 0.f;
     }
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
-  // warp w: frames 4w..4w+3, lane: channels lane, lane+32, ...
+// warp w: frames 4w..4w+3 of the tile, lane: channels lane, lane+32, ...
+__device__ __forceinline__ void cm_compute(const float* tile, long long f0, int nf, int d, float* __restrict__ raw,
+                                           float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
+                                           float* __restrict__ err, CtaStats* cta_stats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fw = 4 * warp;
   const long long row0 = f0 + fw;
   const int nv = max(0, min(4, nf - fw));
-  if (nv > 0) {
+  if (nv == 0) return;
   const float4* t4 = reinterpret_cast<const float4*>(tile) + warp;     // tile[j*36 + 4w] = t4[j*9]
   double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
 #pragma unroll 4
@@ -285,10 +294,40 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e2[c] += __shfl_xor_sync(0xffffffffu, e2[c], o);
     finite[c] = __all_sync(0xffffffffu, finite[c]);
-    if (lane == 0 && c < nv) finish_frame(row0 + c, nrm[c], e2[c], finite[c], norms, err, &cta_stats);
+    if (lane == 0 && c < nv) finish_frame(row0 + c, nrm[c], e2[c], finite[c], norms, err, cta_stats);
   }
-  }  // nv > 0
-  __syncthreads();
+}
+
+template <bool kDouble>
+__global__ void __launch_bounds__(kPackThreads)
+pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride_d, float* __restrict__ raw,
+               float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
+               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+  extern __shared__ __align__(16) float tile[];   // [kDouble ? 2 : 1][d][36]
+  __shared__ CtaStats cta_stats;
+  cta_stats_init(&cta_stats);
+  pdl_launch_dependents();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
+  const long long n_tiles = (n + 31) / 32;
+  const int tile_floats = d * kCmLd;
+  long long t = blockIdx.x;
+  if (t < n_tiles) cm_stage(tile, x, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, stride_d);
+  for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    const float* cur = tile + (kDouble ? (it & 1) * tile_floats : 0);
+    const long long tn = t + gridDim.x;
+    if (kDouble && tn < n_tiles) {
+      cm_stage(tile + ((it + 1) & 1) * tile_floats, x, tn * 32, static_cast<int>(min(32ll, n - tn * 32)), d, stride_d);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    cm_compute(cur, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, raw, norms, packed, err, &cta_stats);
+    __syncthreads();                 // every warp is done with `cur` before it is refilled
+    if (!kDouble && tn < n_tiles)
+      cm_stage(tile, x, tn * 32, static_cast<int>(min(32ll, n - tn * 32)), d, stride_d);
+  }
   cta_stats_publish(&cta_stats, stats);
 }
 
@@ -296,7 +335,7 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
 // transpose - one warp per frame, the 3 KB row lives in registers between the norm and the division.
 constexpr int kRmMaxV = 12;                         // float4 per lane: d <= 1536
 __global__ void __launch_bounds__(kPackThreads)
-pack_rm_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, float* __restrict__ raw,
+pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, float* __restrict__ raw,
                float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
                unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
   pdl_launch_dependents();
@@ -309,7 +348,7 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, long long stride
   const long long row = static_cast<long long>(blockIdx.x) * (kPackThreads / 32) + warp;
   if (row < n) {
   const int d4 = d >> 2;
-  const float4* src = reinterpret_cast<const float4*>(x + row * stride_n);
+  const float4* src = reinterpret_cast<const float4*>(frame_ptr(x, fm, row));
   float4* dst_raw = reinterpret_cast<float4*>(raw + row * d);
   float4 v[kRmMaxV];
 #pragma unroll
@@ -371,7 +410,7 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, long long stride
 // Tiny batches (streaming chunks, T <= 512): one CTA per frame, three channels per thread, two
 // block reductions - one load round trip instead of a 768-row staging loop on a handful of CTAs.
 __global__ void __launch_bounds__(kPackThreads)
-pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long stride_n, long long stride_d,
+pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, long long stride_d,
                   float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
                   float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
   __shared__ double red[kPackThreads / 32];
@@ -382,12 +421,13 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long str
   const long long row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kPer = 6;                      // d <= 1536
+  const float* xrow = frame_ptr(x, fm, row);
   float v[kPer];
   double ss = 0.0;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     const int j = threadIdx.x + i * kPackThreads;
-    v[i] = (j < d) ? x[row * stride_n + j * stride_d] : 0.f;
+    v[i] = (j < d) ? xrow[j * stride_d] : 0.f;
     if (j < d) raw[row * d + j] = v[i];
     ss += static_cast<double>(v[i]) * static_cast<double>(v[i]);
   }
@@ -443,8 +483,17 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, long long str
 namespace alive {
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
-              alive_stream_t stream) {
+              alive_stream_t stream, int64_t item_frames, int64_t stride_b) {
   ALIVE_REQUIRE(x && raw && norms && packed, "alive_knn_pack: NULL argument");
+  if (item_frames <= 0 || item_frames >= n) {       // one item: the plain [n] frame sequence
+    item_frames = n > 0 ? n : 1;
+    stride_b = 0;
+  }
+  ALIVE_REQUIRE(n % item_frames == 0, "alive_knn_pack: n must be a multiple of the frames per item");
+  const bool one_item = item_frames == n || n == 0;
+  // items laid out with a uniform frame stride are one plain sequence
+  const bool uniform = one_item || stride_b == item_frames * stride_n;
+  const FrameMap fm{static_cast<int>(uniform ? (n > 0 ? n : 1) : item_frames), uniform ? 0 : stride_b, stride_n};
   ALIVE_REQUIRE(n >= 0 && n < (1ll << 31), "alive_knn_pack: n out of range (%lld)", static_cast<long long>(n));
   ALIVE_REQUIRE(d >= 2 && d % 2 == 0 && d <= 1536, "alive_knn_pack: d must be even and <= 1536 (got %d)", d);
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 3) == 0, "alive_knn_pack: packed must be 4-byte aligned");
@@ -456,7 +505,8 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
   if (!attr_done) {
     ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
     ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4));
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4));
+    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 768 * kCmLd * 4));
     attr_done = true;
   }
   __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
@@ -466,24 +516,40 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
   static const int fast = !(getenv("ALIVE_KNN_PACK_FAST") && atoi(getenv("ALIVE_KNN_PACK_FAST")) == 0);
   const bool x16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   const bool out16 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
-  if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && x16 && out16) {
+  if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && (uniform || stride_b % 4 == 0) && x16 && out16) {
     pack_rm_kernel<<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, as_stream(stream)>>>(
-        x, n, d, stride_n, raw, norms, pk, err, stats, zero_words, n_zero);
-  } else if (fast && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
+        x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero);
+  } else if (fast && uniform && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
     const size_t smem = static_cast<size_t>(d) * kCmLd * sizeof(float);
-    pack_cm_kernel<<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+    const long long n_tiles = (n + 31) / 32;
+    // ALIVE_KNN_PACK_DOUBLE=1: the persistent double-buffered variant (an experiment that lost: with one
+    // 8-warp CTA per SM the finishing pass cannot hide its arithmetic latency - 55 % of the HBM peak
+    // against 73-77 % for two independent CTAs per SM)
+    static const int dbl = getenv("ALIVE_KNN_PACK_DOUBLE") && atoi(getenv("ALIVE_KNN_PACK_DOUBLE")) == 1;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      ALIVE_CHECK_CUDA(cudaGetDevice(&dev));
+      ALIVE_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (dbl && d <= 768 && n_tiles >= 4ll * num_sms) {
+      pack_cm_kernel<true><<<static_cast<unsigned>(num_sms), kPackThreads, 2 * smem, as_stream(stream)>>>(
+          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+    } else {
+      pack_cm_kernel<false><<<static_cast<unsigned>(n_tiles), kPackThreads, smem, as_stream(stream)>>>(
+          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+    }
   } else if (n <= 512) {
-    pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, stride_n, stride_d, raw,
+    pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, fm, stride_d, raw,
                                                                                        norms, pk, err, stats, zero_words, n_zero);
   } else if (n <= 8192) {
     const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
     pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
+        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
   } else {
     const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
     pack_kernel<32><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, stride_n, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
+        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
   }
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -493,5 +559,5 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
 extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
                               float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
                               alive_stream_t stream) {
-  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream);
+  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream, 0, 0);
 }

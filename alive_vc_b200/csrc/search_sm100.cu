@@ -1070,7 +1070,15 @@ extern "C" int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32
     return 0;
   }
   const int ctas = variant;
-  const int slots = num_sms / ctas;   // units that run concurrently
+  int slots = num_sms / ctas;   // units that run concurrently
+  {
+    // The query groups of one library segment should run in the SAME wave (they share the segment's
+    // tiles through L2): with a few groups per item, give up the slots that would make segments straddle
+    // waves (at most 1/16 of the machine).  ALIVE_KNN_GRID_ALIGN=0/1 (A/B runs).
+    static const int align = getenv("ALIVE_KNN_GRID_ALIGN") ? atoi(getenv("ALIVE_KNN_GRID_ALIGN")) : 0;
+    const int mu = (t + kBlockM * ctas - 1) / (kBlockM * ctas);
+    if (align && items > 1 && mu > 1 && mu <= slots && (slots % mu) * 16 <= slots) slots -= slots % mu;
+  }
   plan->t = t;
   plan->n = n;
   plan->d = d;

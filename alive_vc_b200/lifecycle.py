@@ -229,10 +229,10 @@ class HostStreamingMatcher:
         self.out_host = torch.zeros((batch, T, lib.d), dtype=torch.float32).pin_memory()
         self.stream = torch.cuda.Stream(device=dev)
         self.done = torch.cuda.Event()
-        self.launches_per_call = batch + 4
         with torch.cuda.stream(self.stream):
             self._enqueue()                            # warm-up outside capture
         self.stream.synchronize()
+        self.launches_per_call = M.last_info.launches  # kernels per graph replay
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             self._enqueue()

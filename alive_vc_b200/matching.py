@@ -462,13 +462,13 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
                            ev0.cuda_event if ev0 is not None else None,
                            ev1.cuda_event if ev1 is not None else None, _stream_ptr())
     _cabi.check(rc, "alive_knn_match")
-    _count(B + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
+    _count(1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
                            fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
                            exact_count=workspace[off[9] + 4 * lib.items:off[9] + 4 * lib.items + 4].view(torch.int32),
                            collect=m == 1 and off[7] > off[6],
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
-                           launches=B + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
+                           launches=1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info._workspace = workspace
     return (out if want_out else None), top_idx, top_score
 
@@ -509,6 +509,7 @@ class StreamingMatcher:
         self.workspace = torch.empty((off[11],), dtype=torch.uint8, device=dev)
         self.graph = None
         self._run()                                   # eager warm-up (one-time attribute setup)
+        self._launches = last_info.launches           # kernels per replay = kernels of one eager call
         torch.cuda.synchronize(dev)
         if use_graph:
             side = torch.cuda.Stream(device=dev)
@@ -529,7 +530,7 @@ class StreamingMatcher:
         self.src.copy_(source, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
-            _count(self.src.shape[0] + 4)
+            _count(self._launches)
         else:
             self._run()
         return self.out.transpose(1, 2)

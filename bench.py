@@ -508,11 +508,24 @@ def gpu_arm(args):
             torch.cuda.synchronize()
             p_ms = pe0.elapsed_time(pe1) / reps
             p_bytes = pn * (D * 10 + 8)
-            pack_roof = {"bound": "hbm", "kernel": "pack_kernel<32>", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
+            # the same frames as a row-major producer would hand them over (pack_rows): pack_rm_kernel
+            px_rows = px.t().contiguous()
+            for _ in range(2):
+                M.pack_into(pdst, 0, px_rows.t())
+            pe0.record()
+            for _ in range(reps):
+                M.pack_into(pdst, 0, px_rows.t())
+            pe1.record()
+            torch.cuda.synchronize()
+            p_ms_rows = pe0.elapsed_time(pe1) / reps
+            pack_roof = {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": p_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "avg_kernel_ms": p_ms, "bytes_per_frame": D * 10 + 8, "frames": pn,
-                         "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse)"}
-            del px, pdst
+                         "row_major": {"kernel": "pack_rm_kernel", "achieved": p_bytes / (p_ms_rows * 1e-3) / 1e9,
+                                       "frac": p_bytes / (p_ms_rows * 1e-3) / 1e9 / peaks["hbm_gbs"], "avg_kernel_ms": p_ms_rows},
+                         "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse); "
+                                 "row_major = the same frames as [250k, 768] rows"}
+            del px, pdst, px_rows
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = run_cpu_arm(args.workload, 3, 1)

@@ -178,6 +178,15 @@ def test_match_rows_batched_strided_and_raw_library():
                                     l_rows.t().contiguous()[None].expand(B, D, N), 4, 0.0, return_indices=True)
     assert torch.equal(idx, w_idx)
     assert torch.equal(out, w_out.transpose(1, 2))
+    # batch items that are NOT uniformly strided (a [B, 2T, D] buffer, first T frames of each item), enough
+    # frames for the register-resident row-major pack kernel: one pack launch with a per-item frame map
+    T2 = 200
+    tall = _cuda(rng.standard_normal((B, 2 * T2, D), dtype=np.float32))
+    fr2 = tall[:, :T2]
+    out2, idx2 = match_rows(fr2, l_rows, 4, 0.0, return_indices=True)
+    w2, wi2 = A.match_features(fr2.transpose(1, 2).contiguous(), l_rows.t().contiguous()[None].expand(B, D, N), 4, 0.0,
+                               return_indices=True)
+    assert torch.equal(idx2, wi2) and torch.equal(out2, w2.transpose(1, 2))
     # empty chunk and dtype passthrough
     e = match_rows(frames[:, :0], l_rows)
     assert tuple(e.shape) == (B, 0, D)

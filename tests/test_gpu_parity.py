@@ -440,7 +440,8 @@ def test_batched_libraries_equal_per_item_matches():
     train_decoder.py:134-135) == B separate single-library matches, bit for bit; also vs the oracle."""
     rng = np.random.default_rng(91)
     for (B, T, N, k, alpha, mode) in [(3, 130, 1500, 4, 0.0, "auto"), (5, 7, 300, 2, 0.25, "auto"),
-                                      (2, 40, 900, 16, 0.0, "auto"), (4, 300, 5000, 4, 0.0, "screen")]:
+                                      (2, 40, 900, 16, 0.0, "auto"), (4, 300, 5000, 4, 0.0, "screen"),
+                                      (3, 3000, 2000, 4, 0.0, "screen")]:      # 9000 query frames: 32-frame pack CTAs across items
         src = rng.standard_normal((B, 768, T), dtype=np.float32)
         ref = rng.standard_normal((B, 768, N), dtype=np.float32)
         if B == 3:
@@ -448,7 +449,7 @@ def test_batched_libraries_equal_per_item_matches():
             src[1, :, :10] = ref[1, :, 60:70]                      # ... queried exactly: exact ties
         s, r = _cuda(src), _cuda(ref)
         out, idx = A.match_features(s, r, k, alpha, return_indices=True, mode=mode)
-        assert M.last_info.launches == B + (4 if M.last_info.mode == "screen" else 2)      # one pipeline
+        assert M.last_info.launches == 1 + (4 if M.last_info.mode == "screen" else 2)      # one pipeline, one query pack
         for b in range(B):
             o1, i1 = A.match_features(s[b:b + 1], r[b:b + 1], k, alpha, return_indices=True, mode=mode)
             assert torch.equal(idx[b:b + 1], i1) and torch.equal(out[b:b + 1], o1)
