@@ -57,6 +57,30 @@ def main():
     assert M.last_info.collect and M.last_info.fallback_queries() > 0
     torch.cuda.synchronize()
     print("ok collect pass", M.last_info.fallback_queries(), M.last_info.exact_scan_queries(), flush=True)
+    # every K1 variant: generic 8/32-frame tiles (n % 4 != 0), the 16-byte cp.async channel-major kernel with a
+    # ragged last tile, the register-resident row-major kernel with a ragged last CTA, and one launch for a
+    # batch of query items (uniform and non-uniform item strides)
+    from alive_vc_b200.lifecycle import match_rows
+    for n, row_major in ((8201, False), (8300, False), (9001, False), (8203, True), (700, True)):
+        x = torch.randn(768, n, device="cuda", generator=g)
+        if row_major:
+            x = x.t().contiguous().t()
+        p = M.pack_frames(x)
+        torch.cuda.synchronize()
+        assert torch.equal(p.raw, x.t().contiguous())
+        assert torch.equal(p.packed, (x / p.norms[None, :]).t().bfloat16())
+    tall = torch.randn(3, 400, 768, device="cuda", generator=g)
+    lrows = torch.randn(900, 768, device="cuda", generator=g)
+    o1 = match_rows(tall[:, :200], lrows)                     # non-uniform item stride, 600 frames: pack_rm_kernel
+    o2 = match_rows(tall[:, :200].contiguous(), lrows)        # uniform
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    srcb = torch.randn(3, 768, 3000, device="cuda", generator=g)   # 9000 channel-major query frames in one launch
+    ob, ib = A.match_features(srcb, lrows.t().contiguous()[None].expand(3, 768, 900), 4, 0.0, return_indices=True)
+    o0, i0 = A.match_features(srcb[1:2], lrows.t().contiguous()[None], 4, 0.0, return_indices=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ib[1:2], i0) and torch.equal(ob[1:2], o0)
+    print("ok pack variants", flush=True)
     vl = A.VoiceLibrary(num_tokens=300).cuda()
     s = torch.randn(2, 768, 11, device="cuda", requires_grad=True)
     vl.match(s, alpha=0.5).sum().backward()
