@@ -305,6 +305,33 @@ def test_streaming_matcher_graph_replay_equals_functional_api():
     assert torch.equal(sm2(chunk), A.match_features(chunk, ref, 4, 0.5))
 
 
+@pytest.mark.parametrize("T,N", [(24, 3000), (32, 600_000), (300, 70_000)])
+def test_streaming_matcher_fallback_inside_the_graph(T, N):
+    """The fallback chain of a captured pipeline (collect pass / exhaustive scan): clean chunks and chunks with
+    uncertifiable queries (a cluster of 400 near-identical library frames - more survivors than r_max) alternate
+    on the SAME graph and equal the eager path; the device-side fallback counter is reset by every replay."""
+    g = torch.Generator(device="cuda").manual_seed(33)
+    ref = torch.randn(1, 768, N, device="cuda", generator=g)
+    centre = torch.randn(768, 1, device="cuda", generator=g)
+    ref[0, :, 1000:1400] = centre + 0.01 * torch.randn(768, 400, device="cuda", generator=g)
+    lib = A.pack_library(ref)
+    sm = A.StreamingMatcher(lib, T=T, k=4, alpha=0.0)
+    assert sm.graph is not None
+    info = M.last_info                                         # views of the matcher's own workspace counters
+    clean = torch.randn(1, 768, T, device="cuda", generator=g)
+    dirty = clean.clone()
+    dirty[0, :, :10] = centre + 0.01 * torch.randn(768, 10, device="cuda", generator=g)   # 400 frames inside the band
+    for i, (chunk, expect_fb) in enumerate([(clean, False), (dirty, True), (clean, False), (dirty, True), (dirty, True),
+                                            (clean, False)]):
+        out = sm(chunk).clone()
+        idx = sm.top_idx.clone()
+        fb = info.fallback_queries()
+        assert (fb > 0) == expect_fb, (i, fb)
+        want, widx = A.match_features(chunk, ref, 4, 0.0, return_indices=True)
+        assert torch.equal(idx, widx), i
+        assert torch.equal(out, want), i
+
+
 def test_one_call_pipeline_equals_step_by_step_kernels():
     """alive_knn_match == pack + search + prune + rescore + exact + gather called one by one"""
     g = torch.Generator(device="cuda").manual_seed(22)
