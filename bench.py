@@ -484,10 +484,29 @@ def gpu_arm(args):
                 torch.cuda.synchronize()
                 g_ms = ge0.elapsed_time(ge1) / reps
                 g_bytes = rows * (K * D * 4 + D * 4 + D * 4)
+                # what the memory system gives ANY kernel for this access pattern: torch's own row gather of
+                # the same T*k random 3 KB rows (read + write T*k rows) - the practical ceiling beside the
+                # streaming-copy peak
+                flat_idx = g_idx.reshape(-1)
+                sel_out = torch.empty((flat_idx.numel(), D), dtype=torch.float32, device=dev)
+                for _ in range(3):
+                    torch.index_select(lib.raw, 0, flat_idx, out=sel_out)
+                torch.cuda.synchronize()
+                ge0.record()
+                for _ in range(reps):
+                    torch.index_select(lib.raw, 0, flat_idx, out=sel_out)
+                ge1.record()
+                torch.cuda.synchronize()
+                sel_ms = ge0.elapsed_time(ge1) / reps
+                sel_gbs = 2.0 * flat_idx.numel() * D * 4 / (sel_ms * 1e-3) / 1e9
+                del sel_out
                 gather_roof = {"bound": "hbm", "kernel": "gather_mean_kernel", "achieved": g_bytes / (g_ms * 1e-3) / 1e9,
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                "avg_kernel_ms": g_ms, "bytes_per_query_frame": g_bytes // rows,
-                               "note": "standalone K4 on this step's indices; random 3 KB rows of the raw library"}
+                               "torch_index_select_gbs": sel_gbs,
+                               "note": "standalone K4 on this step's indices; random 3 KB rows of the raw library; "
+                                       "torch_index_select_gbs = torch's row gather of the same rows (read + write), "
+                                       "the practical ceiling of this access pattern"}
         # K1 alone (once per library, generate_voice_library.py / load time): the pack kernel on a fresh
         # channel-major [D, n] chunk far larger than L2.  Algorithmic bytes per frame: D*(4 read + 4 raw
         # + 2 packed) + 8 (norm, err) = 7,688 B.
