@@ -537,11 +537,24 @@ def gpu_arm(args):
             pe1.record()
             torch.cuda.synchronize()
             p_ms_rows = pe0.elapsed_time(pe1) / reps
+            # torch's own transposing copy of the same chunk ([768, n] -> [n, 768], read + write 4 B per element):
+            # what a library kernel gets out of the channel-major access pattern
+            t_out = torch.empty((pn, D), dtype=torch.float32, device=dev)
+            for _ in range(2):
+                t_out.copy_(px.t())
+            pe0.record()
+            for _ in range(reps):
+                t_out.copy_(px.t())
+            pe1.record()
+            torch.cuda.synchronize()
+            t_gbs = 2.0 * pn * D * 4 / (pe0.elapsed_time(pe1) / reps * 1e-3) / 1e9
+            del t_out
             pack_roof = {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": p_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "avg_kernel_ms": p_ms, "bytes_per_frame": D * 10 + 8, "frames": pn,
                          "row_major": {"kernel": "pack_rm_kernel", "achieved": p_bytes / (p_ms_rows * 1e-3) / 1e9,
                                        "frac": p_bytes / (p_ms_rows * 1e-3) / 1e9 / peaks["hbm_gbs"], "avg_kernel_ms": p_ms_rows},
+                         "torch_transpose_copy_gbs": t_gbs,
                          "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse); "
                                  "row_major = the same frames as [250k, 768] rows"}
             del px, pdst, px_rows
