@@ -9,12 +9,15 @@
 //        norms  [n]   f32  sqrt(sum x^2), sum in fp64
 //        packed [n,d] bf16 row-major x/|x| (IEEE division, then round-to-nearest-even)
 //        err    [n]   f32  || bf16(x/|x|) - x/|x| ||_2   (screening error bound input)
-//        stats  [0] atomicMax of err bits, [1] count of non-finite normalised rows
+//        stats  [0] max of the err bits, [1] count of non-finite normalised rows
 //
-// HBM-bound: algorithmic bytes per frame = d*(4 read + 4 raw + 2 packed) = 7,680 B at d=768.
-// A CTA owns 32 consecutive frames: the channel-major input is read as 128-byte rows
-// (32 frames x 4 B, coalesced), staged transposed in shared memory, and written back as
-// full 3 KB / 1.5 KB frame rows.
+// HBM-bound: algorithmic bytes per frame = d*(4 read + 4 raw + 2 packed) + 8 = 7,688 B at d=768.
+// Kernels (dispatch in pack_impl at the end of this file; DESIGN.md §4 K1 has the measurements):
+//   pack_cm_kernel     channel-major libraries: 32-frame [d][36] tile filled by 16-byte cp.async
+//   pack_rm_kernel     row-major frames: one warp per frame, the row stays in registers
+//   pack_kernel<8/32>  any strides / alignment, batches of query items (FrameMap)
+//   pack_frame_kernel  <= 512 frames (a streaming chunk): one CTA per frame
+// All of them compute the same bits: fp64 norm, correctly rounded x/|x|, RN-even bf16.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 

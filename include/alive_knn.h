@@ -79,7 +79,10 @@ int alive_knn_abi_version(void);
  *   err    [n]   float32 || bf16(x/|x|) - x/|x| ||_2 per row (may be NULL)
  *   stats  [2]   see above; must be zeroed by the caller before the FIRST pack
  *                of a library (several packs may accumulate into one stats).
- * Also used per call for the query frames (common.py:100,102,104 lhs). */
+ * Also used per call for the query frames (common.py:100,102,104 lhs).
+ * Any strides are accepted; the two layouts that matter have kernels of their own: the
+ * reference's channel-major [D,N] (stride_n == 1) and a producer's row-major [N,D]
+ * (stride_d == 1), both with 16-byte aligned rows.  Every variant writes the same bits. */
 int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
                    float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
                    alive_stream_t stream);
