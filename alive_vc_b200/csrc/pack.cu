@@ -175,14 +175,19 @@ pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, 
 // ---------------------------------------------------------------------------------------------
 
 // x / nrm, correctly rounded, for 2^-40 <= nrm <= 2^40 and r = __frcp_rn(nrm) (correctly rounded
-// reciprocal): quotient estimate + two exact-remainder corrections (Markstein); a quotient too small
-// for the remainders to be exact (or a signed zero) takes the full IEEE division.
+// reciprocal): quotient estimate + ONE exact-remainder correction (Markstein: with a correctly rounded
+// reciprocal and a faithful estimate, q + r*(x - q*nrm) rounds to the correctly rounded quotient;
+// checked in exact rational arithmetic on adversarial mantissas and bit for bit against __fdiv_rn by
+// test_fast_pack_kernels_equal_the_generic_kernel); a quotient too small for the remainder to be exact
+// (or a signed zero) takes the full IEEE division.
 __device__ __forceinline__ float div_by_norm(float x, float nrm, float r) {
   float q = __fmul_rn(x, r);
   float e = __fmaf_rn(-q, nrm, x);
   q = __fmaf_rn(e, r, q);
+#ifdef ALIVE_PACK_TWO_CORRECTIONS    // not needed (see above); costs 2-3 % of the pack rate
   e = __fmaf_rn(-q, nrm, x);
   q = __fmaf_rn(e, r, q);
+#endif
   return (fabsf(q) >= 0x1p-40f) ? q : __fdiv_rn(x, nrm);
 }
 __device__ __forceinline__ bool norm_is_tame(float nrm) { return nrm >= 0x1p-40f && nrm <= 0x1p40f; }
