@@ -11,8 +11,6 @@ All device work goes through the C ABI (include/alive_knn.h); torch is used for 
 """
 from __future__ import annotations
 
-from typing import Sequence
-
 import torch
 
 from . import matching as M

@@ -20,8 +20,6 @@ CUDA-only and has no fallback).
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 import torch.distributed as dist
 

@@ -2,7 +2,6 @@
 fallback counts and timings for clustered / low-rank libraries, and the exact-scan speed."""
 import os
 import sys
-import time
 
 import torch
 

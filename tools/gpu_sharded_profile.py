@@ -8,7 +8,6 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from alive_vc_b200 import matching as M                      # noqa: E402
 from alive_vc_b200.sharded import CudaShardBackend, ShardedLibrary, shard_bounds  # noqa: E402
 import bench                                                   # noqa: E402
 
