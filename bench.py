@@ -15,6 +15,10 @@ A "step" = one pass of the hot path over one batch of T synthetic query frames:
           H2D -> match -> D2H of the matched features, every step
   roofline      : the fused tcgen05 similarity+top-list kernel (alive_knn_search), its own
                   CUDA-event duration inside the timed region vs MEASURED_PEAKS.json
+  roofline_gather : the standalone gather-mean kernel (K4) on the step's own indices vs the HBM peak, with
+                  torch's index_select of the same rows beside it (the practical ceiling of random 3 KB rows)
+  roofline_pack : the library pack (K1) alone on a fresh 250k-frame chunk, channel-major (the reference's
+                  layout) and row-major, vs the HBM peak; torch's transposing copy of the chunk beside it
   cpu_baseline  : the oracle's torch port of the reference (oracle/knn_oracle.py
                   match_features_torch = module/common.py:96-109 on CPU) on the box's host
                   cores, bounded sample, rank 0 at N=1 only
