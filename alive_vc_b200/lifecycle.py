@@ -206,6 +206,8 @@ def match_rows(frames: torch.Tensor, lib, k: int = 4, alpha: float = 0.0, *, ret
         out = out.to(frames.dtype)
     if squeeze:
         out, idx = out[0], idx[0]
+    if torch.is_grad_enabled() and frames.requires_grad:
+        out = M._BlendGrad.apply(frames, out, float(alpha))      # d(out)/d(frames) = alpha, as in match_features
     return (out, idx) if return_indices else out
 
 

@@ -187,6 +187,10 @@ def test_match_rows_batched_strided_and_raw_library():
     w2, wi2 = A.match_features(fr2.transpose(1, 2).contiguous(), l_rows.t().contiguous()[None].expand(B, D, N), 4, 0.0,
                                return_indices=True)
     assert torch.equal(idx2, wi2) and torch.equal(out2, w2.transpose(1, 2))
+    # autograd: the frames receive alpha * grad, like `source` of match_features (common.py:109)
+    leaf = frames.clone().requires_grad_(True)
+    match_rows(leaf, l_rows, 4, 0.25).sum().backward()
+    assert torch.equal(leaf.grad, torch.full_like(leaf, 0.25))
     # empty chunk and dtype passthrough
     e = match_rows(frames[:, :0], l_rows)
     assert tuple(e.shape) == (B, 0, D)
