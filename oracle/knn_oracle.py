@@ -19,7 +19,10 @@ outputs of the unmodified reference function imported in the build container
 (`oracle/gen_golden.py` -> `tests/golden/*.npz`; `tests/test_oracle.py`
 replays them without the reference being present).
 
-Two restatements are provided:
+A third, independent restatement in plain C lives in `oracle/knn_oracle.c` (loader: `oracle/c_oracle.py`);
+`tests/test_oracle.py` pins it to the same golden vectors and to this module.
+
+Two restatements are provided here:
 
 * `match_features_np`  - numpy, float32 end to end, used by the parity tests.
   It also returns the top-k indices and similarities, which the reference
