@@ -23,11 +23,19 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", "-o", LIB, SRC, "-lm"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    return LIB
+    tmp = LIB + ".tmp"
+    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", "-o", tmp, SRC, "-lm"]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        err = res.stdout + res.stderr if res.returncode != 0 else None
+    except OSError as e:                       # no gcc on this box
+        err = str(e)
+    if err is None:
+        os.replace(tmp, LIB)
+        return LIB
+    if os.path.exists(LIB):                    # a prebuilt library travelled with the snapshot: use it
+        return LIB
+    raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + err)
 
 
 def _load():
