@@ -28,7 +28,7 @@ EXPORTS = [
     "alive_knn_exact", "alive_knn_merge", "alive_knn_gather_mean", "alive_knn_gather_rows",
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
     "alive_knn_finish", "alive_knn_gather_mean_peers", "alive_knn_ipc_export", "alive_knn_ipc_open",
-    "alive_knn_ipc_close",
+    "alive_knn_ipc_close", "alive_knn_merge_records", "alive_knn_merge_gather",
 ]
 
 
@@ -61,29 +61,58 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+OBJ_DIR = os.path.join(CSRC, "_obj")
+_HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(_ROOT, "include", "alive_knn.h")]
+
+
+def _obj_path(src: str) -> str:
+    return os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
-                                                       os.path.join(_ROOT, "include", "alive_knn.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def needs_build() -> bool:
+    return _stale(LIB_PATH, [os.path.join(CSRC, s) for s in SOURCES] + _HEADERS)
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libalive_knn.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into libalive_knn.so for sm_100a (nvcc cross-compiles without a GPU).
+    Every source is compiled to its own object (in parallel, only when it or a header changed), then linked."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH,
-           *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = _obj_path(src)
+        path = os.path.join(CSRC, src)
+        if not force and not _stale(obj, [path] + _HEADERS):
+            return ""
+        cmd = [nvcc_path(), *compile_flags, "-I", os.path.join(_ROOT, "include"), "-c", "-o", obj, path]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        logs = list(pool.map(compile_one, SOURCES))
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *[_obj_path(s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 
@@ -124,7 +153,7 @@ def _declare(lib):
     lib.alive_knn_merge.restype = ctypes.c_int
     lib.alive_knn_merge.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]
     lib.alive_knn_gather_mean.restype = ctypes.c_int
-    lib.alive_knn_gather_mean.argtypes = [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _f32, _vp, _vp]
+    lib.alive_knn_gather_mean.argtypes = [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp]
     lib.alive_knn_gather_rows.restype = ctypes.c_int
     lib.alive_knn_gather_rows.argtypes = [_vp, _i64, _i32, _i64, _vp, _i32, _i32, _vp, _vp]
     lib.alive_knn_mean_blend.restype = ctypes.c_int
@@ -132,7 +161,12 @@ def _declare(lib):
     lib.alive_knn_scatter_grad.restype = ctypes.c_int
     lib.alive_knn_scatter_grad.argtypes = [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _i64, _vp]
     lib.alive_knn_gather_mean_peers.restype = ctypes.c_int
-    lib.alive_knn_gather_mean_peers.argtypes = [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _f32, _vp, _vp]
+    lib.alive_knn_gather_mean_peers.argtypes = [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp]
+    lib.alive_knn_merge_records.restype = ctypes.c_int
+    lib.alive_knn_merge_records.argtypes = [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]
+    lib.alive_knn_merge_gather.restype = ctypes.c_int
+    lib.alive_knn_merge_gather.argtypes = [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _f32,
+                                           _vp, _vp, _vp, _vp]
     lib.alive_knn_ipc_export.restype = ctypes.c_int
     lib.alive_knn_ipc_export.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_i64)]
     lib.alive_knn_ipc_open.restype = ctypes.c_int
@@ -160,7 +194,7 @@ def load():
             # ALIVE_KNN_LIB: an instrumented build of the same sources (tests/gpu_tools/finish_phases.py)
             lib = ctypes.CDLL(os.environ.get("ALIVE_KNN_LIB") or LIB_PATH)
             _declare(lib)
-            if lib.alive_knn_abi_version() != 3:
+            if lib.alive_knn_abi_version() != 4:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")
             _lib = lib
     return _lib

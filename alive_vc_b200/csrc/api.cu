@@ -125,6 +125,7 @@ extern "C" int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_
   ALIVE_REQUIRE(offsets12 != nullptr, "alive_knn_match_layout: offsets is NULL");
   ALIVE_REQUIRE(rows >= 1 && n >= 1 && k >= 1 && k <= ALIVE_KNN_MAX_K, "alive_knn_match_layout: bad sizes");
   ALIVE_REQUIRE(items >= 1 && rows % items == 0, "alive_knn_match_layout: rows must be a multiple of items");
+  ALIVE_REQUIRE(d >= 4 && d % 4 == 0 && d <= 1536, "alive_knn_match: d must be a multiple of 4, <= 1536 (got %d)", d);
   alive_knn_plan_t plan;
   return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets12, nullptr);
 }
@@ -143,6 +144,8 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   const int32_t rows = batch * t;
   const int32_t d = lib->d;
   const int32_t items = lib->items < 1 ? 1 : lib->items;
+  // checked before anything is enqueued (the exact scan at the end of the chain has the same limit)
+  ALIVE_REQUIRE(d >= 4 && d % 4 == 0 && d <= 1536, "alive_knn_match: d must be a multiple of 4, <= 1536 (got %d)", d);
   ALIVE_REQUIRE(items == 1 || items == batch,
                 "alive_knn_match: a library of %d items needs a query batch of the same size (got %d)", items, batch);
   ALIVE_REQUIRE(items == 1 || lib->row_base == 0, "alive_knn_match: batched items cannot be row-sharded");

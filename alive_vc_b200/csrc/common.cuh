@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <utility>
 
 #include "alive_knn.h"
@@ -90,6 +91,24 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 }
 
 static inline cudaStream_t as_stream(alive_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// One-time setup that is PER DEVICE (cudaFuncSetAttribute, device allocations): one process may drive
+// several GPUs, from several threads.  Bit i of `done` = the setup has run on device i; two threads racing
+// on the same device both run `f` (the setups are idempotent).  Devices >= 64 run it on every call.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <class F> int run(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      set_error("cudaGetDevice failed");
+      return -2;
+    }
+    if (dev >= 0 && dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
+    const int rc = f();
+    if (rc == 0 && dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+    return rc;
+  }
+};
 
 // Ordering used everywhere a top-k is taken (mirrors torch.topk: NaN ranks above
 // everything; ties resolve to the lowest frame index).

@@ -509,13 +509,16 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
     if (n_zero > 0) ALIVE_CHECK_CUDA(cudaMemsetAsync(zero_words, 0, sizeof(int32_t) * n_zero, as_stream(stream)));
     return 0;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4));
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4));
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 768 * kCmLd * 4));
-    attr_done = true;
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4));
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4));
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 768 * kCmLd * 4));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
   // ALIVE_KNN_PACK_ASYNC=0: register-staged loads (the first version; kept for A/B runs)
@@ -534,8 +537,8 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
     // 8-warp CTA per SM the finishing pass cannot hide its arithmetic latency - 55 % of the HBM peak
     // against 73-77 % for two independent CTAs per SM)
     static const int dbl = getenv("ALIVE_KNN_PACK_DOUBLE") && atoi(getenv("ALIVE_KNN_PACK_DOUBLE")) == 1;
-    static int num_sms = 0;
-    if (num_sms == 0) {
+    int num_sms = 148;
+    if (dbl) {      // (per device: only the experiment needs it)
       int dev = 0;
       ALIVE_CHECK_CUDA(cudaGetDevice(&dev));
       ALIVE_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -30,6 +30,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace alive {
@@ -862,14 +865,23 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t d, uint
   return 0;
 }
 
-// pacing counters: a small ring of device words, one per in-flight launch
+// pacing counters: a small ring of device words per DEVICE, one word per in-flight launch
 unsigned int* pacing_slot(cudaStream_t stream) {
-  static unsigned int* base = nullptr;
-  static unsigned int seq = 0;
-  if (!base) {
-    if (cudaMalloc(&base, 64 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  static std::mutex mu;
+  static unsigned int* base[64] = {};
+  static std::atomic<unsigned int> seq{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  unsigned int* b;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!base[dev] && cudaMalloc(&base[dev], 64 * sizeof(unsigned int)) != cudaSuccess) {
+      base[dev] = nullptr;
+      return nullptr;
+    }
+    b = base[dev];
   }
-  unsigned int* slot = base + (seq++ % 64);
+  unsigned int* slot = b + (seq.fetch_add(1, std::memory_order_relaxed) % 64);
   if (cudaMemsetAsync(slot, 0, sizeof(unsigned int), stream) != cudaSuccess) return nullptr;
   return slot;
 }
@@ -948,11 +960,14 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
     }
   }
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(knn_search_kernel<kCtas, kCollect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(C::kSmemBytes))));
-    attr_done = true;
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(knn_search_kernel<kCtas, kCollect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(C::kSmemBytes))));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
@@ -1007,11 +1022,14 @@ int launch_skinny(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   }
   p.stages = stages;
   const size_t smem = fixed + static_cast<size_t>(stages) * kABytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(knn_search_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kSkinnySmemMax)));
-    attr_done = true;
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(knn_search_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(kSkinnySmemMax)));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
@@ -1039,7 +1057,9 @@ extern "C" int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32
   ALIVE_REQUIRE(n >= 1 && n < (1ll << 31) - 512, "alive_knn_plan: n out of range (%lld)", static_cast<long long>(n));
   ALIVE_REQUIRE(static_cast<long long>(items) * n < (1ll << 31) - 512 && static_cast<long long>(items) * t < (1ll << 31) - 512,
                 "alive_knn_plan: items * n and items * t must stay below 2^31");
-  ALIVE_REQUIRE(d >= 64 && d % 64 == 0 && d <= 8192, "alive_knn_plan: d must be a multiple of 64 (got %d)", d);
+  // d <= 1536: the exact scan behind every screened call (alive_knn_exact) and the certificate's accumulation
+  // slack (select.cu kAccumSlack) are both sized for at most 1536 channels - refuse here, before anything is launched
+  ALIVE_REQUIRE(d >= 64 && d % 64 == 0 && d <= 1536, "alive_knn_plan: d must be a multiple of 64, <= 1536 (got %d)", d);
   ALIVE_REQUIRE(num_sms >= 2, "alive_knn_plan: num_sms must be >= 2");
   // default: the CTA-pair kernel (cta_group::2) once there is more than one 128-query tile - it
   // moves a third less operand data per flop and is ~10% faster under the power cap; a single

@@ -225,10 +225,12 @@ __device__ __forceinline__ float blend_exact(float acc, float kf, float a1, floa
   return __fadd_rn(__fmul_rn(__fdiv_rn(acc, kf), a1), __fmul_rn(q, a0));
 }
 
-// out[j..j+3] = mean of the k raw rows (sequential fp32 sum, true division) blended with q
+// out[j..j+3] = mean of the k raw rows (sequential fp32 sum, true division) blended with q.  The query row is
+// only fetched when it can change the result (`need_q`: alpha != 0 or a non-finite query; or a mean of exactly
+// zero, where the sign of 0 * q matters) - see gather.cu.
 __device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_raw, long long n, int d,
                                                 const long long* idx, long long idx_base, int k,
-                                                const float* __restrict__ q_row, float a1, float a0,
+                                                const float* __restrict__ q_row, bool need_q, float a1, float a0,
                                                 float* __restrict__ out_row, int tid, int nthreads) {
   for (int j = tid * 4; j < d; j += nthreads * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -252,11 +254,15 @@ __device__ __forceinline__ void gather_mean_row(const float* __restrict__ lib_ra
         }
       }
     }
-    const float4 qv = *reinterpret_cast<const float4*>(q_row + j);
     const float kf = static_cast<float>(k);
-    *reinterpret_cast<float4*>(out_row + j) =
-        make_float4(blend_exact(acc.x, kf, a1, qv.x, a0), blend_exact(acc.y, kf, a1, qv.y, a0),
-                    blend_exact(acc.z, kf, a1, qv.z, a0), blend_exact(acc.w, kf, a1, qv.w, a0));
+    float4 r = make_float4(__fmul_rn(__fdiv_rn(acc.x, kf), a1), __fmul_rn(__fdiv_rn(acc.y, kf), a1),
+                           __fmul_rn(__fdiv_rn(acc.z, kf), a1), __fmul_rn(__fdiv_rn(acc.w, kf), a1));
+    if (need_q || r.x == 0.f || r.y == 0.f || r.z == 0.f || r.w == 0.f) {
+      const float4 qv = *reinterpret_cast<const float4*>(q_row + j);
+      r = make_float4(blend_exact(acc.x, kf, a1, qv.x, a0), blend_exact(acc.y, kf, a1, qv.y, a0),
+                      blend_exact(acc.z, kf, a1, qv.z, a0), blend_exact(acc.w, kf, a1, qv.w, a0));
+    }
+    *reinterpret_cast<float4*>(out_row + j) = r;
   }
 }
 
@@ -513,7 +519,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
   if (out == nullptr) return;
   __syncthreads();
   ALIVE_FT(7);
-  gather_mean_row(lib_raw, n, d, s_top, idx_base, k, q_raw + static_cast<size_t>(q) * d, a1, a0,
+  gather_mean_row(lib_raw, n, d, s_top, idx_base, k, q_raw + static_cast<size_t>(q) * d, a0 != 0.f || !isfinite(qn), a1, a0,
                   out + static_cast<size_t>(q) * d, threadIdx.x, kThreads);
 #ifdef ALIVE_FINISH_TIMING
   __syncthreads();
@@ -592,8 +598,8 @@ collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ 
   }
   if (out == nullptr) return;
   __syncthreads();
-  gather_mean_row(lib_raw, n, d, s_top, 0, k, q_raw + static_cast<size_t>(q) * d, a1, a0, out + static_cast<size_t>(q) * d,
-                  threadIdx.x, kCollectThreads);
+  gather_mean_row(lib_raw, n, d, s_top, 0, k, q_raw + static_cast<size_t>(q) * d, a0 != 0.f || !isfinite(qn), a1, a0,
+                  out + static_cast<size_t>(q) * d, threadIdx.x, kCollectThreads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1010,7 +1016,7 @@ exact_final_kernel(int t, int k, const int* __restrict__ q_list, const int* __re
   __threadfence_block();
   // the warp that selected the top-k of this query also gathers it (top_idx written by lane 0)
   gather_mean_row(lib_raw, n, d, top_idx + static_cast<size_t>(q) * k, idx_base, k, q_raw + static_cast<size_t>(q) * d,
-                  a1, a0, out + static_cast<size_t>(q) * d, lane, 32);
+                  true, a1, a0, out + static_cast<size_t>(q) * d, lane, 32);
 }
 
 __global__ void __launch_bounds__(128)
@@ -1075,7 +1081,7 @@ extern "C" int alive_knn_rescore(const float* q_raw, const float* q_norm, int32_
   using namespace alive;
   ALIVE_REQUIRE(q_raw && q_norm && lib_raw && lib_norm && sel_idx && sel_n && top_score && top_idx,
                 "alive_knn_rescore: NULL argument");
-  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 8192, "alive_knn_rescore: d must be a multiple of 4");
+  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 1536, "alive_knn_rescore: d must be a multiple of 4, <= 1536 (got %d)", d);
   ALIVE_REQUIRE(k >= 1 && k <= r_max && r_max <= kMaxRMax, "alive_knn_rescore: need 1 <= k <= r_max <= %d", kMaxRMax);
   ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw)) & 15) == 0,
                 "alive_knn_rescore: raw buffers must be 16-byte aligned");
@@ -1119,10 +1125,14 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
   float* part_score = reinterpret_cast<float*>(part_idx + static_cast<size_t>(items) * groups * kEQ * splits * k);
   const size_t smem = static_cast<size_t>(kEK) * (kEQ + kER) * 8 + (static_cast<size_t>(kEQ) * kEScPitch + 1) * 4 +
                       static_cast<size_t>(kEQ) * k * 12 + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_done = true;
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
   // at most ~4 waves of CTAs; the (group, split) items beyond that are reached grid-stride
@@ -1139,11 +1149,6 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
                                   lib_raw, lib_norm, static_cast<long long>(n), d, k, q_list, q_count, splits, part_score,
                                   part_idx, t_item, few));
   if (few > 0) {
-    static bool rattr_done = false;
-    if (!rattr_done) {
-      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      rattr_done = true;
-    }
     const size_t rwork = static_cast<size_t>((few + kRQ - 1) / kRQ) * splits;
     size_t rgx = (4 * 148 + items - 1) / items;
     if (rgx > rwork) rgx = rwork;
@@ -1192,7 +1197,7 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
   ALIVE_REQUIRE(items >= 1 && t % items == 0, "alive_knn_finish: t must be a multiple of items");
   ALIVE_REQUIRE(k >= 1 && k <= kListLen, "alive_knn_finish: k must be in [1,%d] for the screened path (got %d)", kListLen, k);
   ALIVE_REQUIRE(r_max >= k && r_max <= kMaxRMax, "alive_knn_finish: r_max must be in [k,%d]", kMaxRMax);
-  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 8192, "alive_knn_finish: d must be a multiple of 4");
+  ALIVE_REQUIRE(d % 4 == 0 && d >= 4 && d <= 1536, "alive_knn_finish: d must be a multiple of 4, <= 1536 (got %d)", d);
   ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(lib_raw) | reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "alive_knn_finish: raw/out buffers must be 16-byte aligned");
   ALIVE_REQUIRE(out == nullptr || idx_base == 0, "alive_knn_finish: gather needs an unsharded library");
@@ -1201,19 +1206,20 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
   const int staged = entries <= kFinishMaxStagedEntries ? 1 : 0;
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
                       (staged ? static_cast<size_t>(entries) * 8 : 0);
-  static bool attr_done = false;
   // 0 = by batch size: 128 threads x 8 CTAs/SM keeps more queries in flight once the batch spans many
   // waves (measured at T = 10k: 360 -> 286 us), 256 x 4 in between, 512 / 1024 threads when there are
   // fewer queries than SMs can hold; ALIVE_KNN_FINISH_THREADS=128|256|512|1024 forces one
-  static int variant = 0;
-  if (!attr_done) {
-    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
-    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
-    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
-    ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
-    const char* v = getenv("ALIVE_KNN_FINISH_THREADS");
-    if (v) variant = atoi(v);
-    attr_done = true;
+  static const int variant = getenv("ALIVE_KNN_FINISH_THREADS") ? atoi(getenv("ALIVE_KNN_FINISH_THREADS")) : 0;
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
@@ -1258,10 +1264,13 @@ int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_
                          float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list, int32_t* fb2_count,
                          alive_stream_t stream) {
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(c_cap) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    ALIVE_CHECK_CUDA(cudaFuncSetAttribute(collect_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(collect_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
   }
   ALIVE_REQUIRE(smem <= 64 * 1024, "collect pass: candidate buffer too large for shared memory");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));

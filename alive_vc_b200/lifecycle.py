@@ -25,20 +25,34 @@ class LibraryBuilder:
     the library by whole utterances (inference.py:76 / realtime_inference.py:88 concatenate encoder
     output the same way), so a library of arbitrary N can be built from a corpus without ever leaving
     the device.  `packed()` runs K1 (alive_knn_pack) once over the accumulated frames.
+
+    Slots that were never written have no content: the reference's loop starts from `VoiceLibrary()`,
+    whose tokens are random-normal (voice_library.py:9), so its untouched slots are noise frames.  Ask for
+    the same start with `init="randn"` (all `capacity` slots filled like `VoiceLibrary(num_tokens=capacity)`)
+    or pass the initial `tokens=`; otherwise `tokens()` / `packed()` / `save()` raise while a slot below
+    the highest written one is still empty (an all-zero frame would rank first in every match, like the
+    NaN similarity it produces in the reference).
     """
 
-    def __init__(self, d: int = 768, capacity: int = 512, device="cuda", tokens: torch.Tensor | None = None):
+    def __init__(self, d: int = 768, capacity: int = 512, device="cuda", tokens: torch.Tensor | None = None,
+                 init: str | None = None, generator: torch.Generator | None = None):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("alive_vc_b200: LibraryBuilder needs a CUDA device (no CPU path)")
         if d < 1 or capacity < 0:
             raise ValueError("LibraryBuilder: d >= 1 and capacity >= 0 expected")
+        if init not in (None, "randn"):
+            raise ValueError("LibraryBuilder: init must be None or 'randn'")
         self.d = d
         self._rows = torch.zeros((max(capacity, 1), d), dtype=torch.float32, device=dev)   # [cap, D] row-major
+        self._written = torch.zeros((max(capacity, 1),), dtype=torch.bool, device=dev)
         self._n = 0
         self._packed = None
         if tokens is not None:
             self.append(tokens)
+        elif init == "randn" and capacity > 0:
+            # VoiceLibrary(num_tokens=capacity).tokens (voice_library.py:9), generated in its [1, D, N] layout
+            self.append(torch.randn(1, d, capacity, device=dev, generator=generator))
 
     # -- geometry -----------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -55,6 +69,21 @@ class LibraryBuilder:
         grown = torch.zeros((cap, self.d), dtype=torch.float32, device=self.device)
         grown[:self._n] = self._rows[:self._n]
         self._rows = grown
+        mask = torch.zeros((cap,), dtype=torch.bool, device=self.device)
+        mask[:self._n] = self._written[:self._n]
+        self._written = mask
+
+    def unwritten_slots(self) -> torch.Tensor:
+        """Indices of the slots below len(self) that no put/append has filled."""
+        return (~self._written[:self._n]).nonzero().reshape(-1)
+
+    def _require_complete(self):
+        missing = self.unwritten_slots()
+        if missing.numel():
+            raise RuntimeError(
+                f"LibraryBuilder: {missing.numel()} of {self._n} slots were never written (first: "
+                f"{missing[:8].tolist()}); start from tokens=... or init='randn' (what VoiceLibrary() holds in "
+                "generate_voice_library.py:30) or fill them")
 
     @staticmethod
     def _as_dn(frames: torch.Tensor, d: int) -> torch.Tensor:
@@ -76,6 +105,7 @@ class LibraryBuilder:
         n = f.shape[1]
         self._reserve(self._n + n)
         self._rows[self._n:self._n + n].copy_(f.t())
+        self._written[self._n:self._n + n] = True
         self._n += n
         self._packed = None
         return self
@@ -99,23 +129,27 @@ class LibraryBuilder:
         last.scatter_reduce_(0, slots, torch.arange(m, device=self.device), reduce="amax", include_self=True)
         written = (last >= 0).nonzero().reshape(-1)
         self._rows[written] = f.t()[last[written]]
+        self._written[written] = True
         self._packed = None
         return self
 
     # -- reads --------------------------------------------------------------------------------
     def tokens(self) -> torch.Tensor:
         """The library as the reference stores it: [1, D, N] float32 (module/voice_library.py:9)."""
+        self._require_complete()
         return self._rows[:self._n].t().unsqueeze(0).contiguous()
 
     def packed(self) -> M.PackedFrames:
         if self._n == 0:
             raise RuntimeError("selected index k out of range")      # an empty library cannot be matched
+        self._require_complete()
         if self._packed is None:
             self._packed = M.pack_frames(self._rows[:self._n].t())    # [D, N] view of the row-major block
         return self._packed
 
     def save(self, path: str):
-        """Packed layout + the reference's own `tokens` key in one file (save_packed_library)."""
+        """`path` = the reference's own checkpoint ({"tokens": [1, D, N]}, strict-loadable by the unmodified
+        reference), `path + ".alive_knn"` = the packed layout (matching.save_packed_library)."""
         M.save_packed_library(self.packed(), path, include_legacy_tokens=True)
 
 

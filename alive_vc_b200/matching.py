@@ -15,6 +15,7 @@ libalive_knn.so must be built, otherwise a RuntimeError is raised.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import weakref
 from dataclasses import dataclass, field
@@ -39,8 +40,18 @@ def _num_sms(device: torch.device) -> int:
     return _sm_count[idx]
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    """torch's current stream ON `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on(device):
+    """The C ABI launches on the CURRENT CUDA device and never switches it: make the device the buffers
+    live on current for the duration of the call (a no-op context when it already is)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if torch.cuda.current_device() == idx:
+        return contextlib.nullcontext()
+    return torch.cuda.device(idx)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -103,11 +114,12 @@ def pack_into(dst: PackedFrames, row0: int, frames_dn: torch.Tensor):
     if n == 0:
         return
     assert frames_dn.dtype == torch.float32 and frames_dn.is_cuda
-    assert d == dst.d and row0 + n <= dst.n
-    rc = lib.alive_knn_pack(
-        frames_dn.data_ptr(), n, d, frames_dn.stride(1), frames_dn.stride(0),
-        dst.raw[row0:].data_ptr(), dst.norms[row0:].data_ptr(), dst.packed[row0:].data_ptr(),
-        dst.err[row0:].data_ptr(), dst.stats.data_ptr(), _stream_ptr())
+    assert d == dst.d and row0 + n <= dst.n and frames_dn.device == dst.device
+    with _on(dst.device):
+        rc = lib.alive_knn_pack(
+            frames_dn.data_ptr(), n, d, frames_dn.stride(1), frames_dn.stride(0),
+            dst.raw[row0:].data_ptr(), dst.norms[row0:].data_ptr(), dst.packed[row0:].data_ptr(),
+            dst.err[row0:].data_ptr(), dst.stats.data_ptr(), _stream_ptr(dst.device))
     _cabi.check(rc, "alive_knn_pack")
     _count(1)
 
@@ -152,111 +164,164 @@ def pack_libraries(reference: torch.Tensor) -> PackedFrames:
 
 
 # ---------------------------------------------------------------------------------------
-# library lifecycle: the packed layout stored next to the legacy pickle
+# library lifecycle: the reference's own checkpoint + a sidecar with the packed layout
 # ---------------------------------------------------------------------------------------
-PACKED_FORMAT_VERSION = 1
+PACKED_FORMAT_VERSION = 2
+SIDECAR_SUFFIX = ".alive_knn"
+
+
+def _fingerprint(raw: torch.Tensor):
+    """Cheap content check tying a sidecar to its tokens file (fp64 sum and sum of squares, on the device)."""
+    r = raw.double()
+    return [float(r.sum()), float((r * r).sum())]
 
 
 def save_packed_library(lib: PackedFrames, path: str, include_legacy_tokens: bool = True):
-    """torch.save the packed library.  With `include_legacy_tokens` the file also carries the
-    reference's own checkpoint key `tokens` ([1, D, N] float32, generate_voice_library.py:42 /
-    module/voice_library.py:9), so `VoiceLibrary(num_tokens=N).load_state_dict(..., strict=False)`
-    of the REFERENCE still reads it."""
-    blob = {
-        "alive_knn_packed_version": PACKED_FORMAT_VERSION,
-        "n": lib.n, "d": lib.d, "row_base": lib.row_base,
-        "raw": lib.raw.cpu(), "norms": lib.norms.cpu(), "packed": lib.packed.cpu(), "err": lib.err.cpu(),
-        "stats": lib.stats.cpu(),
-    }
+    """Persist a packed library as TWO files:
+
+    `path`               exactly what generate_voice_library.py:42 / fine_tune.py:199 write: the state dict
+                         `{"tokens": [1, D, N] float32}` and nothing else, so the UNMODIFIED reference reads it with
+                         its strict `VL.load_state_dict(torch.load(path))` (inference.py:81, realtime_inference.py:93,
+                         fine_tune.py:126) - given `VoiceLibrary(num_tokens=N)`.  A set of B per-speaker libraries
+                         (`pack_libraries`, items = B) is stored as tokens [B, D, N].
+    `path + ".alive_knn"` the packed layout K1 produced (bf16 rows, norms, error norms, stats) plus n, d, items,
+                         row_base and a fingerprint of the tokens; the raw fp32 rows are NOT stored twice (they are
+                         the transposed tokens).
+    `include_legacy_tokens=False` skips the first file (the sidecar alone cannot be loaded)."""
+    n_item = lib.n_item
+    tokens = lib.raw.view(lib.items, n_item, lib.d).transpose(1, 2).contiguous().cpu()     # [items, D, N]
     if include_legacy_tokens:
-        blob["tokens"] = lib.raw.t().unsqueeze(0).contiguous().cpu()
-    torch.save(blob, path)
+        torch.save({"tokens": tokens}, path)
+    torch.save({
+        "alive_knn_packed_version": PACKED_FORMAT_VERSION,
+        "n": lib.n, "d": lib.d, "row_base": lib.row_base, "items": lib.items,
+        "norms": lib.norms.cpu(), "packed": lib.packed.cpu(), "err": lib.err.cpu(), "stats": lib.stats.cpu(),
+        "fingerprint": _fingerprint(lib.raw),
+    }, path + SIDECAR_SUFFIX)
 
 
 def load_packed_library(path: str, device="cuda") -> PackedFrames:
-    """Inverse of save_packed_library.  A legacy reference checkpoint ({"tokens": [1,D,N]}) is
-    accepted too and packed on the fly (K1)."""
-    blob = torch.load(path, map_location="cpu", weights_only=True)
+    """Inverse of save_packed_library.  `path` is a reference voice-library checkpoint (`{"tokens": [1, D, N]}`,
+    or [B, D, N] for a set of libraries); when the sidecar `path + ".alive_knn"` exists and its fingerprint matches
+    the tokens, the packed layout is taken from it, otherwise the tokens are packed on the fly (K1) - so every
+    checkpoint the reference wrote loads too."""
+    import os
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("alive_vc_b200: packed libraries live on a CUDA device (no CPU path)")
-    if "alive_knn_packed_version" not in blob:
-        if "tokens" not in blob:
-            raise RuntimeError(f"{path}: neither a packed library nor a reference voice-library checkpoint")
-        return pack_library(blob["tokens"].to(dev))
-    if blob["alive_knn_packed_version"] != PACKED_FORMAT_VERSION:
-        raise RuntimeError(f"{path}: unsupported packed format version {blob['alive_knn_packed_version']}")
-    return PackedFrames(n=int(blob["n"]), d=int(blob["d"]), raw=blob["raw"].to(dev), norms=blob["norms"].to(dev),
-                        packed=blob["packed"].to(dev), err=blob["err"].to(dev), stats=blob["stats"].to(dev),
-                        row_base=int(blob["row_base"]))
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    if "alive_knn_packed_version" in blob:        # round-1 single-file format (packed arrays next to `tokens`)
+        if blob["alive_knn_packed_version"] != 1:
+            raise RuntimeError(f"{path}: unsupported packed format version {blob['alive_knn_packed_version']}")
+        return PackedFrames(n=int(blob["n"]), d=int(blob["d"]), raw=blob["raw"].to(dev), norms=blob["norms"].to(dev),
+                            packed=blob["packed"].to(dev), err=blob["err"].to(dev), stats=blob["stats"].to(dev),
+                            row_base=int(blob["row_base"]))
+    if "tokens" not in blob:
+        raise RuntimeError(f"{path}: not a voice-library checkpoint (no `tokens` key)")
+    tokens = blob["tokens"]
+    if tokens.dim() != 3:
+        raise RuntimeError(f"{path}: tokens must be [1, D, N] (or [B, D, N]), got {tuple(tokens.shape)}")
+    items, d, n_item = tokens.shape
+    side = path + SIDECAR_SUFFIX
+    if os.path.exists(side):
+        sc = torch.load(side, map_location="cpu", weights_only=True)
+        raw = tokens.to(dev).float().transpose(1, 2).contiguous().view(items * n_item, d)
+        ok = (sc.get("alive_knn_packed_version") == PACKED_FORMAT_VERSION and int(sc["n"]) == items * n_item and
+              int(sc["d"]) == d and int(sc["items"]) == items and sc["fingerprint"] == _fingerprint(raw))
+        if ok:
+            return PackedFrames(n=items * n_item, d=d, raw=raw, norms=sc["norms"].to(dev), packed=sc["packed"].to(dev),
+                                err=sc["err"].to(dev), stats=sc["stats"].to(dev), row_base=int(sc["row_base"]),
+                                items=items)
+        del raw      # stale sidecar (the tokens were edited since): pack again
+    tok = tokens.to(dev)
+    return pack_library(tok) if items == 1 else pack_libraries(tok)
 
 
 # ---------------------------------------------------------------------------------------
-# pack cache: invisible to callers, keyed on the tensor OBJECT and validated against its
-# storage pointer / version counter / geometry (SURVEY §8(b) "Ownership")
+# pack cache: invisible to callers (SURVEY §8(b) "Ownership").  Keyed on the tensor OBJECT that owns the
+# memory (the base of a view) plus the view's geometry, validated against the version counter.
 # ---------------------------------------------------------------------------------------
 _pack_cache: dict = {}
 _PACK_CACHE_MAX = 16
+# Libraries below this many elements are re-packed on every call instead of cached (K1 on 512 x 768 tokens is
+# one launch of a few microseconds): writes through `.data` (`VL.tokens.data[:, :, n] = t`,
+# generate_voice_library.py:38), which do NOT bump the version counter, are then always seen - the default
+# 512-token VoiceLibrary included.  Larger tensors written through `.data` (or by a custom kernel / a graph
+# replay) need an explicit clear_pack_cache(tensor) / VoiceLibrary.invalidate().
+PACK_CACHE_MIN_ELEMENTS = 1 << 20
 
 
-def _cache_key(t: torch.Tensor):
-    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), str(t.device), t.dtype)
+def _version_of(t: torch.Tensor):
+    try:
+        return t._version
+    except RuntimeError:          # "Inference tensors do not track version counter": nothing to validate against
+        return None
 
 
-def cached_pack(owner: torch.Tensor, frames_dn: torch.Tensor, tag=0) -> PackedFrames:
-    """Pack `frames_dn` (a view of `owner`) unless `owner` was packed before and has not
-    changed since (same object, same storage pointer, same version counter)."""
-    oid = (id(owner), tag)
+def _owner_of(t: torch.Tensor) -> torch.Tensor:
+    """The object whose lifetime and version counter govern `t`: its base when `t` is a view."""
+    try:
+        base = t._base
+    except RuntimeError:
+        base = None
+    return t if base is None else base
+
+
+def _geometry(t: torch.Tensor):
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t.device.index)
+
+
+def _cached(reference: torch.Tensor, tag, build) -> PackedFrames:
+    version = _version_of(reference)
+    if version is None or reference.numel() < PACK_CACHE_MIN_ELEMENTS:
+        return build()            # inference tensors (realtime_inference.py:143) and small libraries: never cached
+    owner = _owner_of(reference)
+    oid = (id(owner), tag, _geometry(reference))
     ent = _pack_cache.get(oid)
-    key = _cache_key(owner)
     if ent is not None:
-        ref, old_key, packed = ent
-        if ref() is owner and old_key == key:
+        ref, old_version, packed = ent
+        if ref() is owner and old_version == version:
             return packed
         del _pack_cache[oid]
-    packed = pack_frames(frames_dn)
+    packed = build()
     if len(_pack_cache) >= _PACK_CACHE_MAX:
         for dead in [k for k, (r, _, _) in _pack_cache.items() if r() is None]:
             del _pack_cache[dead]
         while len(_pack_cache) >= _PACK_CACHE_MAX:
             del _pack_cache[next(iter(_pack_cache))]
 
-    def _drop(_ref, oid=oid):
-        _pack_cache.pop(oid, None)
+    def _drop(_ref, owner_id=id(owner)):
+        for key in [k for k in _pack_cache if k[0] == owner_id]:
+            _pack_cache.pop(key, None)
 
     try:
-        _pack_cache[oid] = (weakref.ref(owner, _drop), key, packed)
+        _pack_cache[oid] = (weakref.ref(owner, _drop), version, packed)
     except TypeError:
         pass
     return packed
 
 
-def cached_pack_many(owner: torch.Tensor, reference_bdn: torch.Tensor) -> PackedFrames:
-    """pack_libraries with the same invisible cache as cached_pack (keyed on the tensor object)."""
-    oid = (id(owner), "many")
-    ent = _pack_cache.get(oid)
-    key = _cache_key(owner)
-    if ent is not None:
-        ref, old_key, packed = ent
-        if ref() is owner and old_key == key:
-            return packed
-        del _pack_cache[oid]
-    packed = pack_libraries(reference_bdn)
-
-    def _drop(_ref, oid=oid):
-        _pack_cache.pop(oid, None)
-
-    try:
-        if len(_pack_cache) >= _PACK_CACHE_MAX:
-            del _pack_cache[next(iter(_pack_cache))]
-        _pack_cache[oid] = (weakref.ref(owner, _drop), key, packed)
-    except TypeError:
-        pass
-    return packed
+def cached_pack(reference: torch.Tensor, frames_dn: torch.Tensor, tag=0) -> PackedFrames:
+    """Pack `frames_dn` (the [D, N] float32 frames of `reference`) unless the same view of the same tensor
+    object was packed before and its version counter has not moved since."""
+    return _cached(reference, tag, lambda: pack_frames(frames_dn))
 
 
-def clear_pack_cache():
-    _pack_cache.clear()
+def cached_pack_many(reference: torch.Tensor, reference_bdn: torch.Tensor) -> PackedFrames:
+    """pack_libraries with the same invisible cache as cached_pack."""
+    return _cached(reference, "many", lambda: pack_libraries(reference_bdn))
+
+
+def clear_pack_cache(tensor: Optional[torch.Tensor] = None):
+    """Forget every cached packed library - or, given a tensor, the ones made from it or from views of the same
+    base.  Needed after writes the version counter does not see (`t.data[...] = x`, custom kernels, CUDA-graph
+    replays writing into the library) when the tensor holds at least PACK_CACHE_MIN_ELEMENTS elements."""
+    if tensor is None:
+        _pack_cache.clear()
+        return
+    owner_id = id(_owner_of(tensor))
+    for key in [k for k in _pack_cache if k[0] == owner_id]:
+        _pack_cache.pop(key, None)
 
 
 # ---------------------------------------------------------------------------------------
@@ -313,12 +378,13 @@ def exact_topk(q: PackedFrames, lib: PackedFrames, k: int, top_score=None, top_i
         top_idx = torch.empty((t, k), dtype=torch.int64, device=dev)
     ws_bytes = c.alive_knn_exact_workspace_bytes(t, lib.n, k, 1)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    rc = c.alive_knn_exact(q.raw.data_ptr(), q.norms.data_ptr(), t, lib.raw.data_ptr(), lib.norms.data_ptr(),
-                           lib.n, lib.d, k,
-                           q_list.data_ptr() if q_list is not None else None,
-                           q_count.data_ptr() if q_count is not None else None,
-                           lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), 0.0, None, 1,
-                           _stream_ptr())
+    with _on(dev):
+        rc = c.alive_knn_exact(q.raw.data_ptr(), q.norms.data_ptr(), t, lib.raw.data_ptr(), lib.norms.data_ptr(),
+                               lib.n, lib.d, k,
+                               q_list.data_ptr() if q_list is not None else None,
+                               q_count.data_ptr() if q_count is not None else None,
+                               lib.row_base, ws.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), 0.0, None, 1,
+                               _stream_ptr(dev))
     _cabi.check(rc, "alive_knn_exact")
     _count(2)
     return top_score, top_idx
@@ -350,7 +416,14 @@ def search_topk(q: PackedFrames, lib: PackedFrames, k: int, mode: str = "auto",
         raise RuntimeError(f"the screened path needs k <= {LIST_LEN}")
 
     plan = make_plan(t, n, d, dev, variant)
-    stream = _stream_ptr()
+    with _on(dev):
+        return _search_topk_screen(c, q, lib, k, r_max, plan, dev)
+
+
+def _search_topk_screen(c, q, lib, k, r_max, plan, dev):
+    global last_info
+    t, d = q.n, lib.d
+    stream = _stream_ptr(dev)
     cand_score = torch.empty((t, plan.lists, LIST_LEN), dtype=torch.float32, device=dev)
     cand_idx = torch.empty((t, plan.lists, LIST_LEN), dtype=torch.int32, device=dev)
     if search_events is not None:
@@ -389,8 +462,10 @@ def search_topk(q: PackedFrames, lib: PackedFrames, k: int, mode: str = "auto",
 def gather_mean(lib: PackedFrames, top_idx: torch.Tensor, q: PackedFrames, alpha: float, out: torch.Tensor):
     """K4: common.py:107-109 into `out` [T,D] float32."""
     t, k = top_idx.shape
-    rc = _cabi.load().alive_knn_gather_mean(lib.raw.data_ptr(), lib.n, lib.d, top_idx.data_ptr(), t, k,
-                                            q.raw.data_ptr(), float(alpha), out.data_ptr(), _stream_ptr())
+    with _on(out.device):
+        rc = _cabi.load().alive_knn_gather_mean(lib.raw.data_ptr(), lib.n, lib.d, top_idx.data_ptr(), t, k,
+                                                q.raw.data_ptr(), q.norms.data_ptr() if q.norms is not None else None,
+                                                float(alpha), out.data_ptr(), _stream_ptr(out.device))
     _cabi.check(rc, "alive_knn_gather_mean")
     _count(1)
     return out
@@ -408,12 +483,23 @@ def pack_queries(source: torch.Tensor) -> PackedFrames:
 _MODES = {"auto": 0, "screen": 1, "exact": 2}
 
 
+_layout_cache: dict = {}
+
+
 def _layout(rows: int, lib: PackedFrames, k: int, r_max: int, mode: int, variant: int, device):
+    """Workspace layout of alive_knn_match for this shape (a pure function of its arguments: memoised, so a
+    steady-state call makes ONE C call)."""
+    key = (rows, lib.n_item, lib.d, k, r_max, mode, _num_sms(device), variant, lib.items)
+    hit = _layout_cache.get(key)
+    if hit is not None:
+        return hit
     off = (ctypes.c_int64 * 12)()
-    rc = _cabi.load().alive_knn_match_layout(rows, lib.n_item, lib.d, k, r_max, mode, _num_sms(device), variant,
-                                             lib.items, off)
+    rc = _cabi.load().alive_knn_match_layout(*key[:8], lib.items, off)
     _cabi.check(rc, "alive_knn_match_layout")
-    return list(off)
+    if len(_layout_cache) > 256:
+        _layout_cache.clear()
+    _layout_cache[key] = list(off)
+    return _layout_cache[key]
 
 
 def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0, mode: str = "auto",
@@ -436,6 +522,8 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
     _require_cuda(source, "source")
     assert source.dtype == torch.float32
     dev = source.device
+    if dev != lib.device:
+        raise RuntimeError(f"source is on {dev} but the packed library is on {lib.device}")
     rows = B * T
     m = _MODES[mode]
     if m == 0:
@@ -449,18 +537,19 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
         top_idx = torch.empty((B, T, k), dtype=torch.int64, device=dev)
         top_score = torch.empty((B, T, k), dtype=torch.float32, device=dev)
     ev0 = ev1 = None
-    if search_events is not None and m == 1:
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()      # forces creation of the cudaEvent_t handles; re-recorded inside the C call
-        ev1.record()
-        search_events.append((ev0, ev1))
-    rc = c.alive_knn_match(source.data_ptr(), B, T, source.stride(0), source.stride(2), source.stride(1),
-                           ctypes.byref(lib.handle()), k, float(alpha), r_max, m, _num_sms(dev), variant,
-                           workspace.data_ptr(), workspace.numel(), out.data_ptr() if want_out else None,
-                           top_idx.data_ptr(), top_score.data_ptr(),
-                           ev0.cuda_event if ev0 is not None else None,
-                           ev1.cuda_event if ev1 is not None else None, _stream_ptr())
+    with _on(dev):
+        if search_events is not None and m == 1:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()      # forces creation of the cudaEvent_t handles; re-recorded inside the C call
+            ev1.record()
+            search_events.append((ev0, ev1))
+        rc = c.alive_knn_match(source.data_ptr(), B, T, source.stride(0), source.stride(2), source.stride(1),
+                               ctypes.byref(lib.handle()), k, float(alpha), r_max, m, _num_sms(dev), variant,
+                               workspace.data_ptr(), workspace.numel(), out.data_ptr() if want_out else None,
+                               top_idx.data_ptr(), top_score.data_ptr(),
+                               ev0.cuda_event if ev0 is not None else None,
+                               ev1.cuda_event if ev1 is not None else None, _stream_ptr(dev))
     _cabi.check(rc, "alive_knn_match")
     _count(1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
@@ -470,6 +559,7 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
                            launches=1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info._workspace = workspace
+    last_info._offsets = off
     return (out if want_out else None), top_idx, top_score
 
 
@@ -536,6 +626,9 @@ class StreamingMatcher:
         return self.out.transpose(1, 2)
 
 
+_SCALAR_NAMES = {torch.float32: "Float", torch.float16: "Half", torch.bfloat16: "BFloat16", torch.float64: "Double"}
+
+
 def _check_inputs(source: torch.Tensor, reference: torch.Tensor, k: int):
     # shape / k errors first, with the reference's own messages, then the device check
     if source.dim() != 3 or reference.dim() != 3:
@@ -553,18 +646,31 @@ def _check_inputs(source: torch.Tensor, reference: torch.Tensor, k: int):
     _require_cuda(reference, "reference")
     if source.device != reference.device:
         raise RuntimeError(f"source is on {source.device} but reference is on {reference.device}")
+    _check_dtypes(source, reference)
+
+
+def _check_dtypes(source: torch.Tensor, reference: torch.Tensor):
+    """Mixed dtypes only work in the reference under autocast (realtime_inference.py:144: fp16 encoder output
+    against an fp32 library); outside it torch.bmm at common.py:104 raises - so does this."""
+    if source.dtype != reference.dtype and not torch.is_autocast_enabled("cuda"):
+        raise RuntimeError(f"expected scalar type {_SCALAR_NAMES.get(reference.dtype, reference.dtype)} "
+                           f"but found {_SCALAR_NAMES.get(source.dtype, source.dtype)}")
 
 
 def match_indices(source: torch.Tensor, reference: torch.Tensor, k: int = 4, mode: str = "auto",
                   variant: int = 0):
     """The neighbour indices the reference computes at common.py:105 but never returns:
     ([B,T,k] int64, [B,T,k] float32 similarities)."""
-    out = _match_impl(source, reference, k, 0.0, mode, variant, want_out=False)
+    _check_inputs(source, reference, k)
+    with torch.no_grad():
+        out = _match_impl(source, reference, k, 0.0, mode, variant, want_out=False)
     return out[1], out[2]
 
 
 def _match_impl(source, reference, k, alpha, mode, variant, want_out=True):
-    _check_inputs(source, reference, k)
+    """source [B, D, T]; reference [B, D, N] (one library per batch item) or a library shared by every item
+    ([1, D, N], or a stride-0 expand of it as VoiceLibrary.match builds at voice_library.py:16-19).
+    Returns (out [B, T, D] float32, idx [B, T, k] int64, score [B, T, k] float32)."""
     B, D, T = source.shape
     src32 = source if source.dtype == torch.float32 else source.float()
     ref32 = reference if reference.dtype == torch.float32 else reference.float()
@@ -573,22 +679,23 @@ def _match_impl(source, reference, k, alpha, mode, variant, want_out=True):
         return (torch.empty((B, 0, D), dtype=torch.float32, device=dev),
                 torch.empty((B, 0, k), dtype=torch.int64, device=dev),
                 torch.empty((B, 0, k), dtype=torch.float32, device=dev))
-    shared = B == 1 or ref32.stride(0) == 0
-    if shared:
-        # one library for every batch item (VoiceLibrary.match: tokens.expand, voice_library.py:16-19)
-        owner = reference if (reference.dtype == torch.float32) else ref32
-        lib = cached_pack(owner, ref32[0])
-        return match_packed(src32, lib, k, alpha, mode, variant)
-    # a different library per batch item (train_decoder.py:134-135, BASELINE cfg5): all items are
-    # packed back to back and matched in ONE pipeline launch
-    owner = reference if (reference.dtype == torch.float32) else ref32
-    lib = cached_pack_many(owner, ref32)
-    return match_packed(src32, lib, k, alpha, mode, variant)
+    if reference.shape[0] == 1 or ref32.stride(0) == 0:
+        lib = cached_pack(reference, ref32[0])
+    else:
+        # a different library per batch item (train_decoder.py:134-135, BASELINE cfg5): all items are
+        # packed back to back and matched in ONE pipeline launch
+        lib = cached_pack_many(reference, ref32)
+    out, idx, score = run_match(src32, lib, k, alpha, mode, variant, want_out=want_out)
+    if lib.items > 1:
+        idx = idx - (torch.arange(lib.items, device=idx.device, dtype=idx.dtype) * lib.n_item).view(-1, 1, 1)
+    if out is None:
+        out = torch.empty((B, 0, D), dtype=torch.float32, device=dev)
+    return out, idx, score
 
 
 class _BlendGrad(torch.autograd.Function):
-    """d(out)/d(source) of common.py:109: the matched term carries no gradient to `source`
-    (indices are not differentiable), the blend contributes alpha * g."""
+    """d(out)/d(frames) of common.py:109 for the row-major entry point (lifecycle.match_rows): the matched term
+    carries no gradient to the query frames (indices are not differentiable), the blend contributes alpha * g."""
 
     @staticmethod
     def forward(ctx, source, out_bdt, alpha):
@@ -611,18 +718,27 @@ def match_features(source: torch.Tensor, reference: torch.Tensor, k: int = 4, al
     `result*(1-alpha) + source*alpha`.  `reference` never receives a gradient and
     `source` receives `alpha * grad`, as in the reference (`torch.no_grad` at :98).
 
+    The work is one registered custom op (`torch.ops.alive_vc_b200.knn_match`, alive_vc_b200/ops.py: fake
+    kernel + autograd formula), so callers may be traced / torch.compile'd; it works under
+    `torch.inference_mode()` and autocast like the call at realtime_inference.py:143-165.
+
+    dtypes: the result has `torch.promote_types(source.dtype, reference.dtype)` like the reference's last
+    line; mixed dtypes outside autocast raise like its bmm.  Similarities are always evaluated from the
+    float32 values of the inputs (under fp16 autocast the reference's own bmm runs in half precision; this
+    path returns the float32-exact neighbours of the same inputs).
+
     Raises RuntimeError("selected index k out of range") when k > N or the library is
     empty, and the bmm size error on a batch mismatch, like the reference.
     `return_indices=True` additionally returns the [B,T,k] int64 indices (extension used
     for parity checks; the reference computes but never returns them).
     """
-    with torch.no_grad():
-        out_btd, idx, _ = _match_impl(source, reference, k, float(alpha), mode, variant)
+    from . import ops
+    _check_inputs(source, reference, k)
+    out_btd, idx, _ = ops.knn_match(source, reference, k, float(alpha), mode, variant, False)
     out = out_btd.transpose(1, 2)
-    if out.dtype != source.dtype:
-        out = out.to(source.dtype)
-    if torch.is_grad_enabled() and source.requires_grad:
-        out = _BlendGrad.apply(source, out, float(alpha))
+    want = torch.promote_types(source.dtype, reference.dtype)
+    if out.dtype != want:
+        out = out.to(want)
     if return_indices:
         return out, idx
     return out

@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* alive_stream_t; /* cudaStream_t */
 
-#define ALIVE_KNN_ABI_VERSION 3
+#define ALIVE_KNN_ABI_VERSION 4
 #define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
 #define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
 #define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
@@ -167,14 +167,23 @@ int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t t,
 int alive_knn_merge(const float* scores, const int64_t* idx, int32_t ranks, int32_t t, int32_t k,
                     float* top_score, int64_t* top_idx, alive_stream_t stream);
 
+/* The same merge on RECORDS - what one all-gather moves per rank: idx [t,k] int64 immediately
+ * followed by score [t,k] float32 (t*k*12 bytes), the records of consecutive ranks `record_stride`
+ * bytes apart.  Entries with idx < 0 are padding (a shard holding fewer than k frames). */
+int alive_knn_merge_records(const void* records, int64_t record_stride, int32_t ranks, int32_t t,
+                            int32_t k, float* top_score, int64_t* top_idx, alive_stream_t stream);
+
 /* K4 - gather + mean + blend.  Replaces common.py:107-109
  * (voice_library.py:31-33): out[t,:] = mean_j raw[top_idx[t,j],:] summed
  * sequentially in descending-score order then divided by k, blended as
  * out*(1-alpha) + q_raw*alpha with separately rounded products.
  *   out [t,d] float32 row-major (the reference returns exactly this block
- *   viewed as [D,T]). */
+ *   viewed as [D,T]).
+ *   q_norm [t] float32 or NULL: the norms alive_knn_pack wrote for the query frames.  When given,
+ *   the query row is only read where it can change the result (alpha != 0, a non-finite query -
+ *   0*inf is NaN in the reference - or a mean of exactly zero); NULL = always read it.  Same bits. */
 int alive_knn_gather_mean(const float* lib_raw, int64_t n, int32_t d, const int64_t* top_idx,
-                          int32_t t, int32_t k, const float* q_raw, float alpha,
+                          int32_t t, int32_t k, const float* q_raw, const float* q_norm, float alpha,
                           float* out, alive_stream_t stream);
 
 /* Sharded variant, step 1: rows[t,k,d] = raw[top_idx - row_lo] where
@@ -192,7 +201,22 @@ int alive_knn_mean_blend(const float* rows, int32_t t, int32_t k, int32_t d, con
  * rank computes the full, bit-identical [t,d] result with no collective after the merge. */
 int alive_knn_gather_mean_peers(const float* const* shard_raw, const int64_t* bounds, int32_t shards,
                                 int32_t d, const int64_t* top_idx, int32_t t, int32_t k,
-                                const float* q_raw, float alpha, float* out, alive_stream_t stream);
+                                const float* q_raw, const float* q_norm, float alpha, float* out,
+                                alive_stream_t stream);
+
+/* The final step of the row-sharded match as ONE kernel (common.py:105 across shards + :107-109):
+ * for query rows [row0, row0+rows) of the t queries, merge the per-rank records (see
+ * alive_knn_merge_records) into the global top-k and gather + mean + blend the k winning raw frames
+ * straight from the GPU that owns them (shard_raw / bounds as in alive_knn_gather_mean_peers; a local
+ * pointer is fine).  No collective follows the all-gather of the records.
+ *   q_raw [t,d] / q_norm [t] (nullable) are indexed by the GLOBAL row; out [rows,d],
+ *   top_score [rows,k] / top_idx [rows,k] (both nullable) by the row inside the range.
+ *   d must be 128, 256, 512, 768, 1024 or 1536. */
+int alive_knn_merge_gather(const void* records, int64_t record_stride, int32_t ranks, int32_t t, int32_t k,
+                           int32_t row0, int32_t rows, const float* const* shard_raw,
+                           const int64_t* bounds, int32_t shards, int32_t d, const float* q_raw,
+                           const float* q_norm, float alpha, float* out, float* top_score,
+                           int64_t* top_idx, alive_stream_t stream);
 
 /* CUDA IPC plumbing for the peer-memory gather (host-side; one process per GPU, same box):
  * export the allocation containing dev_ptr (64-byte handle + byte offset of dev_ptr inside it),
