@@ -135,7 +135,7 @@ class ThreadComm:
     class _Shared:
         def __init__(self, world):
             self.world = world
-            self.barrier = threading.Barrier(world)
+            self.barrier = threading.Barrier(world, timeout=300)     # a rank that died breaks the barrier for the others
             self.slots = [None] * world
 
     def __init__(self, shared, rank):

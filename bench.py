@@ -1,27 +1,33 @@
 """bench.py - headline benchmark of the kNN voice-library matching path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg4] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg4] [--impl reference] [--no-extras]
 
-Metric (BASELINE.json): query frames/sec matched (k=4) vs library size N at 1/2/4/8 B200.
-Default workload = BASELINE configs[3] ("cfg4"): T=10,000 query frames against a
-10,000,000-frame library (D=768, k=4), the library row-sharded over the N GPUs of one box
-(strong scaling: total work fixed).  It fits one B200 (15.4 GB bf16 + 30.7 GB fp32), so the
-same workload is used at N=1.  Other workloads: cfg1, cfg2 (latency), cfg3, cfg5.
+Metric (BASELINE.json): query frames/sec matched (k=4) vs library size N at 1/2/4/8 B200; p50 chunk latency.
+Headline workload = BASELINE configs[3] ("cfg4"): T=10,000 query frames against a 10,000,000-frame library
+(D=768, k=4), the library row-sharded over the N GPUs of one box (strong scaling: total work fixed).  It fits one
+B200 (15.4 GB bf16 + 30.7 GB fp32), so the same workload is used at N=1.
 
 A "step" = one pass of the hot path over one batch of T synthetic query frames:
-  value : inputs resident in HBM, CUDA-event timed, barrier + synchronize on both sides,
-          max over ranks, value = T / time
-  e2e   : the same call through the public API with HOST buffers: pinned-host queries ->
-          H2D -> match -> D2H of the matched features, every step
-  roofline      : the fused tcgen05 similarity+top-list kernel (alive_knn_search), its own
-                  CUDA-event duration inside the timed region vs MEASURED_PEAKS.json
-  roofline_gather : the standalone gather-mean kernel (K4) on the step's own indices vs the HBM peak, with
-                  torch's index_select of the same rows beside it (the practical ceiling of random 3 KB rows)
-  roofline_pack : the library pack (K1) alone on a fresh 250k-frame chunk, channel-major (the reference's
-                  layout) and row-major, vs the HBM peak; torch's transposing copy of the chunk beside it
-  cpu_baseline  : the oracle's torch port of the reference (oracle/knn_oracle.py
-                  match_features_torch = module/common.py:96-109 on CPU) on the box's host
-                  cores, bounded sample, rank 0 at N=1 only
+  value : inputs resident in HBM, CUDA-event timed, barrier + synchronize on both sides, max over ranks,
+          value = T / time
+  e2e   : the same call through the public API with HOST buffers: pinned-host queries -> H2D -> match -> D2H of
+          the matched features, every step.  At N > 1 every query byte crosses PCIe ONCE: rank r copies its T/N
+          slice of the frames, the slices are all-gathered over NVLink, and rank r reads back its T/N slice of
+          the result (ShardedLibrary.match(scattered=True)); the byte counts are the whole job's.
+  roofline        : the fused tcgen05 similarity+top-list kernel (alive_knn_search), its own CUDA-event duration
+                    inside the timed region vs MEASURED_PEAKS.json
+  roofline_gather : the standalone gather-mean kernel (K4) on the step's own indices vs the HBM peak (algorithmic
+                    bytes k*D*4 read + D*4 written per query frame), torch's index_select of the same rows beside it
+  roofline_pack   : the library pack (K1) alone on a fresh 250k-frame chunk, channel-major (the reference's
+                    layout) and row-major, vs the HBM peak
+  parity          : after the timed loops, 256 query frames through the SAME sharded call vs the exhaustive fp64
+                    scan of every shard merged across ranks (indices) and vs the sequential mean of the raw frames
+                    (features); any mismatch beyond a 1e-6 similarity tie makes the run exit 1
+  cpu_baseline    : the oracle's torch port of the reference (oracle/knn_oracle.py match_features_torch =
+                    module/common.py:96-109 on CPU) on the box's host cores, bounded sample, rank 0 at N=1 only
+  workloads       : (N=1, default run) the other BASELINE configs measured the same way in the same process -
+                    cfg2 (p50/p99 chunk latency, host-to-host chunk latency), cfg1, cfg3, cfg5 - and `clustered`:
+                    cfg1's shape on a library of 100 tight clusters (nothing a bf16 screen can certify)
 `--impl reference` times that CPU arm alone on the same config and prints the same line.
 """
 from __future__ import annotations
@@ -53,22 +59,27 @@ WORKLOADS = {
     "real_offline": (1, 450, 3512, "inference.py defaults: T=450 frames per chunk vs N=3512-frame library"),
     "real_realtime": (1, 24, 3512, "realtime_inference.py defaults: T=24 frames per chunk vs N=3512-frame library"),
 }
-
+LATENCY_WORKLOADS = ("cfg2", "real_offline", "real_realtime")
+GRAPH_WORKLOADS = ("cfg1", "cfg2", "real_offline", "real_realtime")
 
 # cfg2 is a latency config: SURVEY §8(d) asks for >= 1000 timed calls
 DEFAULT_STEPS = {"cfg1": 50, "cfg2": 1000, "cfg3": 5, "cfg4": 5, "cfg5": 3, "real_offline": 1000, "real_realtime": 1000}
+EXTRA_WORKLOADS = ("cfg2", "cfg1", "cfg3", "cfg5")       # measured after the headline in the default N=1 run
+PARITY_ROWS = 256
 
 
 def load_traffic(workload: str, world: int):
     """DRAM bytes per launch of the dominant kernel from a committed ncu --set full capture
-    (profiles/traffic_r01.json), or None when this (workload, n_gpus) has not been captured."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    try:
-        with open(p) as f:
-            ent = json.load(f).get(f"{workload}@{world}")
-        return ent["dram_bytes_per_launch"] if ent else None
-    except Exception:
-        return None
+    (profiles/traffic_r02.json, else traffic_r01.json), or None when this (workload, n_gpus) has not been captured."""
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                ent = json.load(f).get(f"{workload}@{world}")
+            if ent:
+                return ent["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    return None
 
 
 def load_peaks():
@@ -251,33 +262,112 @@ def build_library(n_lo, n_hi, seed, device, chunk=250_000):
     return lib
 
 
-def gpu_arm(args):
+def build_clustered(T, N, nclus, noise, seed, device):
+    """cfg1's shape on a library of `nclus` tight clusters (centre + noise * N(0,1)): near-duplicate frames, what
+    silence and sustained vowels look like to a content encoder - nothing a bf16 screen can certify."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    cent = torch.randn(D, nclus, device=device, generator=g)
+    ref = cent[:, torch.randint(0, nclus, (N,), device=device, generator=g)] + noise * torch.randn(D, N, device=device, generator=g)
+    src = cent[:, torch.randint(0, nclus, (T,), device=device, generator=g)] + noise * torch.randn(D, T, device=device, generator=g)
+    return src[None].contiguous(), ref[None].contiguous()
+
+
+class Env:
+    pass
+
+
+def parity_block(env, sharded, lib, src_dev, batched: bool):
+    """256 query frames through the product call vs (a) the exhaustive fp64 scan of every shard (mode="exact")
+    merged across ranks with alive_knn_merge_records, (b) the sequential float32 mean of the winning raw frames
+    assembled with torch ops (each rank contributes the rows it owns; the sum over ranks adds zeros).  Returns
+    the dict printed as `parity`; `ok` False makes the run exit 1."""
     import torch
     import torch.distributed as dist
+    from alive_vc_b200 import _cabi, matching as M
+    from alive_vc_b200.sharded import record_bytes
 
-    import __graft_entry__ as entry
+    dev, world = env.dev, env.world
+    if batched:
+        # cfg5: per-speaker libraries, no exchange step - screen vs exhaustive scan per item, 32 frames per speaker
+        rows_per = 32
+        q = src_dev[:, :, :rows_per].contiguous()
+        out_s, idx_s, sc_s = M.match_packed(q, lib, K, 0.0, "screen", env.variant)
+        out_e, idx_e, sc_e = M.match_packed(q, lib, K, 0.0, "exact", env.variant)
+        rows = q.shape[0] * rows_per
+        i_s, i_e = idx_s.reshape(rows, K), idx_e.reshape(rows, K)
+        same = (i_s == i_e).all(dim=1)
+        tie = (~same) & ((sc_s.reshape(rows, K) - sc_e.reshape(rows, K)).abs() <= 1e-6).all(dim=1)
+        feat_ok = bool(torch.equal(out_s.reshape(rows, D)[same], out_e.reshape(rows, D)[same]))
+        n_same, n_tie = int(same.sum()), int(tie.sum())
+        return {"rows": rows, "index_exact": n_same, "tie_excused": n_tie, "features_bit_exact_rows": n_same if feat_ok else 0,
+                "checker": "exhaustive fp64 scan per speaker (alive_knn_exact)", "ok": n_same + n_tie == rows and feat_ok}
+    t_par = min(PARITY_ROWS, src_dev.shape[2])
+    q = src_dev[:, :, :t_par].contiguous()
+    out, idx = sharded.match(q, K, 0.0, return_indices=True)
+    rows = q.shape[0] * t_par
+    out_rows = out.transpose(1, 2).reshape(rows, D)
+    idx = idx.reshape(rows, K)
+    # (a) exhaustive scan of the local shard, records all-gathered, merged
+    stride = record_bytes(rows, K)
+    rec = torch.empty((stride,), dtype=torch.uint8, device=dev)
+    rec_i = rec[: rows * K * 8].view(torch.int64)
+    rec_s = rec[rows * K * 8: rows * K * 12].view(torch.float32)
+    M.run_match(q, lib, K, 0.0, mode="exact", want_out=False,
+                top_idx=rec_i.view(q.shape[0], t_par, K), top_score=rec_s.view(q.shape[0], t_par, K))
+    if world > 1:
+        gathered = torch.empty((world, stride), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered.view(-1), rec)
+    else:
+        gathered = rec.view(1, stride)
+    want_s = torch.empty((rows, K), dtype=torch.float32, device=dev)
+    want_i = torch.empty((rows, K), dtype=torch.int64, device=dev)
+    _cabi.check(_cabi.load().alive_knn_merge_records(gathered.data_ptr(), stride, world, rows, K, want_s.data_ptr(),
+                                                     want_i.data_ptr(), torch.cuda.current_stream().cuda_stream), "merge_records")
+    same = (idx == want_i).all(dim=1)
+    # a differing row is excused only by a similarity tie within 1e-6: compare the exact scores of OUR frames
+    # (computed by the exact scan as well: every frame's exact score is unique per (query, frame)) position-wise.
+    # Ours are not returned with scores here, so recompute them from the raw frames in float64.
+    n_tie = 0
+    if not bool(same.all()):
+        bad = (~same).nonzero().reshape(-1)
+        qn = torch.nn.functional.normalize(q.transpose(1, 2).reshape(rows, D)[bad].double(), dim=1)
+        mine = torch.zeros((bad.numel(), K), dtype=torch.float64, device=dev)
+        lo, hi = lib.row_base, lib.row_base + lib.n
+        own = (idx[bad] >= lo) & (idx[bad] < hi)
+        loc = (idx[bad] - lo).clamp(0, max(lib.n - 1, 0))
+        fr = torch.nn.functional.normalize(lib.raw[loc].double(), dim=2)                 # [bad, K, D]
+        mine = torch.where(own, (fr * qn[:, None, :]).sum(dim=2), mine)
+        if world > 1:
+            dist.all_reduce(mine)
+        n_tie = int(((mine.float() - want_s[bad]).abs() <= 1e-6).all(dim=1).sum())
+    # (b) features: ((r0 + r1) + r2) + r3 in descending-score order, / k  (alpha = 0)
+    lo, hi = lib.row_base, lib.row_base + lib.n
+    own = (idx >= lo) & (idx < hi)
+    loc = (idx - lo).clamp(0, max(lib.n - 1, 0))
+    picked = torch.where(own[:, :, None], lib.raw[loc] if lib.n > 0 else torch.zeros((rows, K, D), device=dev),
+                         torch.zeros((), device=dev))
+    if world > 1:
+        dist.all_reduce(picked)
+    acc = picked[:, 0].clone()
+    for j in range(1, K):
+        acc = acc + picked[:, j]
+    feat_rows = int((out_rows == acc / K).all(dim=1).sum())
+    n_same = int(same.sum())
+    return {"rows": rows, "index_exact": n_same, "tie_excused": n_tie, "features_bit_exact_rows": feat_rows,
+            "checker": "exhaustive fp64 scan of every shard (alive_knn_exact) merged over ranks; sequential float32 mean of the raw frames",
+            "ok": n_same + n_tie == rows and feat_rows == rows}
+
+
+def measure(env, workload: str, steps: int, warmup: int, headline: bool, clustered=None):
+    """One workload on env.world GPUs -> the dict of its numbers (rank 0; None elsewhere)."""
+    import torch
+    import torch.distributed as dist
     from alive_vc_b200 import matching as M
     from alive_vc_b200.sharded import CudaShardBackend, ShardedLibrary, shard_bounds
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        entry.build()          # no-op when the in-tree .so is current (it travels with the snapshot)
-    if world > 1:
-        dist.barrier()         # nobody loads the library before rank 0 has (re)built it
-    B, T, N, desc = WORKLOADS[args.workload]
-    peaks = load_peaks()
-    variant = args.variant
+    world, rank, dev, args, peaks, variant = env.world, env.rank, env.dev, env.args, env.peaks, env.variant
+    B, T, N, desc = WORKLOADS[workload]
 
     def barrier():
         if world > 1:
@@ -286,7 +376,9 @@ def gpu_arm(args):
 
     # ---- resident data: the (sharded) packed library, device queries, pinned host queries ----
     g = torch.Generator(device=dev).manual_seed(args.seed)
-    if args.workload == "cfg5":
+    sharded = None
+    batched = workload == "cfg5"
+    if batched:
         if world > 1:
             per = B // world
             my_items = list(range(rank * per, (rank + 1) * per))
@@ -302,7 +394,6 @@ def gpu_arm(args):
                 x = torch.randn(D, c1 - c0, device=dev, generator=gg)
                 M.pack_into(lib, i * N + c0, x)
                 del x
-        libs = [lib]
         src_dev = torch.randn(len(my_items), D, T, device=dev, generator=g)
 
         def step(src):
@@ -314,59 +405,58 @@ def gpu_arm(args):
         parallelism = f"{len(my_items)} speakers per GPU, no collective"
     else:
         lo, hi = shard_bounds(N, world, rank)
-        lib = build_library(lo, hi, args.seed, dev)
+        if clustered is not None:
+            src_dev, ref = build_clustered(T, N, clustered["clusters"], clustered["noise"], args.seed, dev)
+            lib = M.pack_library(ref)
+            del ref
+        else:
+            lib = build_library(lo, hi, args.seed, dev)
+            src_dev = torch.randn(B, D, T, device=dev, generator=g)
         sharded = ShardedLibrary(CudaShardBackend(lib, "screen", variant), lib.n, lo, N, None,
                                  peer_memory=(args.exchange == "peer"))
-        src_dev = torch.randn(B, D, T, device=dev, generator=g)
         if world > 1:
             dist.broadcast(src_dev, 0)
 
         def step(src):
             return sharded.match(src, K, 0.0)
-        if args.workload in ("cfg1", "cfg2", "real_offline", "real_realtime") and world == 1 and not args.no_graph:
-            # fixed-shape chunks (inference.py / realtime_inference.py call the match once per chunk with
-            # the same T): pre-allocated buffers, the whole pipeline replayed as one CUDA graph
-            streamer = M.StreamingMatcher(lib, T, K, 0.0, batch=B, mode="screen", variant=variant)
-
-            def step(src):                                             # noqa: F811
-                return streamer(src)
         units_per_step = B * T
         n_local = hi - lo
         scaling = "strong"
-        parallelism = f"library rows sharded x{world}" + (
-            "" if world == 1 else
-            ", all-gather top-k + one peer-memory (NVLink) gather kernel" if args.exchange == "peer" else
-            ", all-gather top-k + reduce-scatter rows + all-gather result")
-    src_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
-    src_host.copy_(src_dev)
-    # the result is a transposed view of a contiguous [B,T,D] block (like the reference's); the pinned
-    # host buffer has the same strides, so the device->host read is one plain memcpy
-    _b, _d, _t = src_dev.shape
-    out_host = torch.empty((_b, _t, _d), dtype=torch.float32).pin_memory().transpose(1, 2)
+        exchange = "one fused merge + peer-memory (NVLink, CUDA IPC) gather kernel" if sharded.peers is not None else \
+            "merge + reduce-scatter of the owned rows + all-gather of the result (NCCL)"
+        parallelism = f"library rows sharded x{world}" + ("" if world == 1 else f", one all-gather of the top-k records, {exchange}")
+    streaming = workload in GRAPH_WORKLOADS and world == 1 and not args.no_graph and not batched
+    if streaming:
+        # fixed-shape chunks (inference.py / realtime_inference.py call the match once per chunk with
+        # the same T): pre-allocated buffers, the whole pipeline replayed as one CUDA graph
+        streamer = M.StreamingMatcher(lib, T, K, 0.0, batch=B, mode="screen", variant=variant)
+
+        def step(src):                                             # noqa: F811
+            return streamer(src)
+    latency_workload = workload in LATENCY_WORKLOADS
     barrier()
 
     # ---- device-resident timing ----
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(src_dev)
     barrier()
     M.search_events = []
     launches0 = M.launch_count
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lat = []
     barrier()
     e0.record()
-    latency_workload = args.workload in ("cfg2", "real_offline", "real_realtime")
     if latency_workload:
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         evs[0].record()
-        for i in range(args.steps):
+        for i in range(steps):
             step(src_dev)
             evs[i + 1].record()
     else:
-        for _ in range(args.steps):
+        for _ in range(steps):
             step(src_dev)
     e1.record()
     barrier()
@@ -377,34 +467,56 @@ def gpu_arm(args):
     if not search_ms:
         # graph-replayed path: the kernel cannot be bracketed inside the graph, so time the same
         # launches eagerly right after the timed region (same buffers, same clocks)
-        for _ in range(min(args.steps, 50)):
+        for _ in range(min(steps, 50)):
             sharded.match(src_dev, K, 0.0)
         torch.cuda.synchronize()
         search_ms = [a.elapsed_time(b) for a, b in M.search_events]
     M.search_events = None
     if latency_workload:
-        lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
-    fallback = M.last_info.fallback_queries() if M.last_info is not None else 0
+        lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    info = M.last_info
+    fallback = info.fallback_queries() if info is not None else 0
+    exact_scan = info.exact_scan_queries() if info is not None else 0
     if world > 1:
         tmax = torch.tensor([ms_total], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_total = float(tmax.item())
-    ms_per_step = ms_total / args.steps
+    ms_per_step = ms_total / steps
     value = units_per_step / (ms_per_step * 1e-3)
 
     # ---- end-to-end: host buffers through the public API ----
-    streaming = args.workload in ("cfg1", "cfg2", "real_offline", "real_realtime") and world == 1 and not args.no_graph
+    scattered = world > 1 and not batched and B == 1
+    if scattered:
+        # every query byte crosses PCIe once: this rank's T/world slice in, its slice of the result out
+        q_lo, q_hi = shard_bounds(T, world, rank)
+        src_host = torch.empty((1, D, q_hi - q_lo), dtype=torch.float32).pin_memory()
+        src_host.copy_(src_dev[:, :, q_lo:q_hi])
+        out_host = torch.empty((1, q_hi - q_lo, D), dtype=torch.float32).pin_memory().transpose(1, 2)
 
-    def e2e_step():
-        # the streaming matcher copies the pinned host chunk straight into its static input buffer
-        s = src_host if streaming else src_host.to(dev, non_blocking=True)
-        o = step(s)
-        out_host.copy_(o, non_blocking=True)
-    for _ in range(min(args.warmup, 3)):
+        def e2e_step():
+            s = src_host.to(dev, non_blocking=True)
+            o = sharded.match(s, K, 0.0, scattered=True, t_total=T)
+            out_host.copy_(o, non_blocking=True)
+        io_bytes = T * D * 4                       # whole job, all ranks together
+    else:
+        src_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()
+        src_host.copy_(src_dev)
+        # the result is a transposed view of a contiguous [B,T,D] block (like the reference's); the pinned
+        # host buffer has the same strides, so the device->host read is one plain memcpy
+        _b, _d, _t = src_dev.shape
+        out_host = torch.empty((_b, _t, _d), dtype=torch.float32).pin_memory().transpose(1, 2)
+
+        def e2e_step():
+            # the streaming matcher copies the pinned host chunk straight into its static input buffer
+            s = src_host if streaming else src_host.to(dev, non_blocking=True)
+            o = step(s)
+            out_host.copy_(o, non_blocking=True)
+        io_bytes = src_host.numel() * 4 * (world if batched else 1)
+    for _ in range(min(warmup, 3)):
         e2e_step()
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     e1.record()
     barrier()
@@ -413,8 +525,7 @@ def gpu_arm(args):
         tmax = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmax.item())
-    e2e_value = units_per_step / (e2e_ms / args.steps * 1e-3)
-    io_bytes = src_host.numel() * 4
+    e2e_value = units_per_step / (e2e_ms / steps * 1e-3)
 
     # latency workloads: the synchronous host-to-host chunk time of the realtime loop
     # (realtime_inference.py:158-176) - pinned buffers, ONE graph (H2D + pipeline + D2H), one event wait
@@ -425,21 +536,27 @@ def gpu_arm(args):
         chunk = src_host.clone()
         for _ in range(20):
             hm(chunk)
-        for _ in range(min(args.steps, 2000)):
+        for _ in range(min(steps, 2000)):
             t0 = time.perf_counter()
             hm(chunk)
             host_lat.append((time.perf_counter() - t0) * 1e3)
         host_lat.sort()
+        del hm
 
+    # ---- parity of what was just timed (every rank takes part; rank 0 reports) ----
+    parity = parity_block(env, sharded, lib, src_dev, batched)
+    if world > 1:
+        flag = torch.tensor([1 if parity["ok"] else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity["ok"] = bool(flag.item())
+
+    res = None
     if rank == 0:
         # roofline of the dominant kernel: algorithmic flops of ONE alive_knn_search launch
         # (2 * T * N_local * D) over its average CUDA-event duration
-        if args.workload == "cfg5":
-            flops_per_launch = 2.0 * lib.items * T * N * D
-        else:
-            flops_per_launch = 2.0 * B * T * n_local * D
+        flops_per_launch = 2.0 * (lib.items if batched else B) * T * n_local * D
         avg_search_ms = sum(search_ms) / max(1, len(search_ms))
-        if args.workload == "cfg5":
+        if batched:
             search_kernel = "knn_search_kernel"
         else:
             _plan = M.make_plan(B * T, n_local, D, dev, variant)
@@ -448,162 +565,270 @@ def gpu_arm(args):
             bytes_per_launch = float(n_local) * D * 2
             achieved = bytes_per_launch / (avg_search_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(args.workload, world),
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(workload, world),
                     "kernel": search_kernel, "avg_kernel_ms": avg_search_ms, "peak_source": peaks["source"]}
         else:
             achieved = flops_per_launch / (avg_search_ms * 1e-3) / 1e12
             # conservative denominator: the burst cuBLAS figure, even though the kernel runs
             # back-to-back under the power cap (frac_of_sustained is reported beside it)
-            sustained = False
             peak = peaks["bf16_burst"]
             roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": load_traffic(args.workload, world), "kernel": search_kernel,
-                    "avg_kernel_ms": avg_search_ms,
+                    "frac": achieved / peak, "traffic": load_traffic(workload, world) if clustered is None else None,
+                    "kernel": search_kernel, "avg_kernel_ms": avg_search_ms,
                     "kernel_share_of_step": avg_search_ms / ms_per_step,
-                    "peak_kind": "sustained" if sustained else "burst", "peak_source": peaks["source"],
+                    "peak_kind": "burst", "peak_source": peaks["source"],
                     "frac_of_burst": achieved / peaks["bf16_burst"],
                     "frac_of_sustained": achieved / peaks["bf16_sustained"]}
-        # K4 alone (north_star: "fraction of HBM bandwidth for the gather"): the standalone gather-mean
-        # kernel on this step's own neighbour indices; in the pipeline the same arithmetic is fused
-        # into finish_kernel.  Algorithmic bytes per query frame: k*D*4 read + D*4 write (+ D*4 query).
-        gather_roof = None
-        if args.workload != "cfg5" and world == 1:   # (cfg5: batched libraries, skipped)
-            info = M.last_info
-            ws = getattr(info, "_workspace", None)
-            if ws is not None:
-                rows = B * T
-                q_view = M.PackedFrames(n=rows, d=D, raw=ws[: rows * D * 4].view(torch.float32).view(rows, D),
-                                        norms=None, packed=None, err=None, stats=None)
-                _, g_idx, _ = M.run_match(src_dev, lib, K, 0.0, "screen", variant, want_out=False)
-                g_out = torch.empty((rows, D), dtype=torch.float32, device=dev)
-                for _ in range(3):
-                    M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
-                torch.cuda.synchronize()
-                ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = 20
-                ge0.record()
-                for _ in range(reps):
-                    M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
-                ge1.record()
-                torch.cuda.synchronize()
-                g_ms = ge0.elapsed_time(ge1) / reps
-                g_bytes = rows * (K * D * 4 + D * 4 + D * 4)
-                # what the memory system gives ANY kernel for this access pattern: torch's own row gather of
-                # the same T*k random 3 KB rows (read + write T*k rows) - the practical ceiling beside the
-                # streaming-copy peak
-                flat_idx = g_idx.reshape(-1)
-                sel_out = torch.empty((flat_idx.numel(), D), dtype=torch.float32, device=dev)
-                for _ in range(3):
-                    torch.index_select(lib.raw, 0, flat_idx, out=sel_out)
-                torch.cuda.synchronize()
-                ge0.record()
-                for _ in range(reps):
-                    torch.index_select(lib.raw, 0, flat_idx, out=sel_out)
-                ge1.record()
-                torch.cuda.synchronize()
-                sel_ms = ge0.elapsed_time(ge1) / reps
-                sel_gbs = 2.0 * flat_idx.numel() * D * 4 / (sel_ms * 1e-3) / 1e9
-                del sel_out
-                gather_roof = {"bound": "hbm", "kernel": "gather_mean_kernel", "achieved": g_bytes / (g_ms * 1e-3) / 1e9,
-                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                               "avg_kernel_ms": g_ms, "bytes_per_query_frame": g_bytes // rows,
-                               "torch_index_select_gbs": sel_gbs,
-                               "note": "standalone K4 on this step's indices; random 3 KB rows of the raw library; "
-                                       "torch_index_select_gbs = torch's row gather of the same rows (read + write), "
-                                       "the practical ceiling of this access pattern"}
-        # K1 alone (once per library, generate_voice_library.py / load time): the pack kernel on a fresh
-        # channel-major [D, n] chunk far larger than L2.  Algorithmic bytes per frame: D*(4 read + 4 raw
-        # + 2 packed) + 8 (norm, err) = 7,688 B.
-        pack_roof = None
-        if world == 1:
-            pn = 250_000
-            px = torch.randn(D, pn, device=dev)
-            pdst = M.alloc_packed(pn, D, dev)
-            for _ in range(2):
-                M.pack_into(pdst, 0, px)
-            torch.cuda.synchronize()
-            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
-            pe0.record()
-            for _ in range(reps):
-                M.pack_into(pdst, 0, px)
-            pe1.record()
-            torch.cuda.synchronize()
-            p_ms = pe0.elapsed_time(pe1) / reps
-            p_bytes = pn * (D * 10 + 8)
-            # the same frames as a row-major producer would hand them over (pack_rows): pack_rm_kernel
-            px_rows = px.t().contiguous()
-            for _ in range(2):
-                M.pack_into(pdst, 0, px_rows.t())
-            pe0.record()
-            for _ in range(reps):
-                M.pack_into(pdst, 0, px_rows.t())
-            pe1.record()
-            torch.cuda.synchronize()
-            p_ms_rows = pe0.elapsed_time(pe1) / reps
-            # torch's own transposing copy of the same chunk ([768, n] -> [n, 768], read + write 4 B per element):
-            # what a library kernel gets out of the channel-major access pattern
-            t_out = torch.empty((pn, D), dtype=torch.float32, device=dev)
-            for _ in range(2):
-                t_out.copy_(px.t())
-            pe0.record()
-            for _ in range(reps):
-                t_out.copy_(px.t())
-            pe1.record()
-            torch.cuda.synchronize()
-            t_gbs = 2.0 * pn * D * 4 / (pe0.elapsed_time(pe1) / reps * 1e-3) / 1e9
-            del t_out
-            pack_roof = {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": p_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "avg_kernel_ms": p_ms, "bytes_per_frame": D * 10 + 8, "frames": pn,
-                         "row_major": {"kernel": "pack_rm_kernel", "achieved": p_bytes / (p_ms_rows * 1e-3) / 1e9,
-                                       "frac": p_bytes / (p_ms_rows * 1e-3) / 1e9 / peaks["hbm_gbs"], "avg_kernel_ms": p_ms_rows},
-                         "torch_transpose_copy_gbs": t_gbs,
-                         "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse); "
-                                 "row_major = the same frames as [250k, 768] rows"}
-            del px, pdst, px_rows
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            cpu = run_cpu_arm(args.workload, 3, 1)
-        eager = None
-        if world == 1 and args.torch_eager:
-            eager = run_torch_eager_gpu(args.workload, dev)
-        line = {
-            "metric": "query_frames_per_sec_matched_k4", "value": value, "unit": "query_frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": desc, "B": B, "T": T, "N": N, "D": D, "k": K, "parallelism": parallelism,
+        res = {
+            "value": value, "unit": "query_frames/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+            "scaling": scaling,
+            "config": {"workload": desc if clustered is None else
+                       f"clustered: cfg1 shape (T={T}, N={N}), {clustered['clusters']} clusters, noise {clustered['noise']}",
+                       "B": B, "T": T, "N": N, "D": D, "k": K, "parallelism": parallelism,
                        "l2": "library (bf16 %.1f GB per GPU) is far larger than L2, no flush needed"
                              % (n_local * D * 2 / 1e9) if n_local * D * 2 > 256e6 else
                              "library smaller than 2x L2: numbers are warm-L2 steady state of a resident library",
-                       "variant": variant, "fallback_queries_last_step": fallback,
+                       "variant": variant, "fallback_queries_last_step": fallback, "exact_scan_queries_last_step": exact_scan,
                        "api": "StreamingMatcher (one CUDA graph per chunk)" if streaming else
-                              ("match_packed on pack_libraries (one launch for all speakers)" if args.workload == "cfg5" else "ShardedLibrary.match")},
+                              ("match_packed on pack_libraries (one launch for all speakers)" if batched else "ShardedLibrary.match")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "query_frames/s", "h2d_bytes_per_step": io_bytes,
-                    "d2h_bytes_per_step": io_bytes, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": io_bytes, "ms_per_step": e2e_ms / steps,
+                    "path": "per rank: H2D of its T/N query slice -> all-gather over NVLink -> match -> D2H of its T/N result slice"
+                            if scattered else "H2D of the queries -> match -> D2H of the result"},
             "gpu_launches": launches,
             "roofline": roof,
-            "cpu_baseline": cpu,
+            "parity": parity,
         }
-        if eager is not None:
-            line["torch_eager_gpu"] = eager
-        if gather_roof is not None:
-            line["roofline_gather"] = gather_roof
-        if pack_roof is not None:
-            line["roofline_pack"] = pack_roof
         if lat:
-            line["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
-                                  "min": lat[0]}
+            res["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
+                                 "min": lat[0]}
         if host_lat:
-            line["host_chunk_latency_ms"] = {"p50": host_lat[len(host_lat) // 2],
-                                             "p99": host_lat[min(len(host_lat) - 1, int(len(host_lat) * 0.99))],
-                                             "min": host_lat[0], "timer": "perf_counter around one blocking call"}
+            res["host_chunk_latency_ms"] = {"p50": host_lat[len(host_lat) // 2],
+                                            "p99": host_lat[min(len(host_lat) - 1, int(len(host_lat) * 0.99))],
+                                            "min": host_lat[0], "timer": "perf_counter around one blocking call"}
+        if headline:
+            g_roof = gather_roofline(env, lib, src_dev, B, T) if (not batched and world == 1) else None
+            if g_roof is not None:
+                res["roofline_gather"] = g_roof
+    # ---- release everything this workload held (the next one may need all of HBM) ----
+    if sharded is not None:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sharded.close()
+    del lib, src_dev, sharded, info
+    if streaming:
+        del streamer
+    M.clear_pack_cache()
+    M.last_info = None
+    torch.cuda.empty_cache()
+    return res
+
+
+def gather_roofline(env, lib, src_dev, B, T):
+    """K4 alone (north_star: "fraction of HBM bandwidth for the gather"): the standalone gather-mean kernel on this
+    step's own neighbour indices; in the pipeline the same arithmetic is fused into finish_kernel.  Algorithmic
+    bytes per query frame: k*D*4 read + D*4 written = 15,360 B (alpha = 0: the query row is not read)."""
+    import torch
+    from alive_vc_b200 import matching as M
+
+    dev, peaks = env.dev, env.peaks
+    rows = B * T
+    _, g_idx, _ = M.run_match(src_dev, lib, K, 0.0, "screen", env.variant, want_out=False)
+    ws, off = M.last_info._workspace, M.last_info._offsets
+    q_view = M.PackedFrames(n=rows, d=D, raw=ws[off[0]: off[0] + rows * D * 4].view(torch.float32).view(rows, D),
+                            norms=ws[off[1]: off[1] + rows * 4].view(torch.float32), packed=None, err=None, stats=None)
+    g_out = torch.empty((rows, D), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
+    torch.cuda.synchronize()
+    ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    ge0.record()
+    for _ in range(reps):
+        M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
+    ge1.record()
+    torch.cuda.synchronize()
+    g_ms = ge0.elapsed_time(ge1) / reps
+    g_bytes = rows * (K * D * 4 + D * 4)
+    # what the memory system gives ANY kernel for this access pattern: torch's own row gather of
+    # the same T*k random 3 KB rows (read + write T*k rows) - the practical ceiling beside the
+    # streaming-copy peak
+    flat_idx = g_idx.reshape(-1)
+    sel_out = torch.empty((flat_idx.numel(), D), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        torch.index_select(lib.raw, 0, flat_idx, out=sel_out)
+    torch.cuda.synchronize()
+    ge0.record()
+    for _ in range(reps):
+        torch.index_select(lib.raw, 0, flat_idx, out=sel_out)
+    ge1.record()
+    torch.cuda.synchronize()
+    sel_ms = ge0.elapsed_time(ge1) / reps
+    sel_gbs = 2.0 * flat_idx.numel() * D * 4 / (sel_ms * 1e-3) / 1e9
+    del sel_out
+    return {"bound": "hbm", "kernel": "gather_mean_warp_kernel", "achieved": g_bytes / (g_ms * 1e-3) / 1e9,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "avg_kernel_ms": g_ms, "bytes_per_query_frame": g_bytes // rows,
+            "torch_index_select_gbs": sel_gbs,
+            "note": "standalone K4 on this step's indices; random 3 KB rows of the raw library; "
+                    "torch_index_select_gbs = torch's row gather of the same rows (read + write), "
+                    "the practical ceiling of this access pattern"}
+
+
+def pack_roofline(env):
+    """K1 alone (once per library, generate_voice_library.py / load time): the pack kernel on a fresh
+    channel-major [D, n] chunk far larger than L2.  Algorithmic bytes per frame: D*(4 read + 4 raw
+    + 2 packed) + 8 (norm, err) = 7,688 B."""
+    import torch
+    from alive_vc_b200 import matching as M
+
+    dev, peaks = env.dev, env.peaks
+    pn = 250_000
+    px = torch.randn(D, pn, device=dev)
+    pdst = M.alloc_packed(pn, D, dev)
+    for _ in range(2):
+        M.pack_into(pdst, 0, px)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    pe0.record()
+    for _ in range(reps):
+        M.pack_into(pdst, 0, px)
+    pe1.record()
+    torch.cuda.synchronize()
+    p_ms = pe0.elapsed_time(pe1) / reps
+    p_bytes = pn * (D * 10 + 8)
+    # the same frames as a row-major producer would hand them over (pack_rows): pack_rm_kernel
+    px_rows = px.t().contiguous()
+    for _ in range(2):
+        M.pack_into(pdst, 0, px_rows.t())
+    pe0.record()
+    for _ in range(reps):
+        M.pack_into(pdst, 0, px_rows.t())
+    pe1.record()
+    torch.cuda.synchronize()
+    p_ms_rows = pe0.elapsed_time(pe1) / reps
+    # torch's own transposing copy of the same chunk ([768, n] -> [n, 768], read + write 4 B per element):
+    # what a library kernel gets out of the channel-major access pattern
+    t_out = torch.empty((pn, D), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        t_out.copy_(px.t())
+    pe0.record()
+    for _ in range(reps):
+        t_out.copy_(px.t())
+    pe1.record()
+    torch.cuda.synchronize()
+    t_gbs = 2.0 * pn * D * 4 / (pe0.elapsed_time(pe1) / reps * 1e-3) / 1e9
+    del t_out, px, pdst, px_rows
+    torch.cuda.empty_cache()
+    return {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": p_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "avg_kernel_ms": p_ms, "bytes_per_frame": D * 10 + 8, "frames": pn,
+            "row_major": {"kernel": "pack_rm_kernel", "achieved": p_bytes / (p_ms_rows * 1e-3) / 1e9,
+                          "frac": p_bytes / (p_ms_rows * 1e-3) / 1e9 / peaks["hbm_gbs"], "avg_kernel_ms": p_ms_rows},
+            "torch_transpose_copy_gbs": t_gbs,
+            "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse); "
+                    "row_major = the same frames as [250k, 768] rows"}
+
+
+def summary_of(res):
+    """the per-workload entry of `workloads`"""
+    keep = ("value", "unit", "ms_per_step", "steps", "latency_ms", "host_chunk_latency_ms", "gpu_launches", "parity")
+    out = {k: res[k] for k in keep if k in res}
+    out["e2e"] = res["e2e"]
+    r = res["roofline"]
+    out["roofline"] = {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "avg_kernel_ms",
+                                           "frac_of_sustained", "kernel_share_of_step") if k in r}
+    out["config"] = {k: res["config"][k] for k in ("workload", "B", "T", "N", "api", "fallback_queries_last_step",
+                                                    "exact_scan_queries_last_step")}
+    out["clocks"] = res["clocks"]
+    return out
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    env = Env()
+    env.args = args
+    env.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.rank = rank = int(os.environ.get("RANK", "0"))
+    env.local_rank = local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    env.dev = dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()          # no-op when the in-tree .so is current (it travels with the snapshot)
+    if world > 1:
+        dist.barrier()         # nobody loads the library before rank 0 has (re)built it
+    env.peaks = load_peaks()
+    env.variant = args.variant
+
+    res = measure(env, args.workload, args.steps, args.warmup, headline=True)
+    ok = True
+    line = None
+    if rank == 0:
+        ok = res["parity"]["ok"]
+        line = {
+            "metric": "query_frames_per_sec_matched_k4", "value": res["value"], "unit": "query_frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],
+            "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "parity": res["parity"],
+        }
+        for key in ("latency_ms", "host_chunk_latency_ms", "roofline_gather"):
+            if key in res:
+                line[key] = res[key]
+        if world == 1:
+            line["roofline_pack"] = pack_roofline(env)
+            line["cpu_baseline"] = None if args.no_cpu else run_cpu_arm(args.workload, 3, 1)
+            if args.torch_eager:
+                line["torch_eager_gpu"] = run_torch_eager_gpu(args.workload, dev)
+    # ---- the other BASELINE configs, same process, same measurement (default N=1 run of the headline) ----
+    if world == 1 and args.workload == "cfg4" and not args.no_extras:
+        extras = {}
+        for w in EXTRA_WORKLOADS:
+            try:
+                r = measure(env, w, DEFAULT_STEPS[w], 3, headline=False)
+            except Exception as e:       # noqa: BLE001 - an extra must never take the headline down with it
+                extras[w] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+                continue
+            extras[w] = summary_of(r)
+            ok = ok and r["parity"]["ok"]
+            if not args.no_cpu:
+                extras[w]["cpu_baseline"] = run_cpu_arm(w, 2, 1)
+        # clustered libraries: cfg1's shape, 100 clusters of ~1000 near-identical frames
+        for noise in (0.2, 0.5):
+            try:
+                r = measure(env, "cfg1", 20, 3, headline=False, clustered={"clusters": 100, "noise": noise})
+                ent = summary_of(r)
+                ent["slowdown_vs_random_cfg1"] = (r["ms_per_step"] / extras["cfg1"]["ms_per_step"]
+                                                  if "ms_per_step" in extras.get("cfg1", {}) else None)
+                extras[f"clustered_noise{noise}"] = ent
+                ok = ok and r["parity"]["ok"]
+            except Exception as e:       # noqa: BLE001
+                extras[f"clustered_noise{noise}"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+        line["workloads"] = extras
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        print("bench.py: PARITY FAILURE (see the `parity` entries above)", file=sys.stderr, flush=True)
+        sys.exit(1)
 
 
 def main():
@@ -617,8 +842,11 @@ def main():
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="cfg1/cfg2: do not use the CUDA-graph streaming matcher")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
-                    help="multi-GPU row exchange: NCCL reduce-scatter/all-gather, or one gather kernel over CUDA-IPC peer memory")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default cfg4 run at N=1: skip the other BASELINE configs (`workloads` in the JSON line)")
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
+                    help="multi-GPU row exchange: one fused merge+gather kernel over CUDA-IPC peer memory (falls back "
+                         "to NCCL when the mapping fails), or always the NCCL reduce-scatter/all-gather")
     ap.add_argument("--torch-eager", action="store_true",
                     help="also time the reference's torch ops on the GPU (secondary line, where it fits)")
     args = ap.parse_args()

@@ -24,7 +24,7 @@ def build(force: bool = False) -> str:
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     tmp = LIB + ".tmp"
-    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", "-o", tmp, SRC, "-lm"]
+    cmd = ["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", "-o", tmp, SRC, "-lm"]
     try:
         res = subprocess.run(cmd, capture_output=True, text=True)
         err = res.stdout + res.stderr if res.returncode != 0 else None
@@ -42,27 +42,34 @@ def _load():
     global _lib
     if _lib is None:
         lib = ctypes.CDLL(build())
-        lib.alive_oracle_match.restype = ctypes.c_int
-        lib.alive_oracle_match.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 6 + [
-            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.alive_oracle_match2.restype = ctypes.c_int
+        lib.alive_oracle_match2.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 6 + [
+            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
         _lib = lib
     return _lib
 
 
-def match_features_c(source, reference, k: int = 4, alpha: float = 0.0, return_indices: bool = False):
+def match_features_c(source, reference, k: int = 4, alpha: float = 0.0, return_indices: bool = False,
+                     rows: bool = False):
     """module/common.py:96-109 through the C restatement: source [B,D,T], reference [B,D,N] (or [1,D,N], the
-    shared library of VoiceLibrary.match) -> out [B,D,T] float32 (+ idx [B,T,k] int64, val [B,T,k])."""
+    shared library of VoiceLibrary.match) -> out [B,D,T] float32 (+ idx [B,T,k] int64, val [B,T,k]).
+    rows=True: the same frames handed over frame-major - source [B,T,D], reference [B,N,D] (or [1,N,D]),
+    out [B,T,D] (what the GPU side keeps; spares the large parity tests two multi-GB transposes)."""
     src = np.ascontiguousarray(source, dtype=np.float32)
     ref = np.ascontiguousarray(reference, dtype=np.float32)
-    B, D, T = src.shape
-    RB, D2, N = ref.shape
+    if rows:
+        B, T, D = src.shape
+        RB, N, D2 = ref.shape
+    else:
+        B, D, T = src.shape
+        RB, D2, N = ref.shape
     if D2 != D or (RB != B and RB != 1):
         raise RuntimeError("batch1 and batch2 must have same batch size")
-    out = np.empty((B, D, T), dtype=np.float32)
+    out = np.empty(src.shape, dtype=np.float32)
     idx = np.empty((B, T, k), dtype=np.int64)
     val = np.empty((B, T, k), dtype=np.float32)
-    rc = _load().alive_oracle_match(src.ctypes.data, ref.ctypes.data, B, RB, D, T, N, k, float(alpha),
-                                    out.ctypes.data, idx.ctypes.data, val.ctypes.data)
+    rc = _load().alive_oracle_match2(src.ctypes.data, ref.ctypes.data, B, RB, D, T, N, k, float(alpha),
+                                     out.ctypes.data, idx.ctypes.data, val.ctypes.data, 1 if rows else 0)
     if rc == -1:
         raise RuntimeError("selected index k out of range")
     if rc == -2:

@@ -84,3 +84,29 @@ def test_match_rows_host_checks_without_a_gpu():
         pack_rows(torch.randn(20, 768))
     with pytest.raises(RuntimeError, match="no CPU path"):
         match_rows(torch.randn(5, 768), torch.randn(20, 768))
+
+
+def test_custom_ops_are_registered_and_traceable_without_a_gpu():
+    """north_star: "a thin C-ABI torch custom op".  The ops exist in the dispatcher with a fake (meta) kernel, so
+    shape propagation / tracing needs neither a GPU nor the CUDA library."""
+    from alive_vc_b200 import ops   # noqa: F401  (registers the ops)
+    op = torch.ops.alive_vc_b200.knn_match.default
+    assert "reference_grad" in str(op._schema)
+    src = torch.empty(3, 768, 11, device="meta", dtype=torch.float16)
+    ref = torch.empty(1, 768, 500, device="meta")
+    out, idx, score = op(src, ref, 4, 0.0, "auto", 0, False)
+    assert tuple(out.shape) == (3, 11, 768) and out.dtype == torch.float32
+    assert tuple(idx.shape) == (3, 11, 4) and idx.dtype == torch.int64 and tuple(score.shape) == (3, 11, 4)
+    g = torch.ops.alive_vc_b200.knn_scatter_grad.default(torch.empty(33, 768, device="meta"),
+                                                         torch.empty(33, 4, device="meta", dtype=torch.int64), 500, 0.25)
+    assert tuple(g.shape) == (500, 768)
+    # no CPU kernel: the op itself refuses CPU tensors (the public wrappers raise their own message first)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        op(torch.randn(1, 768, 3), torch.randn(1, 768, 20), 4, 0.0, "auto", 0, False)
+
+
+def test_record_layout_of_the_sharded_exchange():
+    from alive_vc_b200.sharded import record_bytes
+    assert record_bytes(10_000, 4) == 480_000 and record_bytes(5, 3) == 192 and record_bytes(1, 1) == 16
+    for t, k in ((7, 3), (1250, 4), (33, 8)):
+        assert record_bytes(t, k) >= t * k * 12 and record_bytes(t, k) % 16 == 0
