@@ -28,7 +28,7 @@ EXPORTS = [
     "alive_knn_exact", "alive_knn_merge", "alive_knn_gather_mean", "alive_knn_gather_rows",
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
     "alive_knn_finish", "alive_knn_gather_mean_peers", "alive_knn_ipc_export", "alive_knn_ipc_open",
-    "alive_knn_ipc_close", "alive_knn_merge_records", "alive_knn_merge_gather",
+    "alive_knn_ipc_close", "alive_knn_merge_records", "alive_knn_merge_gather", "alive_knn_match_packed",
 ]
 
 
@@ -175,6 +175,9 @@ def _declare(lib):
     lib.alive_knn_ipc_close.argtypes = [_vp]
     lib.alive_knn_match_layout.restype = ctypes.c_int
     lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
+    lib.alive_knn_match_packed.restype = ctypes.c_int
+    lib.alive_knn_match_packed.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(Library), _i32, _f32, _i32,
+                                           _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]
     lib.alive_knn_match.restype = ctypes.c_int
     lib.alive_knn_match.argtypes = [_vp, _i32, _i32, _i64, _i64, _i64, ctypes.POINTER(Library), _i32, _f32, _i32,
                                     _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]

@@ -130,13 +130,53 @@ extern "C" int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_
   return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets12, nullptr);
 }
 
+namespace alive {
+namespace {
+// queries that arrive already packed (alive_knn_match_packed): the buffers K1 would have written
+struct PackedQueries {
+  const float* raw;
+  const float* norm;
+  const uint16_t* packed;
+  const float* err;
+};
+int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
+               int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max, int32_t mode,
+               int32_t num_sms, int32_t variant, void* workspace, size_t workspace_bytes, float* out, int64_t* top_idx,
+               float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream);
+}  // namespace
+}  // namespace alive
+
 extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
                                int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha,
                                int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
                                size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
                                void* ev_search_start, void* ev_search_stop, alive_stream_t stream) {
-  using namespace alive;
-  ALIVE_REQUIRE(source && lib && workspace && top_idx && top_score, "alive_knn_match: NULL argument");
+  ALIVE_REQUIRE(source != nullptr, "alive_knn_match: NULL argument");
+  return alive::match_impl(source, nullptr, batch, t, stride_b, stride_t, stride_d, lib, k, alpha, r_max, mode, num_sms,
+                           variant, workspace, workspace_bytes, out, top_idx, top_score, ev_search_start, ev_search_stop,
+                           stream);
+}
+
+extern "C" int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16_t* q_packed,
+                                      const float* q_err, int32_t batch, int32_t t, const alive_knn_library_t* lib,
+                                      int32_t k, float alpha, int32_t r_max, int32_t mode, int32_t num_sms,
+                                      int32_t variant, void* workspace, size_t workspace_bytes, float* out,
+                                      int64_t* top_idx, float* top_score, alive_stream_t stream) {
+  ALIVE_REQUIRE(q_raw && q_norm && q_packed && q_err, "alive_knn_match_packed: NULL argument");
+  ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(q_packed)) & 15) == 0,
+                "alive_knn_match_packed: q_raw and q_packed must be 16-byte aligned");
+  const alive::PackedQueries pq{q_raw, q_norm, q_packed, q_err};
+  return alive::match_impl(nullptr, &pq, batch, t, 0, 0, 0, lib, k, alpha, r_max, mode, num_sms, variant, workspace,
+                           workspace_bytes, out, top_idx, top_score, nullptr, nullptr, stream);
+}
+
+namespace alive {
+namespace {
+int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
+               int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max, int32_t mode,
+               int32_t num_sms, int32_t variant, void* workspace, size_t workspace_bytes, float* out, int64_t* top_idx,
+               float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream) {
+  ALIVE_REQUIRE((source || pq) && lib && workspace && top_idx && top_score, "alive_knn_match: NULL argument");
   ALIVE_REQUIRE(batch >= 1 && t >= 1, "alive_knn_match: empty query batch");
   ALIVE_REQUIRE(static_cast<int64_t>(batch) * t < (1ll << 31), "alive_knn_match: too many query frames");
   ALIVE_REQUIRE(k >= 1 && k <= lib->n, "selected index k out of range");
@@ -161,10 +201,10 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
                 "alive_knn_match: workspace too small (%zu < %lld)", workspace_bytes, static_cast<long long>(off[kOffTotal]));
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "alive_knn_match: workspace must be 256-byte aligned");
   char* ws = static_cast<char*>(workspace);
-  float* q_raw = reinterpret_cast<float*>(ws + off[kOffQRaw]);
-  float* q_norm = reinterpret_cast<float*>(ws + off[kOffQNorm]);
-  uint16_t* q_packed = reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]);
-  float* q_err = reinterpret_cast<float*>(ws + off[kOffQErr]);
+  const float* q_raw = pq ? pq->raw : reinterpret_cast<float*>(ws + off[kOffQRaw]);
+  const float* q_norm = pq ? pq->norm : reinterpret_cast<float*>(ws + off[kOffQNorm]);
+  const uint16_t* q_packed = pq ? pq->packed : reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]);
+  const float* q_err = pq ? pq->err : reinterpret_cast<float*>(ws + off[kOffQErr]);
   float* cand_score = reinterpret_cast<float*>(ws + off[kOffCandScore]);
   int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + off[kOffCandIdx]);
   int32_t* sel_n = reinterpret_cast<int32_t*>(ws + off[kOffSelN]);
@@ -172,15 +212,21 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws + off[kOffFbCount]);
   void* exact_ws = ws + off[kOffExact];
 
-  // all batch items in ONE pack launch, which also zeroes the per-item fallback counters (no separate memset node)
-  rc = pack_impl(source, rows, d, stride_t, stride_d, q_raw, q_norm, q_packed, q_err, nullptr, fb_count, items + 1, stream,
-                 t, stride_b);
-  if (rc) return rc;
+  if (pq == nullptr) {
+    // all batch items in ONE pack launch, which also zeroes the per-item fallback counters (no separate memset node)
+    rc = pack_impl(source, rows, d, stride_t, stride_d, reinterpret_cast<float*>(ws + off[kOffQRaw]),
+                   reinterpret_cast<float*>(ws + off[kOffQNorm]), reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]),
+                   reinterpret_cast<float*>(ws + off[kOffQErr]), nullptr, fb_count, items + 1, stream, t, stride_b);
+    if (rc) return rc;
+  } else {
+    // the producer packed the queries (K1 ran as ITS epilogue): only the fallback counters are left to reset
+    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * (items + 1), as_stream(stream)));
+  }
   if (mode == 1) {
     if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
     // the search may start behind the (still running) query pack: see search_impl
     static const bool pdl = !(getenv("ALIVE_KNN_PDL") && atoi(getenv("ALIVE_KNN_PDL")) == 0);
-    rc = search_impl(q_packed, lib->packed, &plan, cand_score, cand_idx, (pdl && !ev_search_start) ? 1 : 0, stream);
+    rc = search_impl(q_packed, lib->packed, &plan, cand_score, cand_idx, (pdl && !ev_search_start && pq == nullptr) ? 1 : 0, stream);
     if (rc) return rc;
     if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
@@ -220,6 +266,8 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
   }
   return 0;
 }
+}  // namespace
+}  // namespace alive
 
 // ---------------------------------------------------------------------------------------------
 // CUDA IPC helpers for the peer-memory gather (one process per GPU on one NVLink box): export

@@ -67,12 +67,20 @@ constexpr int kGatherWarps = 4;      // 128-thread CTAs: ~160 registers per thre
 // One query frame by one warp.  Lane j < k holds neighbour index j (`my_idx`; k <= 32).  The frames are
 // gathered in batches of kBatch rows (all kBatch * kVec 16-byte loads of a lane are issued before the first add;
 // kBatch * kVec <= 24 keeps the batch in registers: 4 rows at d = 768, i.e. the whole k = 4 neighbourhood).
-template <int kVec>
+// kEagerQ: the query row is known to be needed (alpha != 0): it is requested together with the first batch of frames
+// instead of after the sum.
+template <int kVec, bool kEagerQ>
 __device__ __forceinline__ void gather_query(const FrameSource& fs, int d, int k, long long my_idx,
                                              const float* __restrict__ q_row, bool need_q, float a1, float a0,
                                              float* __restrict__ out_row, int lane) {
   constexpr int kBatch = (24 / kVec) < 1 ? 1 : ((24 / kVec) > 8 ? 8 : (24 / kVec));
   float4 acc[kVec];
+  float4 qv[kEagerQ ? kVec : 1];
+  const float4* q4 = reinterpret_cast<const float4*>(q_row);
+  if constexpr (kEagerQ) {
+#pragma unroll
+    for (int c = 0; c < kVec; ++c) qv[c] = __ldg(q4 + lane + 32 * c);
+  }
   for (int r0 = 0; r0 < k; r0 += kBatch) {
     float4 v[kBatch][kVec];
 #pragma unroll
@@ -94,18 +102,22 @@ __device__ __forceinline__ void gather_query(const FrameSource& fs, int d, int k
   }
   const float kf = static_cast<float>(k);
   float4* o4 = reinterpret_cast<float4*>(out_row);
-  const float4* q4 = reinterpret_cast<const float4*>(q_row);
 #pragma unroll
   for (int c = 0; c < kVec; ++c) {
-    bool zero = false;
-    float4 r = finish4_noq(acc[c], kf, a1, &zero);
-    if (need_q || zero) r = finish4(acc[c], kf, a1, q4[lane + 32 * c], a0);
+    float4 r;
+    if constexpr (kEagerQ) {
+      r = finish4(acc[c], kf, a1, qv[c], a0);
+    } else {
+      bool zero = false;
+      r = finish4_noq(acc[c], kf, a1, &zero);
+      if (need_q || zero) r = finish4(acc[c], kf, a1, q4[lane + 32 * c], a0);
+    }
     o4[lane + 32 * c] = r;
   }
 }
 
-template <int kVec>
-__global__ void __launch_bounds__(kGatherWarps * 32, 3)
+template <int kVec, bool kEagerQ>
+__global__ void __launch_bounds__(kGatherWarps * 32, kEagerQ ? 2 : 3)
 gather_mean_warp_kernel(const FrameSource fs, int d, const long long* __restrict__ top_idx, int t, int k,
                         const float* __restrict__ q_raw, const float* __restrict__ q_norm, float a1, float a0,
                         float* __restrict__ out) {
@@ -129,8 +141,8 @@ gather_mean_warp_kernel(const FrameSource fs, int d, const long long* __restrict
       if (q_norm) nx_qn = q_norm[q_next];
     }
     const bool need_q = a0 != 0.f || q_norm == nullptr || !isfinite(my_qn);
-    gather_query<kVec>(fs, d, k, my_idx, q_raw + static_cast<size_t>(q) * d, need_q, a1, a0,
-                       out + static_cast<size_t>(q) * d, lane);
+    gather_query<kVec, kEagerQ>(fs, d, k, my_idx, q_raw + static_cast<size_t>(q) * d, need_q, a1, a0,
+                                out + static_cast<size_t>(q) * d, lane);
     my_idx = nx_idx;
     my_qn = nx_qn;
     q = q_next;
@@ -182,9 +194,13 @@ int launch_gather(const FrameSource& fs, int d, const long long* top_idx, int t,
     static const int per_sm = getenv("ALIVE_KNN_GATHER_CTAS_PER_SM") ? atoi(getenv("ALIVE_KNN_GATHER_CTAS_PER_SM")) : 3;
     int grid = (t + kGatherWarps - 1) / kGatherWarps;
     if (grid > sms * per_sm) grid = sms * per_sm;
-#define ALIVE_GATHER_CASE(V)                                                                                            \
-  case V:                                                                                                                \
-    gather_mean_warp_kernel<V><<<grid, kGatherWarps * 32, 0, stream>>>(fs, d, top_idx, t, k, q_raw, q_norm, a1, alpha, out); \
+    const bool eager = alpha != 0.f || q_norm == nullptr;
+#define ALIVE_GATHER_CASE(V)                                                                                                  \
+  case V:                                                                                                                      \
+    if (eager)                                                                                                                 \
+      gather_mean_warp_kernel<V, true><<<grid, kGatherWarps * 32, 0, stream>>>(fs, d, top_idx, t, k, q_raw, q_norm, a1, alpha, out);  \
+    else                                                                                                                       \
+      gather_mean_warp_kernel<V, false><<<grid, kGatherWarps * 32, 0, stream>>>(fs, d, top_idx, t, k, q_raw, q_norm, a1, alpha, out); \
     break;
     switch (kvec) {
       ALIVE_GATHER_CASE(1)
@@ -333,8 +349,8 @@ merge_gather_kernel(const Records rec, int row0, int rows, const FrameSource fs,
       if (top_score) top_score[static_cast<size_t>(r) * rec.k + lane] = sel_s[lane];
     }
     const bool need_q = a0 != 0.f || q_norm == nullptr || !isfinite(q_norm[q]);
-    gather_query<kVec>(fs, d, rec.k, my_idx, q_raw + static_cast<size_t>(q) * d, need_q, a1, a0,
-                       out + static_cast<size_t>(r) * d, lane);
+    gather_query<kVec, false>(fs, d, rec.k, my_idx, q_raw + static_cast<size_t>(q) * d, need_q, a1, a0,
+                              out + static_cast<size_t>(r) * d, lane);
     __syncwarp();
   }
 }

@@ -251,17 +251,31 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
   if (nv == 0) return;
   const float4* t4 = reinterpret_cast<const float4*>(tile) + warp;     // tile[j*36 + 4w] = t4[j*9]
   double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
+  if (nv == 4) {                       // (every group but the last of a ragged tile: no per-store predicates)
+    float* r0 = raw + row0 * d;
 #pragma unroll 4
-  for (int j = lane; j < d; j += 32) {
-    const float4 v = t4[j * (kCmLd / 4)];
-    raw[row0 * d + j] = v.x;
-    if (nv > 1) raw[(row0 + 1) * d + j] = v.y;
-    if (nv > 2) raw[(row0 + 2) * d + j] = v.z;
-    if (nv > 3) raw[(row0 + 3) * d + j] = v.w;
-    ss0 += static_cast<double>(v.x) * static_cast<double>(v.x);
-    ss1 += static_cast<double>(v.y) * static_cast<double>(v.y);
-    ss2 += static_cast<double>(v.z) * static_cast<double>(v.z);
-    ss3 += static_cast<double>(v.w) * static_cast<double>(v.w);
+    for (int j = lane; j < d; j += 32) {
+      const float4 v = t4[j * (kCmLd / 4)];
+      r0[j] = v.x;
+      r0[j + d] = v.y;
+      r0[j + 2 * d] = v.z;
+      r0[j + 3 * d] = v.w;
+      ss0 += static_cast<double>(v.x) * static_cast<double>(v.x);
+      ss1 += static_cast<double>(v.y) * static_cast<double>(v.y);
+      ss2 += static_cast<double>(v.z) * static_cast<double>(v.z);
+      ss3 += static_cast<double>(v.w) * static_cast<double>(v.w);
+    }
+  } else {
+    for (int j = lane; j < d; j += 32) {
+      const float4 v = t4[j * (kCmLd / 4)];
+      raw[row0 * d + j] = v.x;
+      if (nv > 1) raw[(row0 + 1) * d + j] = v.y;
+      if (nv > 2) raw[(row0 + 2) * d + j] = v.z;
+      ss0 += static_cast<double>(v.x) * static_cast<double>(v.x);
+      ss1 += static_cast<double>(v.y) * static_cast<double>(v.y);
+      ss2 += static_cast<double>(v.z) * static_cast<double>(v.z);
+      ss3 += static_cast<double>(v.w) * static_cast<double>(v.w);
+    }
   }
   float nrm[4];
   nrm[0] = static_cast<float>(sqrt(warp_sum_f64(ss0)));
@@ -277,24 +291,80 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
     finite[c] = true;
     e2[c] = 0.f;
   }
-  unsigned short* pk16 = reinterpret_cast<unsigned short*>(packed);
-#pragma unroll 2
-  for (int j = lane; j < d; j += 32) {
-    const float4 v = t4[j * (kCmLd / 4)];
-    const float xs[4] = {v.x, v.y, v.z, v.w};
+  if (tame[0] && tame[1] && tame[2] && tame[3]) {
+    // Common case, branch-free per element (the per-element `tame` / small-quotient branches of the first version
+    // cost ~50 instructions per element: the kernel was issue-bound at half the HBM rate).  Lane pairs
+    // (2m, 2m+1) hold adjacent channels: they swap half of their four bf16 values so that the even lane
+    // writes frames 0,1 and the odd lane frames 2,3 as 4-byte words (two channels each) - two 32-bit stores per
+    // lane and iteration instead of four 16-bit ones.
+    const bool odd = (lane & 1) != 0;
+    const int my_f = odd ? 2 : 0;                              // first of the two frames this lane stores
+    unsigned* pkA = reinterpret_cast<unsigned*>(packed + (row0 + my_f) * d);
+    unsigned* pkB = reinterpret_cast<unsigned*>(packed + (row0 + my_f + 1) * d);
+    const bool okA = my_f < nv, okB = my_f + 1 < nv;
+    // one 32-channel step; kTail: the last, partial step of a d that is not a multiple of 32 (d is even: the two
+    // lanes of a pair are live together; dead lanes still take part in the exchange)
+    auto step = [&](int j, bool live) {
+      const float4 v = live ? t4[j * (kCmLd / 4)] : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+      float a[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float a;
-      if (tame[c]) {
-        a = div_by_norm(xs[c], nrm[c], rinv[c]);
-      } else {
-        a = __fdiv_rn(xs[c], nrm[c]);
-        finite[c] = finite[c] && isfinite(a);
+      for (int c = 0; c < 4; ++c) {
+        const float q0 = __fmul_rn(xs[c], rinv[c]);
+        const float e = __fmaf_rn(-q0, nrm[c], xs[c]);
+        a[c] = __fmaf_rn(e, rinv[c], q0);
       }
-      const __nv_bfloat16 h = __float2bfloat16_rn(a);
-      const float da = __bfloat162float(h) - a;
-      e2[c] = fmaf(da, da, e2[c]);
-      if (c < nv) pk16[(row0 + c) * d + j] = __bfloat16_as_ushort(h);
+      // zeros (their sign must survive) and quotients too small for an exact remainder: rare, one test per step
+      if (!(fminf(fminf(fabsf(a[0]), fabsf(a[1])), fminf(fabsf(a[2]), fabsf(a[3]))) >= 0x1p-40f)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (xs[c] == 0.f) a[c] = __fmul_rn(xs[c], rinv[c]);
+          else if (!(fabsf(a[c]) >= 0x1p-40f)) a[c] = __fdiv_rn(xs[c], nrm[c]);
+        }
+      }
+      // two F2FP.PACK_AB: (frame 0, frame 1) and (frame 2, frame 3) of MY channel, low half = first frame
+      const __nv_bfloat162 p01 = __floats2bfloat162_rn(a[0], a[1]);
+      const __nv_bfloat162 p23 = __floats2bfloat162_rn(a[2], a[3]);
+      const unsigned w01 = *reinterpret_cast<const unsigned*>(&p01), w23 = *reinterpret_cast<const unsigned*>(&p23);
+      if (live) {
+        const float d0 = __uint_as_float(w01 << 16) - a[0], d1 = __uint_as_float(w01 & 0xffff0000u) - a[1];
+        const float d2 = __uint_as_float(w23 << 16) - a[2], d3 = __uint_as_float(w23 & 0xffff0000u) - a[3];
+        e2[0] = fmaf(d0, d0, e2[0]);
+        e2[1] = fmaf(d1, d1, e2[1]);
+        e2[2] = fmaf(d2, d2, e2[2]);
+        e2[3] = fmaf(d3, d3, e2[3]);
+      }
+      const unsigned keep = odd ? w23 : w01;                                       // my channel, the frames I store
+      const unsigned got = __shfl_xor_sync(0xffffffffu, odd ? w01 : w23, 1);       // partner's channel, my frames
+      const unsigned ev = odd ? got : keep, od = odd ? keep : got;                 // even / odd channel of the pair
+      const int w = j >> 1;                                                         // word index of the channel pair
+      if (okA && live) pkA[w] = __byte_perm(ev, od, 0x5410);                        // frame A: (even ch, odd ch)
+      if (okB && live) pkB[w] = __byte_perm(ev, od, 0x7632);                        // frame B
+    };
+    const int d_full = d & ~31;
+#pragma unroll 2
+    for (int j0 = 0; j0 < d_full; j0 += 32) step(j0 + lane, true);
+    if (d_full < d) step(d_full + lane, d_full + lane < d);
+  } else {
+    // a zero / huge / tiny / non-finite frame in this group of four: full IEEE division, element by element
+    unsigned short* pk16 = reinterpret_cast<unsigned short*>(packed);
+    for (int j = lane; j < d; j += 32) {
+      const float4 v = t4[j * (kCmLd / 4)];
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a;
+        if (tame[c]) {
+          a = div_by_norm(xs[c], nrm[c], rinv[c]);
+        } else {
+          a = __fdiv_rn(xs[c], nrm[c]);
+          finite[c] = finite[c] && isfinite(a);
+        }
+        const __nv_bfloat16 hb = __float2bfloat16_rn(a);
+        const float da = __bfloat162float(hb) - a;
+        e2[c] = fmaf(da, da, e2[c]);
+        if (c < nv) pk16[(row0 + c) * d + j] = __bfloat16_as_ushort(hb);
+      }
     }
   }
 #pragma unroll

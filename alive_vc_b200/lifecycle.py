@@ -246,48 +246,127 @@ def match_rows(frames: torch.Tensor, lib, k: int = 4, alpha: float = 0.0, *, ret
 
 
 class HostStreamingMatcher:
-    """The realtime loop's chunk step with HOST buffers (realtime_inference.py:158-176 moves every
-    block host -> device -> host): pinned input and output buffers, and ONE CUDA graph holding the
-    host->device copy, the whole match pipeline and the device->host copy.  A call is a memcpy into
-    the pinned buffer, one graph launch and one event wait.
+    """The realtime loop's chunk step with HOST buffers (realtime_inference.py:130-191 moves every block
+    host -> device -> host): pinned input and output buffers and ONE CUDA graph per chunk.
 
         hm = HostStreamingMatcher(pack_library(tgt), T=24)
         out = hm(chunk_cpu)            # [B, D, T] float32 CPU tensor -> [B, D, T] view of the pinned result
+
+    Match only (no `pre` / `post`): the graph is one H2D copy node and the match pipeline; the last kernel of the
+    pipeline writes the matched frames (contiguous 3 KB rows) straight into the pinned result over PCIe (unified
+    addressing: zero_copy="out", the default) - no D2H copy node; a call is a memcpy into the pinned buffer, one
+    graph launch and one event wait.  zero_copy="both" also lets K1 read the chunk in place (no H2D node either),
+    zero_copy=False keeps both copy nodes.  `hm.src_host` may be filled in place (`hm.run()`).
+
+    With caller modules - `pre` (e.g. the content encoder, realtime_inference.py:150: spectrogram chunk -> [B, D, T]
+    features) and/or `post` (e.g. the decoder, :166) - the SAME graph holds  H2D copy -> pre -> match -> post -> D2H copy
+    (encoder -> match -> decoder in one capture).  `pre` / `post` must be capture-safe (static shapes,
+    no host synchronisation) like any module run under torch.cuda.graph; `in_shape` is the shape of the host chunk
+    `pre` consumes (default [batch, D, T]), the output shape is whatever `post` returns.
     """
 
     def __init__(self, lib: M.PackedFrames, T: int, k: int = 4, alpha: float = 0.0, batch: int = 1,
-                 mode: str = "auto", variant: int = 0, r_max: int = M.DEFAULT_R_MAX):
+                 mode: str = "auto", variant: int = 0, r_max: int = M.DEFAULT_R_MAX, pre=None, post=None,
+                 in_shape=None, in_dtype=torch.float32, zero_copy="out"):
         dev = lib.device
+        self.lib, self.pre, self.post = lib, pre, post
+        if zero_copy not in (False, "out", "both"):
+            raise ValueError("zero_copy must be False, 'out' or 'both'")
+        # zero-copy needs the match to be the first / last thing in the graph
+        self.zc_in = zero_copy == "both" and pre is None
+        self.zc_out = zero_copy in ("out", "both") and post is None
         self.inner = M.StreamingMatcher(lib, T, k, alpha, batch, mode, variant, r_max, use_graph=False)
-        self.src_host = torch.zeros((batch, lib.d, T), dtype=torch.float32).pin_memory()
-        self.out_host = torch.zeros((batch, T, lib.d), dtype=torch.float32).pin_memory()
+        in_shape = tuple(in_shape) if in_shape is not None else (batch, lib.d, T)
+        self.src_host = torch.zeros(in_shape, dtype=in_dtype).pin_memory()
         self.stream = torch.cuda.Stream(device=dev)
         self.done = torch.cuda.Event()
-        with torch.cuda.stream(self.stream):
-            self._enqueue()                            # warm-up outside capture
-        self.stream.synchronize()
-        self.launches_per_call = M.last_info.launches  # kernels per graph replay
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=self.stream):
-            self._enqueue()
+        with torch.cuda.device(dev):
+            self.in_dev = None if self.zc_in else torch.zeros(in_shape, dtype=in_dtype, device=dev)
+            if post is None:
+                self.out_host = torch.zeros((batch, T, lib.d), dtype=torch.float32).pin_memory()
+            else:
+                with torch.cuda.stream(self.stream), torch.no_grad():
+                    probe = self._device_step(None)            # warm-up outside capture; fixes the output shape
+                self.stream.synchronize()
+                self.out_host = torch.zeros(tuple(probe.shape), dtype=probe.dtype).pin_memory()
+            with torch.cuda.stream(self.stream), torch.no_grad():
+                self._enqueue()                            # warm-up outside capture
+            self.stream.synchronize()
+            self.launches_per_call = M.last_info.launches  # kernels of OURS per graph replay
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream), torch.no_grad():
+                self._enqueue()
+
+    def _device_step(self, out):
+        """[pre ->] match [-> post]; `out`: where the match writes its [B, T, D] block (None = the device buffer).
+        Returns what has to reach the host (None when the match already wrote it there)."""
+        i = self.inner
+        if self.zc_in:
+            src = self.src_host                                 # K1 reads the pinned chunk in place
+        else:
+            feat = self.pre(self.in_dev) if self.pre is not None else self.in_dev
+            if feat.dtype != torch.float32:
+                feat = feat.float()                             # (fp16 encoder output under autocast)
+            src = feat
+        M.run_match(src, self.lib, i.k, i.alpha, i.mode, i.variant, i.r_max, workspace=i.workspace,
+                    out=out if out is not None else i.out, top_idx=i.top_idx, top_score=i.top_score, host_buffers=True)
+        if self.post is not None:
+            return self.post(i.out.transpose(1, 2))             # [B, D, T] view, as match_features returns it
+        return None if out is not None else i.out
 
     def _enqueue(self):
-        self.inner.src.copy_(self.src_host, non_blocking=True)
-        self.inner._run()
-        self.out_host.copy_(self.inner.out, non_blocking=True)
+        if not self.zc_in:
+            self.in_dev.copy_(self.src_host, non_blocking=True)
+        res = self._device_step(self.out_host if self.zc_out else None)
+        if res is not None:
+            self.out_host.copy_(res, non_blocking=True)
 
-    def submit(self, chunk: torch.Tensor):
-        """Stage `chunk` (CPU, [B, D, T]) and launch; returns immediately (see `result`)."""
-        self.src_host.copy_(chunk)
+    def run(self):
+        """Launch on the chunk already sitting in `self.src_host`; returns immediately (see `result`)."""
         with torch.cuda.stream(self.stream):
             self.graph.replay()
             self.done.record(self.stream)
         M._count(self.launches_per_call)
 
+    def submit(self, chunk: torch.Tensor):
+        """Stage `chunk` (CPU) and launch; returns immediately (see `result`)."""
+        self.src_host.copy_(chunk)
+        self.run()
+
     def result(self) -> torch.Tensor:
         self.done.synchronize()
-        return self.out_host.transpose(1, 2)
+        return self.out_host.transpose(1, 2) if self.post is None else self.out_host
 
     def __call__(self, chunk: torch.Tensor) -> torch.Tensor:
         self.submit(chunk)
         return self.result()
+
+
+class RowsContentEncoder(torch.nn.Module):
+    """The producer step around a content encoder with the reference's structure
+    (module/content_encoder.py:8-25: `input_layer` -> `mid_layers` -> `output_layer`, a 1x1 Conv1d to 768 channels;
+    [B, n_fft/2+1, T] spectrogram -> [B, 768, T]).  The encoder's own layers run untouched; only its LAST layer is
+    evaluated channels-last - the same 1x1 convolution written as a linear map on [B, T, C] - so the features leave
+    the encoder as row-major [B, T, 768] frames, the layout the match consumes, and K1 (alive_knn_pack) runs as the
+    encoder's epilogue: `forward` returns the packed queries for `match_packed_queries` (no per-call query pack
+    inside the match, no transposed views either side), `rows` the plain [B, T, 768] frames for `match_rows`.
+    An encoder without that structure is wrapped as `encoder(x).transpose(1, 2)` (a view; K1 takes the strides)."""
+
+    def __init__(self, encoder: torch.nn.Module):
+        super().__init__()
+        self.encoder = encoder
+
+    def rows(self, spec: torch.Tensor) -> torch.Tensor:
+        enc = self.encoder
+        out_layer = getattr(enc, "output_layer", None)
+        if (isinstance(out_layer, torch.nn.Conv1d) and out_layer.kernel_size == (1,) and out_layer.groups == 1 and
+                hasattr(enc, "input_layer") and hasattr(enc, "mid_layers")):
+            x = enc.mid_layers(enc.input_layer(spec))                                   # content_encoder.py:22-23
+            return torch.nn.functional.linear(x.transpose(1, 2), out_layer.weight[:, :, 0], out_layer.bias)   # :24
+        return enc(spec).transpose(1, 2)
+
+    def forward(self, spec: torch.Tensor) -> M.PackedFrames:
+        with torch.no_grad():
+            rows = self.rows(spec)
+            B, T, D = rows.shape
+            return M.pack_frames(rows.reshape(B * T, D).float().t())     # [D, B*T] view with stride_d == 1: K1's row-major kernel

@@ -504,10 +504,13 @@ def _layout(rows: int, lib: PackedFrames, k: int, r_max: int, mode: int, variant
 
 def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0, mode: str = "auto",
               variant: int = 0, r_max: int = DEFAULT_R_MAX, want_out: bool = True, workspace=None,
-              out=None, top_idx=None, top_score=None):
+              out=None, top_idx=None, top_score=None, info_sink: Optional[dict] = None, host_buffers: bool = False):
     """The whole path in ONE C call (alive_knn_match): pack the B*T query frames of `source`
     [B,D,T] (any strides, float32, CUDA), search, certify, rescore, exact-scan the uncertified,
-    gather+mean+blend.  Returns (out [B,T,D] or None, top_idx [B,T,k] int64, top_score [B,T,k])."""
+    gather+mean+blend.  Returns (out [B,T,D] or None, top_idx [B,T,k] int64, top_score [B,T,k]).
+    `info_sink` (a dict) receives the workspace and its layout offsets (q_raw at offsets[0], q_norm at [1]).
+    `host_buffers`: `source` (and a given `out`) may be PINNED HOST tensors - the kernels read / write them in place
+    over PCIe (unified addressing; HostStreamingMatcher's zero-copy chunk path); everything else lives on lib.device."""
     global last_info
     c = _cabi.load()
     B, D, T = source.shape
@@ -519,11 +522,19 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
         raise RuntimeError(f"alive_vc_b200 supports k <= {MAX_K} (got {k})")
     if lib.items > 1 and lib.items != B:
         raise RuntimeError(f"a packed set of {lib.items} libraries needs a query batch of {lib.items} (got {B})")
-    _require_cuda(source, "source")
     assert source.dtype == torch.float32
-    dev = source.device
-    if dev != lib.device:
-        raise RuntimeError(f"source is on {dev} but the packed library is on {lib.device}")
+    if host_buffers:
+        for tns in (source, out):
+            if tns is not None and not tns.is_cuda and not tns.is_pinned():
+                raise RuntimeError("alive_vc_b200: host buffers must be pinned (page-locked) to be read by the kernels")
+        dev = lib.device
+        if source.is_cuda and source.device != dev:
+            raise RuntimeError(f"source is on {source.device} but the packed library is on {dev}")
+    else:
+        _require_cuda(source, "source")
+        dev = source.device
+        if dev != lib.device:
+            raise RuntimeError(f"source is on {dev} but the packed library is on {lib.device}")
     rows = B * T
     m = _MODES[mode]
     if m == 0:
@@ -560,6 +571,8 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
                            launches=1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
     last_info._workspace = workspace
     last_info._offsets = off
+    if info_sink is not None:          # callers on several threads cannot rely on the module-level last_info
+        info_sink["workspace"], info_sink["offsets"] = workspace, off
     return (out if want_out else None), top_idx, top_score
 
 
@@ -572,6 +585,61 @@ def match_packed(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: flo
     if lib.items > 1:
         idx = idx - (torch.arange(lib.items, device=idx.device, dtype=idx.dtype) * lib.n_item).view(-1, 1, 1)
     return out, idx, score
+
+
+def match_packed_queries(q: PackedFrames, lib: PackedFrames, k: int = 4, alpha: float = 0.0, mode: str = "auto",
+                         variant: int = 0, r_max: int = DEFAULT_R_MAX, batch: int = 1, want_out: bool = True,
+                         workspace=None, out=None, top_idx=None, top_score=None):
+    """The match for query frames that are ALREADY packed: `q` = pack_frames / pack_rows /
+    pack_queries output of the producer (K1 ran as the encoder's epilogue - once, however many libraries the
+    utterance is then matched against).  alive_knn_match_packed: no K1 launch, everything else as run_match.
+    `q` holds batch * T frames (frame b*T + t); returns (out [batch, T, D] float32, top_idx [batch, T, k] int64 -
+    global frame indices when `lib` holds several libraries -, top_score [batch, T, k]), bit-identical to
+    run_match on the frames `q` was packed from."""
+    global last_info
+    c = _cabi.load()
+    if q.d != lib.d:
+        raise RuntimeError(f"feature dims differ: queries {q.d}, library {lib.d}")
+    if not isinstance(k, int) or k < 1 or k > lib.n_item:
+        raise RuntimeError("selected index k out of range")
+    if k > MAX_K:
+        raise RuntimeError(f"alive_vc_b200 supports k <= {MAX_K} (got {k})")
+    if batch < 1 or q.n % batch != 0:
+        raise RuntimeError(f"{q.n} packed query frames do not split into a batch of {batch}")
+    if lib.items > 1 and lib.items != batch:
+        raise RuntimeError(f"a packed set of {lib.items} libraries needs a query batch of {lib.items} (got {batch})")
+    dev = q.device
+    if dev != lib.device:
+        raise RuntimeError(f"the packed queries are on {dev} but the packed library is on {lib.device}")
+    rows, D, T = q.n, q.d, q.n // batch
+    m = _MODES[mode]
+    if m == 0:
+        m = 2 if (k > LIST_LEN or lib.n_item < EXACT_BELOW_N or lib.d % 64 != 0) else 1
+    off = _layout(rows, lib, k, r_max, m, variant, dev)
+    if workspace is None:
+        workspace = torch.empty((off[11],), dtype=torch.uint8, device=dev)
+    if want_out and out is None:
+        out = torch.empty((batch, T, D), dtype=torch.float32, device=dev)
+    if top_idx is None:
+        top_idx = torch.empty((batch, T, k), dtype=torch.int64, device=dev)
+        top_score = torch.empty((batch, T, k), dtype=torch.float32, device=dev)
+    with _on(dev):
+        rc = c.alive_knn_match_packed(q.raw.data_ptr(), q.norms.data_ptr(), q.packed.data_ptr(), q.err.data_ptr(), batch, T,
+                                      ctypes.byref(lib.handle()), k, float(alpha), r_max, m, _num_sms(dev), variant,
+                                      workspace.data_ptr(), workspace.numel(), out.data_ptr() if want_out else None,
+                                      top_idx.data_ptr(), top_score.data_ptr(), _stream_ptr(dev))
+    _cabi.check(rc, "alive_knn_match_packed")
+    launches = (6 if off[7] > off[6] else 4) if m == 1 else 2
+    _count(launches)
+    last_info = SearchInfo(mode="screen" if m == 1 else "exact",
+                           fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
+                           exact_count=workspace[off[9] + 4 * lib.items:off[9] + 4 * lib.items + 4].view(torch.int32),
+                           collect=m == 1 and off[7] > off[6],
+                           sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
+                           launches=launches)
+    last_info._workspace = workspace
+    last_info._offsets = off
+    return (out if want_out else None), top_idx, top_score
 
 
 class StreamingMatcher:

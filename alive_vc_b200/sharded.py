@@ -237,9 +237,10 @@ class CudaShardBackend:
         B, D, T = q.source.shape
         if out_idx is not None:
             out_idx, out_score = out_idx.view(B, T, k), out_score.view(B, T, k)
+        sink = {}
         _, idx, score = M.run_match(q.source, self.local, k, 0.0, self.mode, self.variant, want_out=False,
-                                    top_idx=out_idx, top_score=out_score)
-        ws, off = M.last_info._workspace, M.last_info._offsets
+                                    top_idx=out_idx, top_score=out_score, info_sink=sink)
+        ws, off = sink["workspace"], sink["offsets"]
         rows = B * T
         q.raw = ws[off[0]: off[0] + rows * D * 4].view(torch.float32).view(rows, D)
         q.norms = ws[off[1]: off[1] + rows * 4].view(torch.float32)

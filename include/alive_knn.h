@@ -269,6 +269,17 @@ int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t strid
                     size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
                     void* ev_search_start, void* ev_search_stop, alive_stream_t stream);
 
+/* The same pipeline for queries that arrive ALREADY packed (a producer - the content encoder,
+ * module/content_encoder.py:8-25 - that runs alive_knn_pack as its own epilogue, e.g. once per utterance that is
+ * then matched against several speakers' libraries, or on row-major [T, D] frames it kept channels-last):
+ * q_raw [batch*t, d] f32, q_norm [batch*t], q_packed [batch*t, d] bf16, q_err [batch*t] exactly as alive_knn_pack
+ * wrote them.  No K1 launch; everything else (search, certificate, rescoring, fallbacks, gather) as alive_knn_match. */
+int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16_t* q_packed, const float* q_err,
+                           int32_t batch, int32_t t, const alive_knn_library_t* lib_host, int32_t k, float alpha,
+                           int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
+                           size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
+                           alive_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

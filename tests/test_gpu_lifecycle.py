@@ -253,3 +253,98 @@ def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
             assert fast[key][1] == gen[key][1], key                      # count of non-finite rows
             a, b = fast[key][:1].view(np.float32)[0], gen[key][:1].view(np.float32)[0]
             assert abs(a - b) <= 1e-5 * b, key
+
+
+# ---- (f)3: caller modules inside the chunk graph; (f)4: the producer-side pack ---------------------------------
+class _TinyEncoder(torch.nn.Module):
+    """stand-in with the structure of module/content_encoder.py:8-25 (the reference's modules cannot travel to the
+    GPU box): 1x1 conv in, a depthwise + pointwise block, 1x1 conv out to 768 channels"""
+
+    def __init__(self, c_in=65, c_mid=96, d=768):
+        super().__init__()
+        self.input_layer = torch.nn.Conv1d(c_in, c_mid, 1)
+        self.mid_layers = torch.nn.Sequential(torch.nn.Conv1d(c_mid, c_mid, 7, padding=3, groups=c_mid), torch.nn.GELU(),
+                                              torch.nn.Conv1d(c_mid, c_mid, 1))
+        self.output_layer = torch.nn.Conv1d(c_mid, d, 1)
+
+    def forward(self, x):
+        return self.output_layer(self.mid_layers(self.input_layer(x)))
+
+
+@pytest.mark.parametrize("zero_copy", [False, "out", "both"])
+def test_host_streaming_matcher_copy_modes(zero_copy):
+    rng = np.random.default_rng(18)
+    D, T, N = 768, 32, 30_000
+    ref = rng.standard_normal((1, D, N), dtype=np.float32)
+    lib = A.pack_library(_cuda(ref))
+    hm = HostStreamingMatcher(lib, T, 4, 0.25, zero_copy=zero_copy)
+    for _ in range(3):
+        chunk = torch.from_numpy(rng.standard_normal((1, D, T), dtype=np.float32))
+        out = hm(chunk)
+        want, _, _ = A.match_packed(chunk.cuda(), lib, 4, 0.25)
+        assert torch.equal(out, want.transpose(1, 2).cpu())
+    hm.src_host.copy_(chunk * 2.0)                       # fill the pinned buffer in place, then run()
+    hm.run()
+    want, _, _ = A.match_packed((chunk * 2.0).cuda(), lib, 4, 0.25)
+    assert torch.equal(hm.result(), want.transpose(1, 2).cpu())
+
+
+def test_chunk_graph_with_encoder_and_decoder_modules():
+    """realtime_inference.py:143-167 as ONE graph: H2D -> encoder (pre) -> match -> decoder (post) -> D2H, under
+    fp16 autocast like the reference's `-fp16`; equals the same modules run eagerly around match_features."""
+    torch.manual_seed(5)
+    enc = _TinyEncoder().cuda().eval()
+    dec = torch.nn.Sequential(torch.nn.Conv1d(768, 32, 3, padding=1), torch.nn.Tanh()).cuda().eval()
+    T, N = 24, 3512
+    tgt = torch.randn(1, 768, N, device="cuda")
+    lib = A.pack_library(tgt)
+
+    def pre(spec):
+        with torch.autocast("cuda", dtype=torch.float16):
+            return enc(spec)                             # fp16 features, [1, 768, T]
+
+    def post(feat):
+        with torch.autocast("cuda", dtype=torch.float16):
+            return dec(feat).float()
+    hm = HostStreamingMatcher(lib, T, 4, 0.0, pre=pre, post=post, in_shape=(1, 65, T))
+    for _ in range(3):
+        spec = torch.randn(1, 65, T)
+        out = hm(spec)
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.float16):
+            content = enc(spec.cuda())
+            matched = A.match_features(content, tgt, k=4, alpha=0.0)
+            want = dec(matched).float()
+        assert tuple(out.shape) == (1, 32, T)
+        assert torch.equal(out, want.cpu())
+    # encoder only (the decoder stays outside): the matched frames come back as [B, D, T]
+    hm2 = HostStreamingMatcher(lib, T, 4, 0.0, pre=pre, in_shape=(1, 65, T))
+    out2 = hm2(spec)
+    assert tuple(out2.shape) == (1, 768, T) and torch.equal(out2, matched.cpu())
+
+
+def test_producer_side_pack_is_bit_identical():
+    """RowsContentEncoder: the encoder's last 1x1 conv evaluated channels-last + K1 as its epilogue; the match on the
+    packed queries (no K1 inside) equals the match on the same row-major frames, against one and several libraries."""
+    from alive_vc_b200.lifecycle import RowsContentEncoder, match_rows, pack_rows
+    torch.manual_seed(6)
+    enc = _TinyEncoder().cuda().eval()
+    prod = RowsContentEncoder(enc)
+    spec = torch.randn(2, 65, 150, device="cuda")
+    with torch.no_grad():
+        rows = prod.rows(spec)                                        # [2, 150, 768] row-major
+        assert tuple(rows.shape) == (2, 150, 768) and rows.is_contiguous()
+        torch.testing.assert_close(rows, enc(spec).transpose(1, 2), rtol=1e-4, atol=1e-4)   # same layer, other GEMM layout
+    q = prod(spec)
+    assert q.n == 300 and torch.equal(q.raw.view(2, 150, 768), rows)
+    for seed in (1, 2):                                               # one utterance, two speakers' libraries
+        lib = pack_rows(torch.randn(20_000, 768, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed)))
+        launches0 = M.launch_count
+        out, idx, _ = A.match_packed_queries(q, lib, 4, 0.25, batch=2)
+        assert M.launch_count - launches0 == 4                        # search, finish, exact_partial/rows/final - no pack
+        w_out, w_idx = match_rows(rows, lib, 4, 0.25, return_indices=True)
+        assert torch.equal(idx, w_idx) and torch.equal(out, w_out)
+    # per-speaker libraries (items == batch) take packed queries too
+    libs = A.pack_libraries(torch.randn(2, 768, 3000, device="cuda"))
+    out, idx, _ = A.match_packed_queries(q, libs, 4, 0.0, batch=2)
+    w_out, w_idx, _ = M.run_match(rows.transpose(1, 2), libs, 4, 0.0)
+    assert torch.equal(idx, w_idx) and torch.equal(out, w_out)

@@ -79,8 +79,10 @@ def test_thread_ranks_equal_oracle_and_unsharded(world, n_total, T, k, alpha, B,
         lo, hi = shard_bounds(n_total, comm.world, comm.rank)
         assert lib.n_local == hi - lo and lib.row_base == lo
         out, idx = lib.match(s, k, alpha, return_indices=True)
+        res = out.clone(), idx.clone()
         torch.cuda.synchronize()
-        return out.clone(), idx.clone()
+        comm.barrier()          # a rank's shard must outlive every peer's gather (ShardedLibrary.close protocol)
+        return res
 
     for out, idx in _run_ranks(world, rank_fn):
         ok, _, _, bad = O.indices_match_mod_ties(idx.cpu().numpy(), o_idx, scores, 1e-6)
@@ -106,8 +108,10 @@ def test_scattered_queries_and_results(world, n_total, T, peer):
         lib = ShardedLibrary.from_full(r, comm=comm, peer_memory=peer)
         lo, hi = shard_bounds(T, comm.world, comm.rank)
         out, idx = lib.match(s[:, :, lo:hi], 4, 0.25, return_indices=True, scattered=True, t_total=T)
+        res = lo, hi, out.clone(), idx.clone()
         torch.cuda.synchronize()
-        return lo, hi, out.clone(), idx.clone()
+        comm.barrier()
+        return res
 
     for lo, hi, out, idx in _run_ranks(world, rank_fn):
         assert tuple(out.shape) == (1, 768, hi - lo)
@@ -127,8 +131,10 @@ def test_clustered_library_sharded_collect_pass():
     def rank_fn(comm):
         lib = ShardedLibrary.from_full(ref, comm=comm)
         out, idx = lib.match(src, 4, 0.0, return_indices=True)
+        res = out.clone(), idx.clone()
         torch.cuda.synchronize()
-        return out.clone(), idx.clone()
+        comm.barrier()
+        return res
 
     for out, idx in _run_ranks(world, rank_fn):
         assert torch.equal(idx, want_idx) and torch.equal(out, want_out)
