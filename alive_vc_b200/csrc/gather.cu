@@ -462,6 +462,7 @@ extern "C" int alive_knn_merge_gather(const void* records, int64_t record_stride
   using namespace alive;
   int rc = check_records(records, record_stride, ranks, t, k, "alive_knn_merge_gather");
   if (rc) return rc;
+  if (rows == 0) return 0;                 // (a rank whose slice of the query frames is empty)
   ALIVE_REQUIRE(shard_raw && bounds && q_raw && out, "alive_knn_merge_gather: NULL argument");
   ALIVE_REQUIRE(shards >= 1 && shards <= 64, "alive_knn_merge_gather: shards must be in [1,64]");
   ALIVE_REQUIRE(row0 >= 0 && rows >= 0 && row0 + rows <= t, "alive_knn_merge_gather: rows [%d, %d) outside [0, %d)", row0,

@@ -223,11 +223,15 @@ def test_gather_mean_kernels_are_bit_exact(T, N, k, alpha, D):
     idx[0] = torch.arange(k, device="cuda") % 4                    # mean of +0 rows
     idx[1] = 4 + torch.arange(k, device="cuda") % 4                # mean of -0 rows: sign of zero decided by 0 * q
     q_norm = torch.linalg.vector_norm(q_raw.double(), dim=1).float()
-    rows = raw[idx]                                                 # [T, k, D]
-    acc = rows[:, 0].clone()
+    rows = raw[idx].cpu().numpy()                                   # [T, k, D]
+    acc = rows[:, 0].copy()
     for j in range(1, k):
-        acc = acc + rows[:, j]
-    want = (acc / k) * (1.0 - alpha) + q_raw * alpha
+        acc = (acc + rows[:, j]).astype(np.float32)
+    # true float32 division by k on the host (torch's CUDA `tensor / python_scalar` multiplies by a rounded reciprocal)
+    with np.errstate(invalid="ignore"):
+        want = ((acc / np.float32(k)).astype(np.float32) * np.float32(1.0 - alpha)).astype(np.float32) + \
+            (q_raw.cpu().numpy() * np.float32(alpha)).astype(np.float32)
+    want = torch.from_numpy(want.astype(np.float32)).cuda()
     c = _cabi.load()
     for qn in (q_norm, None):
         out = torch.empty((T, D), device="cuda")
