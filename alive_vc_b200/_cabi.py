@@ -50,7 +50,7 @@ class Library(ctypes.Structure):
     _fields_ = [
         ("packed", ctypes.c_void_p), ("raw", ctypes.c_void_p), ("norms", ctypes.c_void_p),
         ("stats", ctypes.c_void_p), ("n", ctypes.c_int64), ("d", ctypes.c_int32), ("row_base", ctypes.c_int64),
-        ("items", ctypes.c_int32),
+        ("items", ctypes.c_int32), ("lo", ctypes.c_void_p),
     ]
 
 
@@ -131,7 +131,7 @@ def _declare(lib):
     lib.alive_knn_abi_version.restype = ctypes.c_int
     lib.alive_knn_abi_version.argtypes = []
     lib.alive_knn_pack.restype = ctypes.c_int
-    lib.alive_knn_pack.argtypes = [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.alive_knn_pack.argtypes = [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.alive_knn_plan.restype = ctypes.c_int
     lib.alive_knn_plan.argtypes = [_i32, _i64, _i32, _i32, _i32, ctypes.POINTER(Plan)]
     lib.alive_knn_plan_batched.restype = ctypes.c_int
@@ -139,7 +139,7 @@ def _declare(lib):
     lib.alive_knn_search.restype = ctypes.c_int
     lib.alive_knn_search.argtypes = [_vp, _vp, ctypes.POINTER(Plan), _vp, _vp, _vp]
     lib.alive_knn_prune.restype = ctypes.c_int
-    lib.alive_knn_prune.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]
+    lib.alive_knn_prune.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]
     lib.alive_knn_rescore.restype = ctypes.c_int
     lib.alive_knn_rescore.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]
     lib.alive_knn_exact_workspace_bytes.restype = ctypes.c_size_t
@@ -176,8 +176,8 @@ def _declare(lib):
     lib.alive_knn_match_layout.restype = ctypes.c_int
     lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
     lib.alive_knn_match_packed.restype = ctypes.c_int
-    lib.alive_knn_match_packed.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(Library), _i32, _f32, _i32,
-                                           _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]
+    lib.alive_knn_match_packed.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(Library), _i32, _f32,
+                                           _i32, _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]
     lib.alive_knn_match.restype = ctypes.c_int
     lib.alive_knn_match.argtypes = [_vp, _i32, _i32, _i64, _i64, _i64, ctypes.POINTER(Library), _i32, _f32, _i32,
                                     _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -197,7 +197,7 @@ def load():
             # ALIVE_KNN_LIB: an instrumented build of the same sources (tests/gpu_tools/finish_phases.py)
             lib = ctypes.CDLL(os.environ.get("ALIVE_KNN_LIB") or LIB_PATH)
             _declare(lib)
-            if lib.alive_knn_abi_version() != 4:
+            if lib.alive_knn_abi_version() != 5:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")
             _lib = lib
     return _lib

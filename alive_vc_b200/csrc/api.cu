@@ -28,7 +28,8 @@ namespace alive {
 namespace {
 
 constexpr int kOffQRaw = 0, kOffQNorm = 1, kOffQPacked = 2, kOffQErr = 3, kOffCandScore = 4, kOffCandIdx = 5,
-              kOffCollect = 6, kOffSelN = 7, kOffFbList = 8, kOffFbCount = 9, kOffExact = 10, kOffTotal = 11;
+              kOffCollect = 6, kOffSelN = 7, kOffFbList = 8, kOffFbCount = 9, kOffExact = 10, kOffTotal = 11,
+              kOffQLo = 12, kOffQErr2 = 13, kOffSlots = 14;
 
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -38,29 +39,38 @@ int resolve_mode(int mode, int64_t n, int d, int k) {
   return mode;
 }
 
-// Second screen pass for uncertified queries (single item; the first screen may have been the tiled
-// or the skinny kernel - the collect pass always runs the tiled one on its own compact query matrix;
-// enough work for the exhaustive scan to hurt): at most kCollectRows queries get a slot and a buffer of kCollectCap
-// candidate frames each.  Area layout: fb2_list [rows] | qc_packed [rows_c, d] bf16 | cut [rows_c] |
-// cnt [rows_c] | idx [rows_c, cap]; fb2_count is the word after the per-item fallback counters.
-constexpr int kCollectRows = 2048;
+// Second screen pass for uncertified queries (the first screen may have been the tiled or the skinny kernel - the
+// collect pass always runs the tiled one on its own compact query matrix; enough work for the exhaustive scan to
+// hurt): per item at most rows_c queries get a slot and a buffer of kCollectCap candidate frames each.
+// Area layout: fb2_list [rows] | qc_packed [items*rows_c, d] bf16 | qc_lo [items*rows_c, d] bf16 (the second plane, used
+// when the library carries one) | cut [items*rows_c] | cnt [items*rows_c] | idx [items*rows_c, cap];
+// the fb2 counters are the `items` words after the per-item fallback counters.
+constexpr int kCollectRows = 8192;
 constexpr int kCollectCap = 2048;
 struct CollectLayout {
   bool on;
   int rows_c;
   alive_knn_plan_t plan;
-  size_t fb2_list, qc, cut, cnt, idx, bytes;
+  size_t fb2_list, qc, qc_lo, cut, cnt, idx, bytes;
 };
 
 int collect_layout(int32_t rows, int64_t n, int32_t d, int32_t num_sms, int mode, int32_t items,
                    const alive_knn_plan_t& screen_plan, CollectLayout* cl) {
   static const bool enabled = !(getenv("ALIVE_KNN_COLLECT") && atoi(getenv("ALIVE_KNN_COLLECT")) == 0);
-  cl->on = enabled && mode == 1 && items == 1 && (screen_plan.kernel == 0 || screen_plan.kernel == 1) && d % 64 == 0 &&
+  cl->on = enabled && mode == 1 && (screen_plan.kernel == 0 || screen_plan.kernel == 1) && d % 64 == 0 &&
            static_cast<double>(rows) * static_cast<double>(n) >= 16777216.0;
   cl->bytes = 0;
   if (!cl->on) return 0;
-  cl->rows_c = rows < kCollectRows ? rows : kCollectRows;
-  int rc = alive_knn_plan(cl->rows_c, n, d, num_sms, cl->rows_c > ALIVE_KNN_TILE_M ? 2 : 1, &cl->plan);
+  const int t_item = rows / items;
+  long long rc_rows = t_item < kCollectRows ? t_item : kCollectRows;
+  const long long budget = (1ll << 30) / (static_cast<long long>(items) * kCollectCap * 4);     // candidate buffers <= 1 GiB
+  if (rc_rows > budget) rc_rows = budget;
+  if (rc_rows < 1) {
+    cl->on = false;
+    return 0;
+  }
+  cl->rows_c = static_cast<int>(rc_rows);
+  int rc = alive_knn_plan_batched(items, cl->rows_c, n, d, num_sms, cl->rows_c > ALIVE_KNN_TILE_M ? 2 : 1, &cl->plan);
   if (rc) return rc;
   size_t cur = 0;
   auto take = [&](size_t bytes) {
@@ -68,11 +78,13 @@ int collect_layout(int32_t rows, int64_t n, int32_t d, int32_t num_sms, int mode
     cur += align256(bytes);
     return at;
   };
+  const size_t slots = static_cast<size_t>(items) * cl->rows_c;
   cl->fb2_list = take(static_cast<size_t>(rows) * 4);
-  cl->qc = take(static_cast<size_t>(cl->rows_c) * d * 2);
-  cl->cut = take(static_cast<size_t>(cl->rows_c) * 4);
-  cl->cnt = take(static_cast<size_t>(cl->rows_c) * 4);
-  cl->idx = take(static_cast<size_t>(cl->rows_c) * kCollectCap * 4);
+  cl->qc = take(slots * d * 2);
+  cl->qc_lo = take(slots * d * 2);
+  cl->cut = take(slots * 4);
+  cl->cnt = take(slots * 4);
+  cl->idx = take(slots * kCollectCap * 4);
   cl->bytes = cur;
   return 0;
 }
@@ -88,6 +100,8 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
   take(kOffQNorm, static_cast<size_t>(rows) * 4);
   take(kOffQPacked, static_cast<size_t>(rows) * d * 2);
   take(kOffQErr, static_cast<size_t>(rows) * 4);
+  take(kOffQLo, static_cast<size_t>(rows) * d * 2);
+  take(kOffQErr2, static_cast<size_t>(rows) * 4);
   size_t lists = 0;
   if (mode == 1) {
     int rc = alive_knn_plan_batched(items, rows / items, n, d, num_sms, variant, plan);
@@ -110,7 +124,7 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
   }
   take(kOffSelN, static_cast<size_t>(rows) * 4);
   take(kOffFbList, static_cast<size_t>(rows) * 4);
-  take(kOffFbCount, static_cast<size_t>(items + 1) * 4);   // per-item counters + the collect pass's fb2 counter
+  take(kOffFbCount, static_cast<size_t>(2 * items) * 4);   // per-item counters: uncertified after the screen, after the collect pass
   take(kOffExact, alive_knn_exact_workspace_bytes(rows, n, k, items));
   off[kOffTotal] = static_cast<int64_t>(cur);
   return 0;
@@ -120,14 +134,14 @@ int layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t
 }  // namespace alive
 
 extern "C" int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
-                                      int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets12) {
+                                      int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets14) {
   using namespace alive;
-  ALIVE_REQUIRE(offsets12 != nullptr, "alive_knn_match_layout: offsets is NULL");
+  ALIVE_REQUIRE(offsets14 != nullptr, "alive_knn_match_layout: offsets is NULL");
   ALIVE_REQUIRE(rows >= 1 && n >= 1 && k >= 1 && k <= ALIVE_KNN_MAX_K, "alive_knn_match_layout: bad sizes");
   ALIVE_REQUIRE(items >= 1 && rows % items == 0, "alive_knn_match_layout: rows must be a multiple of items");
   ALIVE_REQUIRE(d >= 4 && d % 4 == 0 && d <= 1536, "alive_knn_match: d must be a multiple of 4, <= 1536 (got %d)", d);
   alive_knn_plan_t plan;
-  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets12, nullptr);
+  return layout(rows, n, d, k, r_max, num_sms, variant, resolve_mode(mode, n, d, k), items, &plan, offsets14, nullptr);
 }
 
 namespace alive {
@@ -138,6 +152,8 @@ struct PackedQueries {
   const float* norm;
   const uint16_t* packed;
   const float* err;
+  const uint16_t* lo;      // second plane + its error norms (both or neither; without them the collect pass is not refined)
+  const float* err2;
 };
 int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
                int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max, int32_t mode,
@@ -158,14 +174,16 @@ extern "C" int alive_knn_match(const float* source, int32_t batch, int32_t t, in
 }
 
 extern "C" int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16_t* q_packed,
-                                      const float* q_err, int32_t batch, int32_t t, const alive_knn_library_t* lib,
-                                      int32_t k, float alpha, int32_t r_max, int32_t mode, int32_t num_sms,
-                                      int32_t variant, void* workspace, size_t workspace_bytes, float* out,
-                                      int64_t* top_idx, float* top_score, alive_stream_t stream) {
+                                      const float* q_err, const uint16_t* q_lo, const float* q_err2, int32_t batch,
+                                      int32_t t, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max,
+                                      int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
+                                      size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
+                                      alive_stream_t stream) {
   ALIVE_REQUIRE(q_raw && q_norm && q_packed && q_err, "alive_knn_match_packed: NULL argument");
-  ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(q_packed)) & 15) == 0,
-                "alive_knn_match_packed: q_raw and q_packed must be 16-byte aligned");
-  const alive::PackedQueries pq{q_raw, q_norm, q_packed, q_err};
+  ALIVE_REQUIRE((q_lo == nullptr) == (q_err2 == nullptr), "alive_knn_match_packed: q_lo and q_err2 go together");
+  ALIVE_REQUIRE(((reinterpret_cast<uintptr_t>(q_raw) | reinterpret_cast<uintptr_t>(q_packed) | reinterpret_cast<uintptr_t>(q_lo)) & 15) == 0,
+                "alive_knn_match_packed: q_raw, q_packed and q_lo must be 16-byte aligned");
+  const alive::PackedQueries pq{q_raw, q_norm, q_packed, q_err, q_lo, q_err2};
   return alive::match_impl(nullptr, &pq, batch, t, 0, 0, 0, lib, k, alpha, r_max, mode, num_sms, variant, workspace,
                            workspace_bytes, out, top_idx, top_score, nullptr, nullptr, stream);
 }
@@ -193,7 +211,7 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
   ALIVE_REQUIRE(mode == 1 || mode == 2, "alive_knn_match: mode must be 0 (auto), 1 (screen) or 2 (exact)");
   ALIVE_REQUIRE(mode == 2 || k <= ALIVE_KNN_LIST_LEN, "alive_knn_match: the screened path needs k <= %d", ALIVE_KNN_LIST_LEN);
   alive_knn_plan_t plan;
-  int64_t off[12];
+  int64_t off[kOffSlots];
   CollectLayout cl;
   int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, items, &plan, off, &cl);
   if (rc) return rc;
@@ -205,6 +223,8 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
   const float* q_norm = pq ? pq->norm : reinterpret_cast<float*>(ws + off[kOffQNorm]);
   const uint16_t* q_packed = pq ? pq->packed : reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]);
   const float* q_err = pq ? pq->err : reinterpret_cast<float*>(ws + off[kOffQErr]);
+  const uint16_t* q_lo = pq ? pq->lo : reinterpret_cast<uint16_t*>(ws + off[kOffQLo]);
+  const float* q_err2 = pq ? pq->err2 : reinterpret_cast<float*>(ws + off[kOffQErr2]);
   float* cand_score = reinterpret_cast<float*>(ws + off[kOffCandScore]);
   int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + off[kOffCandIdx]);
   int32_t* sel_n = reinterpret_cast<int32_t*>(ws + off[kOffSelN]);
@@ -213,14 +233,15 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
   void* exact_ws = ws + off[kOffExact];
 
   if (pq == nullptr) {
-    // all batch items in ONE pack launch, which also zeroes the per-item fallback counters (no separate memset node)
+    // all batch items in ONE pack launch, which also zeroes the fallback counters (no separate memset node)
     rc = pack_impl(source, rows, d, stride_t, stride_d, reinterpret_cast<float*>(ws + off[kOffQRaw]),
                    reinterpret_cast<float*>(ws + off[kOffQNorm]), reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]),
-                   reinterpret_cast<float*>(ws + off[kOffQErr]), nullptr, fb_count, items + 1, stream, t, stride_b);
+                   reinterpret_cast<float*>(ws + off[kOffQErr]), nullptr, fb_count, 2 * items, stream, t, stride_b,
+                   reinterpret_cast<uint16_t*>(ws + off[kOffQLo]), reinterpret_cast<float*>(ws + off[kOffQErr2]));
     if (rc) return rc;
   } else {
     // the producer packed the queries (K1 ran as ITS epilogue): only the fallback counters are left to reset
-    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * (items + 1), as_stream(stream)));
+    ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * 2 * items, as_stream(stream)));
   }
   if (mode == 1) {
     if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
@@ -241,16 +262,27 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
     const int32_t* x_list = fb_list;
     const int32_t* x_count = fb_count;
     if (cl.on) {
-      // uncertified queries: a second tensor-core pass collects every frame that reaches the query's
-      // cut, those are rescored exactly; only buffer overflows go on to the exhaustive scan
+      // uncertified queries: a second tensor-core pass collects every frame that reaches the query's cut, those are
+      // rescored exactly; only buffer overflows go on to the exhaustive scan.  With the second bf16 plane of library
+      // and queries the pass is REFINED (hi.hi + hi.lo + lo.hi, error ~4e-5) against a cut derived from a handful of
+      // exact rescorings (refine_prep_kernel): tens of candidates per query on clustered libraries, not thousands.
+      static const bool refine_on = !(getenv("ALIVE_KNN_REFINE") && atoi(getenv("ALIVE_KNN_REFINE")) == 0);
+      const bool refine = refine_on && lib->lo != nullptr && q_lo != nullptr && q_err2 != nullptr;
       int32_t* c_idx = reinterpret_cast<int32_t*>(ca + cl.idx);
       int32_t* fb2_list = reinterpret_cast<int32_t*>(ca + cl.fb2_list);
       int32_t* fb2_count = fb_count + items;
-      rc = collect_impl(qc, lib->packed, &cl.plan, fb_count, c_cut, c_cnt, c_idx, kCollectCap, stream);
+      uint16_t* qc_lo = reinterpret_cast<uint16_t*>(ca + cl.qc_lo);
+      if (refine) {
+        rc = refine_prep_impl(cand_score, cand_idx, plan.lists, k, fb_list, fb_count, rows / items, items, cl.rows_c, q_raw,
+                              q_norm, q_err, q_err2, q_lo, qc_lo, lib->raw, lib->norms, lib->stats, d, c_cut, stream);
+        if (rc) return rc;
+      }
+      rc = collect_impl(qc, lib->packed, &cl.plan, fb_count, c_cut, c_cnt, c_idx, kCollectCap, refine ? qc_lo : nullptr,
+                        refine ? lib->lo : nullptr, stream);
       if (rc) return rc;
-      rc = collect_rescore_impl(fb_list, fb_count, rows, cl.rows_c, c_cnt, c_idx, kCollectCap, k, q_raw, q_norm, lib->raw,
-                                lib->norms, lib->n, d, alpha, out, top_score, top_idx, lib->row_base, fb2_list, fb2_count,
-                                stream);
+      rc = collect_rescore_impl(fb_list, fb_count, rows / items, items, cl.rows_c, c_cnt, c_idx, kCollectCap, k, q_raw, q_norm,
+                                lib->raw, lib->norms, lib->n * items, d, alpha, out, top_score, top_idx, lib->row_base,
+                                fb2_list, fb2_count, stream);
       if (rc) return rc;
       x_list = fb2_list;
       x_count = fb2_count;

@@ -39,7 +39,8 @@ void set_error(const char* fmt, ...);
 // [B, D, T] query batch of one call in ONE launch; 0 = a single item)
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
-              alive_stream_t stream, int64_t item_frames = 0, int64_t stride_b = 0);
+              alive_stream_t stream, int64_t item_frames = 0, int64_t stride_b = 0, uint16_t* lo = nullptr,
+              float* err2 = nullptr);
 // `after_query_pack`: the launch directly follows the query pack of the same call in `stream`; kernels
 // that can use it start early (programmatic dependent launch) and wait for the pack on the device
 int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,
@@ -50,15 +51,22 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
                 int64_t idx_base, float alpha, float* out, float* top_score, int64_t* top_idx, int32_t* sel_n,
                 int32_t* fb_list, int32_t* fb_count, int32_t items, int zero_counts, const uint16_t* q_packed,
                 uint16_t* qc_packed, float* c_cut, int32_t* c_cnt, int32_t rows_c, alive_stream_t stream);
-// second screen pass for uncertified queries (search_sm100.cu, select.cu; driven by api.cu)
+// second screen pass for uncertified queries (search_sm100.cu, select.cu; driven by api.cu); `items` independent
+// (query batch, library) pairs, rows_c compact slots per item; qc_lo / lib_lo: the second bf16 planes (refined
+// accumulation) or NULL
 int collect_impl(const uint16_t* qc_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan,
                  const int32_t* active_rows, const float* cut, int32_t* cnt, int32_t* idx, int32_t cap,
-                 alive_stream_t stream);
-int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_t t, int32_t rows_c, const int32_t* c_cnt,
-                         const int32_t* c_idx, int32_t c_cap, int32_t k, const float* q_raw, const float* q_norm,
-                         const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, float alpha, float* out,
-                         float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list, int32_t* fb2_count,
-                         alive_stream_t stream);
+                 const uint16_t* qc_lo, const uint16_t* lib_lo, alive_stream_t stream);
+int refine_prep_impl(const float* cand_score, const int32_t* cand_idx, int32_t lists, int32_t k, const int32_t* fb_list,
+                     const int32_t* fb_count, int32_t t_item, int32_t items, int32_t rows_c, const float* q_raw,
+                     const float* q_norm, const float* q_err, const float* q_err2, const uint16_t* q_lo, uint16_t* qc_lo,
+                     const float* lib_raw, const float* lib_norm, const uint32_t* lib_stats, int32_t d, float* c_cut,
+                     alive_stream_t stream);
+int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_t t_item, int32_t items, int32_t rows_c,
+                         const int32_t* c_cnt, const int32_t* c_idx, int32_t c_cap, int32_t k, const float* q_raw,
+                         const float* q_norm, const float* lib_raw, const float* lib_norm, int64_t n_total, int32_t d,
+                         float alpha, float* out, float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list,
+                         int32_t* fb2_count, alive_stream_t stream);
 
 // programmatic dependent launch (sm_90+): `launch_dependents` lets the next kernel of the stream be
 // scheduled while this one still runs, `wait` blocks until the kernels it depends on have completed and

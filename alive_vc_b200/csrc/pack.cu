@@ -36,24 +36,48 @@ constexpr int kPackThreads = 256;  // 8 warps
 struct CtaStats {
   unsigned int max_bits;
   unsigned int bad;
+  unsigned int max2_bits;
 };
 __device__ __forceinline__ void cta_stats_init(CtaStats* cs) {
   if (threadIdx.x == 0) {
     cs->max_bits = 0u;
     cs->bad = 0u;
+    cs->max2_bits = 0u;
   }
 }
-__device__ __forceinline__ void cta_stats_add(CtaStats* cs, float e, bool finite) {
-  if (finite) atomicMax(&cs->max_bits, __float_as_uint(e));
-  else atomicAdd(&cs->bad, 1u);
+__device__ __forceinline__ void cta_stats_add(CtaStats* cs, float e, bool finite, float e2nd) {
+  if (finite) {
+    atomicMax(&cs->max_bits, __float_as_uint(e));
+    atomicMax(&cs->max2_bits, __float_as_uint(e2nd));
+  } else {
+    atomicAdd(&cs->bad, 1u);
+  }
 }
 // after a __syncthreads() that follows every cta_stats_add of the CTA
 __device__ __forceinline__ void cta_stats_publish(const CtaStats* cs, unsigned int* __restrict__ stats) {
   if (threadIdx.x == 0 && stats != nullptr) {
     if (cs->max_bits > __ldcg(&stats[0])) atomicMax(&stats[0], cs->max_bits);
     if (cs->bad) atomicAdd(&stats[1], cs->bad);
+    if (cs->max2_bits > __ldcg(&stats[2])) atomicMax(&stats[2], cs->max2_bits);
   }
 }
+
+// Optional second bf16 plane (the split-bf16 refinement of the screen, search_sm100.cu collect mode):
+//   lo   [n,d] bf16 = bf16_rn(a - hi)   where a = x/|x| (float32) and hi = bf16_rn(a) is the `packed` plane
+//   err2 [n]   f32  = || a - hi - lo ||_2 (rounded up); stats[2] = max of its bits over the finite rows
+// Both subtractions are exact in float32 (a value minus its own rounding).
+struct Refine {
+  __nv_bfloat16* lo;
+  float* err2;
+};
+// lo bits of an element; fh = float(hi); *r2 = a - hi - lo
+__device__ __forceinline__ unsigned short split_lo(float a, float fh, float* r2) {
+  const float r1 = a - fh;
+  const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+  *r2 = r1 - __bfloat162float(l);
+  return __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ float round_up_norm2(float sumsq) { return sqrtf(sumsq) * 1.0001f + 1e-12f; }
 
 // Query batches [B, D, T] arrive as B items of `item_frames` frames, `stride_b` elements apart (one
 // launch for all items; output rows b*item_frames + t).  A library is one item.
@@ -74,7 +98,7 @@ __global__ void __launch_bounds__(kPackThreads)
 pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, long long stride_d,
             float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
             float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero,
-            int async_stage) {
+            int async_stage, const Refine rf) {
   extern __shared__ float tile[];          // [d][kFrames + 1]
   __shared__ CtaStats cta_stats;
   cta_stats_init(&cta_stats);
@@ -138,7 +162,7 @@ pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, 
     }
     ss = warp_sum_f64(ss);
     const float nrm = static_cast<float>(sqrt(ss));
-    double e2 = 0.0;
+    double e2 = 0.0, e22 = 0.0;
     bool finite = true;
     // two channels per lane so the bf16 row is written as 4-byte words
     for (int j = 2 * lane; j < d; j += 64) {
@@ -152,15 +176,22 @@ pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, 
       h2.x = ha;
       h2.y = hb;
       *reinterpret_cast<__nv_bfloat162*>(packed + row * d + j) = h2;
+      float ra, rb;
+      const unsigned la = split_lo(a, __bfloat162float(ha), &ra), lb = split_lo(b, __bfloat162float(hb), &rb);
+      e22 += static_cast<double>(ra) * ra + static_cast<double>(rb) * rb;
+      if (rf.lo) *reinterpret_cast<unsigned*>(rf.lo + row * d + j) = la | (lb << 16);
     }
     e2 = warp_sum_f64(e2);
+    e22 = warp_sum_f64(e22);
     finite = __all_sync(0xffffffffu, finite);
     if (lane == 0) {
       norms[row] = nrm;
       // round the error norm UP a little: it feeds a bound that must not be under-estimated
       float e = finite ? static_cast<float>(sqrt(e2)) * 1.0001f + 1e-9f : 0.f;
+      const float e2nd = finite ? round_up_norm2(static_cast<float>(e22)) : 0.f;
       if (err) err[row] = e;
-      cta_stats_add(&cta_stats, e, finite);
+      if (rf.err2) rf.err2[row] = e2nd;
+      cta_stats_add(&cta_stats, e, finite, e2nd);
     }
   }
   __syncthreads();
@@ -192,14 +223,17 @@ __device__ __forceinline__ float div_by_norm(float x, float nrm, float r) {
 }
 __device__ __forceinline__ bool norm_is_tame(float nrm) { return nrm >= 0x1p-40f && nrm <= 0x1p40f; }
 
-__device__ __forceinline__ void finish_frame(long long row, float nrm, float e2, bool finite, float* __restrict__ norms,
-                                             float* __restrict__ err, CtaStats* cta_stats) {
+__device__ __forceinline__ void finish_frame(long long row, float nrm, float e2, float e22, bool finite,
+                                             float* __restrict__ norms, float* __restrict__ err, const Refine& rf,
+                                             CtaStats* cta_stats) {
   norms[row] = nrm;
   // round the error norm UP a little: it feeds a bound that must not be under-estimated (the fp32 sum of
   // d squares is within 2e-6 relative of the exact one)
   const float e = finite ? sqrtf(e2) * 1.0001f + 1e-9f : 0.f;
+  const float e2nd = finite ? round_up_norm2(e22) : 0.f;
   if (err) err[row] = e;
-  cta_stats_add(cta_stats, e, finite);
+  if (rf.err2) rf.err2[row] = e2nd;
+  cta_stats_add(cta_stats, e, finite, e2nd);
 }
 
 // Channel-major input (the reference's [D, N], stride_n == 1, 16-byte aligned rows): a tile = 32
@@ -243,7 +277,7 @@ __device__ __forceinline__ void cm_stage(float* tile, const float* __restrict__ 
 // warp w: frames 4w..4w+3 of the tile, lane: channels lane, lane+32, ...
 __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int nf, int d, float* __restrict__ raw,
                                            float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
-                                           float* __restrict__ err, CtaStats* cta_stats) {
+                                           float* __restrict__ err, const Refine& rf, CtaStats* cta_stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fw = 4 * warp;
   const long long row0 = f0 + fw;
@@ -283,13 +317,14 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
   nrm[2] = static_cast<float>(sqrt(warp_sum_f64(ss2)));
   nrm[3] = static_cast<float>(sqrt(warp_sum_f64(ss3)));
   bool tame[4], finite[4];
-  float rinv[4], e2[4];
+  float rinv[4], e2[4], e22[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     tame[c] = norm_is_tame(nrm[c]);
     rinv[c] = tame[c] ? __frcp_rn(nrm[c]) : 0.f;
     finite[c] = true;
     e2[c] = 0.f;
+    e22[c] = 0.f;
   }
   if (tame[0] && tame[1] && tame[2] && tame[3]) {
     // Common case, branch-free per element (the per-element `tame` / small-quotient branches of the first version
@@ -302,6 +337,9 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
     unsigned* pkA = reinterpret_cast<unsigned*>(packed + (row0 + my_f) * d);
     unsigned* pkB = reinterpret_cast<unsigned*>(packed + (row0 + my_f + 1) * d);
     const bool okA = my_f < nv, okB = my_f + 1 < nv;
+    const bool want_lo = rf.lo != nullptr;
+    unsigned* loA = want_lo ? reinterpret_cast<unsigned*>(rf.lo + (row0 + my_f) * d) : nullptr;
+    unsigned* loB = want_lo ? reinterpret_cast<unsigned*>(rf.lo + (row0 + my_f + 1) * d) : nullptr;
     // one 32-channel step; kTail: the last, partial step of a d that is not a multiple of 32 (d is even: the two
     // lanes of a pair are live together; dead lanes still take part in the exchange)
     auto step = [&](int j, bool live) {
@@ -326,13 +364,14 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
       const __nv_bfloat162 p01 = __floats2bfloat162_rn(a[0], a[1]);
       const __nv_bfloat162 p23 = __floats2bfloat162_rn(a[2], a[3]);
       const unsigned w01 = *reinterpret_cast<const unsigned*>(&p01), w23 = *reinterpret_cast<const unsigned*>(&p23);
+      // a - hi per frame (exact), negated: what the second plane has to carry
+      const float r0 = a[0] - __uint_as_float(w01 << 16), r1 = a[1] - __uint_as_float(w01 & 0xffff0000u);
+      const float r2 = a[2] - __uint_as_float(w23 << 16), r3 = a[3] - __uint_as_float(w23 & 0xffff0000u);
       if (live) {
-        const float d0 = __uint_as_float(w01 << 16) - a[0], d1 = __uint_as_float(w01 & 0xffff0000u) - a[1];
-        const float d2 = __uint_as_float(w23 << 16) - a[2], d3 = __uint_as_float(w23 & 0xffff0000u) - a[3];
-        e2[0] = fmaf(d0, d0, e2[0]);
-        e2[1] = fmaf(d1, d1, e2[1]);
-        e2[2] = fmaf(d2, d2, e2[2]);
-        e2[3] = fmaf(d3, d3, e2[3]);
+        e2[0] = fmaf(r0, r0, e2[0]);
+        e2[1] = fmaf(r1, r1, e2[1]);
+        e2[2] = fmaf(r2, r2, e2[2]);
+        e2[3] = fmaf(r3, r3, e2[3]);
       }
       const unsigned keep = odd ? w23 : w01;                                       // my channel, the frames I store
       const unsigned got = __shfl_xor_sync(0xffffffffu, odd ? w01 : w23, 1);       // partner's channel, my frames
@@ -340,6 +379,27 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
       const int w = j >> 1;                                                         // word index of the channel pair
       if (okA && live) pkA[w] = __byte_perm(ev, od, 0x5410);                        // frame A: (even ch, odd ch)
       if (okB && live) pkB[w] = __byte_perm(ev, od, 0x7632);                        // frame B
+      {
+        // second plane: lo = bf16_rn(a - hi), residual a - hi - lo feeds err2 (always) and the plane is stored on request
+        const __nv_bfloat162 q01 = __floats2bfloat162_rn(r0, r1);
+        const __nv_bfloat162 q23 = __floats2bfloat162_rn(r2, r3);
+        const unsigned l01 = *reinterpret_cast<const unsigned*>(&q01), l23 = *reinterpret_cast<const unsigned*>(&q23);
+        if (live) {
+          const float s0 = r0 - __uint_as_float(l01 << 16), s1 = r1 - __uint_as_float(l01 & 0xffff0000u);
+          const float s2 = r2 - __uint_as_float(l23 << 16), s3 = r3 - __uint_as_float(l23 & 0xffff0000u);
+          e22[0] = fmaf(s0, s0, e22[0]);
+          e22[1] = fmaf(s1, s1, e22[1]);
+          e22[2] = fmaf(s2, s2, e22[2]);
+          e22[3] = fmaf(s3, s3, e22[3]);
+        }
+        if (want_lo) {                                                               // (warp-uniform)
+          const unsigned lkeep = odd ? l23 : l01;
+          const unsigned lgot = __shfl_xor_sync(0xffffffffu, odd ? l01 : l23, 1);
+          const unsigned lev = odd ? lgot : lkeep, lod = odd ? lkeep : lgot;
+          if (okA && live) loA[w] = __byte_perm(lev, lod, 0x5410);
+          if (okB && live) loB[w] = __byte_perm(lev, lod, 0x7632);
+        }
+      }
     };
     const int d_full = d & ~31;
 #pragma unroll 2
@@ -364,15 +424,22 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
         const float da = __bfloat162float(hb) - a;
         e2[c] = fmaf(da, da, e2[c]);
         if (c < nv) pk16[(row0 + c) * d + j] = __bfloat16_as_ushort(hb);
+        float r2nd;
+        const unsigned short lb = split_lo(a, __bfloat162float(hb), &r2nd);
+        e22[c] = fmaf(r2nd, r2nd, e22[c]);
+        if (rf.lo && c < nv) reinterpret_cast<unsigned short*>(rf.lo)[(row0 + c) * d + j] = lb;
       }
     }
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e2[c] += __shfl_xor_sync(0xffffffffu, e2[c], o);
+    for (int o = 16; o > 0; o >>= 1) {
+      e2[c] += __shfl_xor_sync(0xffffffffu, e2[c], o);
+      e22[c] += __shfl_xor_sync(0xffffffffu, e22[c], o);
+    }
     finite[c] = __all_sync(0xffffffffu, finite[c]);
-    if (lane == 0 && c < nv) finish_frame(row0 + c, nrm[c], e2[c], finite[c], norms, err, cta_stats);
+    if (lane == 0 && c < nv) finish_frame(row0 + c, nrm[c], e2[c], e22[c], finite[c], norms, err, rf, cta_stats);
   }
 }
 
@@ -380,7 +447,7 @@ template <bool kDouble>
 __global__ void __launch_bounds__(kPackThreads)
 pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride_d, float* __restrict__ raw,
                float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
-               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
   extern __shared__ __align__(16) float tile[];   // [kDouble ? 2 : 1][d][36]
   __shared__ CtaStats cta_stats;
   cta_stats_init(&cta_stats);
@@ -401,7 +468,7 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    cm_compute(cur, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, raw, norms, packed, err, &cta_stats);
+    cm_compute(cur, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, raw, norms, packed, err, rf, &cta_stats);
     __syncthreads();                 // every warp is done with `cur` before it is refilled
     if (!kDouble && tn < n_tiles)
       cm_stage(tile, x, tn * 32, static_cast<int>(min(32ll, n - tn * 32)), d, stride_d);
@@ -415,7 +482,7 @@ constexpr int kRmMaxV = 12;                         // float4 per lane: d <= 153
 __global__ void __launch_bounds__(kPackThreads)
 pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, float* __restrict__ raw,
                float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
-               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+               unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
   pdl_launch_dependents();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
@@ -450,14 +517,15 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
   const bool tame = norm_is_tame(nrm);
   const float rinv = tame ? __frcp_rn(nrm) : 0.f;
   bool finite = true;
-  float e2 = 0.f;
+  float e2 = 0.f, e22 = 0.f;
   uint2* dst_pk = reinterpret_cast<uint2*>(packed + row * d);
+  uint2* dst_lo = rf.lo ? reinterpret_cast<uint2*>(rf.lo + row * d) : nullptr;
 #pragma unroll
   for (int i = 0; i < kRmMaxV; ++i) {
     const int q = lane + 32 * i;
     if (q < d4) {
       const float xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      unsigned short hb[4];
+      unsigned short hb[4], lb[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float a;
@@ -471,15 +539,24 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
         const float da = __bfloat162float(h) - a;
         e2 = fmaf(da, da, e2);
         hb[c] = __bfloat16_as_ushort(h);
+        float r2nd;
+        lb[c] = split_lo(a, __bfloat162float(h), &r2nd);
+        e22 = fmaf(r2nd, r2nd, e22);
       }
       dst_pk[q] = make_uint2(static_cast<unsigned>(hb[0]) | (static_cast<unsigned>(hb[1]) << 16),
                              static_cast<unsigned>(hb[2]) | (static_cast<unsigned>(hb[3]) << 16));
+      if (dst_lo)
+        dst_lo[q] = make_uint2(static_cast<unsigned>(lb[0]) | (static_cast<unsigned>(lb[1]) << 16),
+                               static_cast<unsigned>(lb[2]) | (static_cast<unsigned>(lb[3]) << 16));
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    e22 += __shfl_xor_sync(0xffffffffu, e22, o);
+  }
   finite = __all_sync(0xffffffffu, finite);
-  if (lane == 0) finish_frame(row, nrm, e2, finite, norms, err, &cta_stats);
+  if (lane == 0) finish_frame(row, nrm, e2, e22, finite, norms, err, rf, &cta_stats);
   }  // row < n
   __syncthreads();
   cta_stats_publish(&cta_stats, stats);
@@ -490,8 +567,10 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
 __global__ void __launch_bounds__(kPackThreads)
 pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, long long stride_d,
                   float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
-                  float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero) {
+                  float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero,
+                  const Refine rf) {
   __shared__ double red[kPackThreads / 32];
+  __shared__ double red2[kPackThreads / 32];
   pdl_launch_dependents();                 // a search launched behind this pack may start streaming the library
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
@@ -517,7 +596,7 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMa
   for (int w = 0; w < kPackThreads / 32; ++w) tot += red[w];     // same order in every thread
   const float nrm = static_cast<float>(sqrt(tot));
   __syncthreads();
-  double e2 = 0.0;
+  double e2 = 0.0, e22 = 0.0;
   bool finite = true;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
@@ -529,28 +608,40 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMa
       e2 += static_cast<double>(da) * da;
       finite = finite && isfinite(a);
       packed[row * d + j] = h;
+      float r2nd;
+      const unsigned short lb = split_lo(a, __bfloat162float(h), &r2nd);
+      e22 += static_cast<double>(r2nd) * r2nd;
+      if (rf.lo) reinterpret_cast<unsigned short*>(rf.lo)[row * d + j] = lb;
     }
   }
   e2 = warp_sum_f64(e2);
+  e22 = warp_sum_f64(e22);
   finite = __all_sync(0xffffffffu, finite);
   if (lane == 0) {
     red[warp] = e2;
+    red2[warp] = e22;
     fin[warp] = finite ? 1 : 0;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double et = 0.0;
+    double et = 0.0, et2 = 0.0;
     bool ok = true;
     for (int w = 0; w < kPackThreads / 32; ++w) {
       et += red[w];
+      et2 += red2[w];
       ok = ok && fin[w];
     }
     norms[row] = nrm;
     const float e = ok ? static_cast<float>(sqrt(et)) * 1.0001f + 1e-9f : 0.f;
+    const float e2nd = ok ? round_up_norm2(static_cast<float>(et2)) : 0.f;
     if (err) err[row] = e;
+    if (rf.err2) rf.err2[row] = e2nd;
     if (stats) {
       if (!ok) atomicAdd(&stats[1], 1u);
-      else if (__float_as_uint(e) > __ldcg(&stats[0])) atomicMax(&stats[0], __float_as_uint(e));
+      else {
+        if (__float_as_uint(e) > __ldcg(&stats[0])) atomicMax(&stats[0], __float_as_uint(e));
+        if (__float_as_uint(e2nd) > __ldcg(&stats[2])) atomicMax(&stats[2], __float_as_uint(e2nd));
+      }
     }
   }
 }
@@ -561,8 +652,10 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMa
 namespace alive {
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
-              alive_stream_t stream, int64_t item_frames, int64_t stride_b) {
+              alive_stream_t stream, int64_t item_frames, int64_t stride_b, uint16_t* lo, float* err2) {
   ALIVE_REQUIRE(x && raw && norms && packed, "alive_knn_pack: NULL argument");
+  ALIVE_REQUIRE(lo == nullptr || (reinterpret_cast<uintptr_t>(lo) & 7) == 0, "alive_knn_pack: lo must be 8-byte aligned");
+  const Refine rf{reinterpret_cast<__nv_bfloat16*>(lo), err2};
   if (item_frames <= 0 || item_frames >= n) {       // one item: the plain [n] frame sequence
     item_frames = n > 0 ? n : 1;
     stride_b = 0;
@@ -599,7 +692,7 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
   const bool out16 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
   if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && (uniform || stride_b % 4 == 0) && x16 && out16) {
     pack_rm_kernel<<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, as_stream(stream)>>>(
-        x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero);
+        x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
   } else if (fast && uniform && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
     const size_t smem = static_cast<size_t>(d) * kCmLd * sizeof(float);
     const long long n_tiles = (n + 31) / 32;
@@ -615,22 +708,22 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
     }
     if (dbl && d <= 768 && n_tiles >= 4ll * num_sms) {
       pack_cm_kernel<true><<<static_cast<unsigned>(num_sms), kPackThreads, 2 * smem, as_stream(stream)>>>(
-          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
     } else {
       pack_cm_kernel<false><<<static_cast<unsigned>(n_tiles), kPackThreads, smem, as_stream(stream)>>>(
-          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero);
+          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
     }
   } else if (n <= 512) {
     pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, fm, stride_d, raw,
-                                                                                       norms, pk, err, stats, zero_words, n_zero);
+                                                                                       norms, pk, err, stats, zero_words, n_zero, rf);
   } else if (n <= 8192) {
     const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
     pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
+        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage, rf);
   } else {
     const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
     pack_kernel<32><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage);
+        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage, rf);
   }
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -639,6 +732,6 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
 
 extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
                               float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
-                              alive_stream_t stream) {
-  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream, 0, 0);
+                              uint16_t* lo, float* err2, alive_stream_t stream) {
+  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream, 0, 0, lo, err2);
 }

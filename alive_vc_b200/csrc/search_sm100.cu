@@ -49,14 +49,20 @@ constexpr int kThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);   // 384
 constexpr int kTmemCols = 512;                                  // 2 accumulators x 256 columns
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;             // 16 KB per stage per CTA
 
-template <int kCtas> struct Cfg {
-  static constexpr int kStages = (kCtas == 1) ? 4 : 6;
+// kRefine (collect mode only): every stage carries BOTH bf16 planes of both operands (hi = bf16(x^), lo = bf16(x^ - hi))
+// and the MMA warp accumulates hi.hi + hi.lo + lo.hi - the split-bf16 refinement of the screen (error ~1e-5 instead
+// of ~4e-3).  Twice the bytes per stage, so fewer stages; the collecting epilogue needs no insert scratch.
+template <int kCtas, bool kRefine = false> struct Cfg {
+  static constexpr int kPlanes = kRefine ? 2 : 1;
+  static constexpr int kStages = kRefine ? ((kCtas == 1) ? 2 : 3) : ((kCtas == 1) ? 4 : 6);
   static constexpr int kBRows = kBlockN / kCtas;                       // library rows this CTA loads per tile
-  static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;            // 32 KB or 16 KB
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;            // 32 KB or 16 KB (one plane)
+  static constexpr uint32_t kAStage = kABytes * kPlanes;               // bytes of A per stage (hi [+ lo])
+  static constexpr uint32_t kBStage = kBBytes * kPlanes;
+  static constexpr uint32_t kStageBytes = kAStage + kBStage;
   static constexpr uint32_t kTxBytes = kStageBytes * kCtas;            // bytes landing per stage, whole unit
   static constexpr uint32_t kSmemData = kStages * kStageBytes;
-  static constexpr uint32_t kScratchBytes = 32 * kNumEpiWarps * 32 * 4;  // epilogue chunk scratch, 32 KB
+  static constexpr uint32_t kScratchBytes = kRefine ? 0 : 32 * kNumEpiWarps * 32 * 4;  // epilogue chunk scratch, 32 KB
   static constexpr uint32_t kSmemBytes = kSmemData + kScratchBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -80,10 +86,10 @@ struct SearchParams {
   int sync_rounds;               // ... for this many epochs (every CTA reaches them)
   // collect mode (knn_search_kernel<kCtas, true>): instead of running top lists, EVERY frame whose
   // screened score is not below the row's cut is appended to the row's candidate buffer
-  const int* c_active;           // device: number of live query rows (rows beyond it are skipped)
-  const float* c_cut;            // [t] per-row cut (S_k - 2 eps from the first pass)
-  int* c_cnt;                    // [t] candidates found (may exceed c_cap: overflow)
-  int* c_idx;                    // [t, c_cap] frame indices
+  const int* c_active;           // device [items]: live query rows of every item (rows beyond it are skipped)
+  const float* c_cut;            // [items * t] per-row cut (the refined lower bound, or S_k - 2 eps of the first pass)
+  int* c_cnt;                    // [items * t] candidates found (may exceed c_cap: overflow)
+  int* c_idx;                    // [items * t, c_cap] frame indices
   int c_cap;
 };
 
@@ -337,25 +343,31 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_ba
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int kCtas, bool kCollect>
+template <int kCtas, bool kCollect, bool kRefine>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_lib,
+                  const __grid_constant__ CUtensorMap tmap_q_lo, const __grid_constant__ CUtensorMap tmap_lib_lo,
                   const SearchParams p) {
-  using C = Cfg<kCtas>;
+  static_assert(!kRefine || kCollect, "the refined accumulation exists in collect mode only");
+  using C = Cfg<kCtas, kRefine>;
   constexpr int kStages = C::kStages;
-  // collect mode: only the query units that hold live rows do any work (the count lives on the device)
-  int m_active = p.m_units;
+  // collect mode: only the query units that hold live rows do any work (the counts live on the device)
+  auto m_active_of = [&](int item) -> int {
+    if constexpr (!kCollect) return p.m_units;
+    const int live = min(p.c_active[item], p.t);
+    return (live + kBlockM * kCtas - 1) / (kBlockM * kCtas);
+  };
   if constexpr (kCollect) {
     pdl_wait();
-    const int live = min(*p.c_active, p.t);
-    m_active = (live + kBlockM * kCtas - 1) / (kBlockM * kCtas);
-    if (m_active == 0) return;               // nothing fell back: uniform exit before any setup
+    int any = 0;
+    for (int i = 0; i < p.items; ++i) any |= p.c_active[i];
+    if (any <= 0) return;                    // nothing fell back: uniform exit before any setup
   }
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024 B alignment
-  const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + kStages * kABytes;
+  const uint32_t smem_a = smem_base;                              // per stage: A hi [, A lo]
+  const uint32_t smem_b = smem_base + kStages * C::kAStage;       // per stage: B hi [, B lo]
   const uint32_t scratch_off = C::kSmemData;                     // [32][256] floats
   const uint32_t bars = smem_base + C::kSmemData + C::kScratchBytes;
   const uint32_t bar_full = bars;                                // kStages x 8 B
@@ -377,6 +389,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_lib);
+    if constexpr (kRefine) {
+      tma_prefetch_desc(&tmap_q_lo);
+      tma_prefetch_desc(&tmap_lib_lo);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -411,7 +427,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int item = unit / units_per_item;
         const int rem = unit - item * units_per_item;
         const int m_unit = rem % p.m_units;
-        if (kCollect && m_unit >= m_active) continue;
+        if (kCollect && m_unit >= m_active_of(item)) continue;
         const int seg = rem / p.m_units;
         const int tile0 = seg * p.tiles_per_segment;
         const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
@@ -443,10 +459,15 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               // debug 3 (timing experiment only, results are garbage): query tiles are loaded for the
               // first library tile of a unit only - an upper bound for what a resident query tile would buy
               const bool load_q = p.debug != 3 || tile == tile0;
-              if (leader) mbar_expect_tx(bar_full + 8 * stage, load_q ? C::kTxBytes : C::kBBytes * kCtas);
+              if (leader) mbar_expect_tx(bar_full + 8 * stage, load_q ? C::kTxBytes : C::kBStage * kCtas);
               if (load_q)
-                tma_load_2d<kCtas>(smem_a + stage * kABytes, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row, p.hint_q);
-              tma_load_2d<kCtas>(smem_b + stage * C::kBBytes, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row, p.hint_lib);
+                tma_load_2d<kCtas>(smem_a + stage * C::kAStage, &tmap_q, full0 + 8 * stage, kb * kBlockK, q_row, p.hint_q);
+              tma_load_2d<kCtas>(smem_b + stage * C::kBStage, &tmap_lib, full0 + 8 * stage, kb * kBlockK, lib_row, p.hint_lib);
+              if constexpr (kRefine) {
+                tma_load_2d<kCtas>(smem_a + stage * C::kAStage + kABytes, &tmap_q_lo, full0 + 8 * stage, kb * kBlockK, q_row, p.hint_q);
+                tma_load_2d<kCtas>(smem_b + stage * C::kBStage + C::kBBytes, &tmap_lib_lo, full0 + 8 * stage, kb * kBlockK, lib_row,
+                                   p.hint_lib);
+              }
             }
             __syncwarp();
           }
@@ -460,7 +481,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       constexpr uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN);
       uint32_t it = 0, tile_count = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
-        if (kCollect && (unit % units_per_item) % p.m_units >= m_active) continue;
+        if (kCollect && (unit % units_per_item) % p.m_units >= m_active_of(unit / units_per_item)) continue;
         const int seg = (unit % units_per_item) / p.m_units;
         const int tile0 = seg * p.tiles_per_segment;
         const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
@@ -476,12 +497,22 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             mbar_wait(bar_full + 8 * stage, phase);
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              const uint64_t adesc = make_smem_desc(smem_a + stage * kABytes);
-              const uint64_t bdesc = make_smem_desc(smem_b + stage * C::kBBytes);
+              const uint64_t adesc = make_smem_desc(smem_a + stage * C::kAStage);
+              const uint64_t bdesc = make_smem_desc(smem_b + stage * C::kBStage);
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
                 umma_bf16<kCtas>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              if constexpr (kRefine) {
+                // the two cross terms of (hi + lo).(hi + lo); lo.lo (<= |dq||dr| ~ 3e-6) is part of the error bound
+                const uint64_t adesc_lo = make_smem_desc(smem_a + stage * C::kAStage + kABytes);
+                const uint64_t bdesc_lo = make_smem_desc(smem_b + stage * C::kBStage + C::kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  umma_bf16<kCtas>(tmem_d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1u);
+                  umma_bf16<kCtas>(tmem_d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                }
               }
               umma_commit<kCtas>(bar_empty + 8 * stage);   // smem slot reusable once these MMAs retire
               if (kb == p.k_blocks - 1) umma_commit<kCtas>(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
@@ -504,12 +535,12 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const int item = unit / units_per_item;
       const int rem = unit - item * units_per_item;
       const int m_unit = rem % p.m_units;
-      if (kCollect && m_unit >= m_active) continue;
+      if (kCollect && m_unit >= m_active_of(item)) continue;
       const int seg = rem / p.m_units;
       const int tile0 = seg * p.tiles_per_segment;
       const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
       const int row_in_item = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
-      const bool row_valid = row_in_item < (kCollect ? min(*p.c_active, p.t) : p.t);
+      const bool row_valid = row_in_item < (kCollect ? min(p.c_active[item], p.t) : p.t);
       const int row = item * p.t + row_in_item;          // global query index
       const int col_item0 = item * p.n;                  // frame indices are global: item*n + frame
       const int n_valid = col_item0 + p.n;
@@ -577,7 +608,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
               }
             }
-          } else {
+          } else if constexpr (!kRefine) {
             if (p.debug == 0 || p.debug == 3) scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
             else s[0] = fmaxf(s[0], __uint_as_float(v[0] ^ v[13] ^ v[31]));
           }
@@ -892,18 +923,28 @@ struct CollectArgs {
   int* cnt;
   int* idx;
   int cap;
+  const uint16_t* q_lo;      // second bf16 planes (refined accumulation), or NULL
+  const uint16_t* lib_lo;
 };
 
-template <int kCtas, bool kCollect = false>
+template <int kCtas, bool kCollect = false, bool kRefine = false>
 int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t& plan, float* cand_score,
                   int32_t* cand_idx, int after_query_pack, cudaStream_t stream, const CollectArgs* ca = nullptr) {
-  using C = Cfg<kCtas>;
-  CUtensorMap mq, ml;
+  using C = Cfg<kCtas, kRefine>;
+  CUtensorMap mq, ml, mq_lo, ml_lo;
   const uint64_t items = static_cast<uint64_t>(plan.items < 1 ? 1 : plan.items);
   int rc = make_map(&mq, q, items * static_cast<uint64_t>(plan.t), static_cast<uint64_t>(plan.d), kBlockM);
   if (rc) return rc;
   rc = make_map(&ml, lib, items * static_cast<uint64_t>(plan.n), static_cast<uint64_t>(plan.d), C::kBRows);
   if (rc) return rc;
+  mq_lo = mq;
+  ml_lo = ml;
+  if constexpr (kRefine) {
+    rc = make_map(&mq_lo, ca->q_lo, items * static_cast<uint64_t>(plan.t), static_cast<uint64_t>(plan.d), kBlockM);
+    if (rc) return rc;
+    rc = make_map(&ml_lo, ca->lib_lo, items * static_cast<uint64_t>(plan.n), static_cast<uint64_t>(plan.d), C::kBRows);
+    if (rc) return rc;
+  }
   SearchParams p;
   p.items = static_cast<int>(items);
   p.t = plan.t;
@@ -963,8 +1004,8 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   static PerDeviceOnce attr_once;
   {
     const int rc_attr = attr_once.run([]() -> int {
-      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(knn_search_kernel<kCtas, kCollect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(C::kSmemBytes))));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(knn_search_kernel<kCtas, kCollect, kRefine>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::kSmemBytes))));
       return 0;
     });
     if (rc_attr) return rc_attr;
@@ -983,7 +1024,7 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = after_query_pack ? 2 : 1;
-  ALIVE_CHECK_CUDA((cudaLaunchKernelEx(&cfg, knn_search_kernel<kCtas, kCollect>, mq, ml, p)));
+  ALIVE_CHECK_CUDA((cudaLaunchKernelEx(&cfg, knn_search_kernel<kCtas, kCollect, kRefine>, mq, ml, mq_lo, ml_lo, p)));
   return 0;
 }
 
@@ -1149,12 +1190,19 @@ namespace alive {
 // second screen pass of the one-call pipeline: see SearchParams (collect mode) and select.cu
 int collect_impl(const uint16_t* qc_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan,
                  const int32_t* active_rows, const float* cut, int32_t* cnt, int32_t* idx, int32_t cap,
-                 alive_stream_t stream) {
-  ALIVE_REQUIRE(plan && plan->kernel == 0 && plan->items == 1, "collect pass: needs a tiled single-item plan");
-  CollectArgs ca{active_rows, cut, cnt, idx, cap};
-  if (plan->ctas_per_unit == 1)
-    return launch_search<1, true>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
-  return launch_search<2, true>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
+                 const uint16_t* qc_lo, const uint16_t* lib_lo, alive_stream_t stream) {
+  ALIVE_REQUIRE(plan && plan->kernel == 0, "collect pass: needs a tiled plan");
+  ALIVE_REQUIRE((qc_lo == nullptr) == (lib_lo == nullptr), "collect pass: the second planes of queries and library go together");
+  ALIVE_REQUIRE(lib_lo == nullptr || ((reinterpret_cast<uintptr_t>(qc_lo) | reinterpret_cast<uintptr_t>(lib_lo)) & 15) == 0,
+                "collect pass: second planes must be 16-byte aligned");
+  CollectArgs ca{active_rows, cut, cnt, idx, cap, qc_lo, lib_lo};
+  const bool refine = lib_lo != nullptr;
+  if (plan->ctas_per_unit == 1) {
+    if (refine) return launch_search<1, true, true>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
+    return launch_search<1, true, false>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
+  }
+  if (refine) return launch_search<2, true, true>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
+  return launch_search<2, true, false>(qc_packed, lib_packed, *plan, nullptr, nullptr, 1, as_stream(stream), &ca);
 }
 
 int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,

@@ -17,9 +17,13 @@ namespace {
 constexpr int kListLen = ALIVE_KNN_LIST_LEN;
 constexpr int kMaxK = ALIVE_KNN_MAX_K;
 constexpr int kMaxRMax = 256;
-// slack added to the screening error bound: fp32 accumulation inside the tensor core over
-// d <= 1536 terms with |partial sums| <= 1 (d * 2^-22 = 3.7e-4 worst case) + final roundings
-constexpr float kAccumSlack = 4.0e-4f;
+// Slack added to the screening error bound for the fp32 accumulation inside the tensor core.  Model, measured on the
+// B200 (tools/gpu_tc_error.py, tests/test_gpu_parity.py::test_tensor_core_accumulation_error_model): every
+// tcgen05.mma (K = 16) adds its 16 exact bf16 x bf16 products to the accumulator and TRUNCATES the sum to float32
+// (the error is one-sided, never positive) - at most one ulp of the accumulator, |acc| < 2, per instruction.  Observed
+// over 10^7 pairs with scores up to 1.0: max 2.1e-6 at d = 768 (48 instructions), 4.6e-6 at d = 1536.  The bound
+// used is TWICE the model: n_mma * 2^-22 (d = 768: 1.1e-5), plus the final roundings.
+__host__ __device__ inline float accum_slack(int n_mma) { return static_cast<float>(n_mma) * 0x1p-22f + 2e-7f; }
 
 __device__ __forceinline__ float warp_max_f32(float v) {
 #pragma unroll
@@ -33,7 +37,7 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int prune_query(const float* __restrict__ sc, const int* __restrict__ ix, int lists,
                                            int k, float qe, float qn, const unsigned int* __restrict__ lib_stats,
-                                           int r_max, int* sel, int lane) {
+                                           int r_max, int* sel, int lane, int d) {
   const int entries = lists * kListLen;
   // tau: upper bound on every screened score that any list dropped (= max of list minima;
   // a list that never filled has minimum -inf and dropped nothing)
@@ -71,7 +75,7 @@ __device__ __forceinline__ int prune_query(const float* __restrict__ sc, const i
   }
 
   const float le = __uint_as_float(lib_stats[0]);
-  const float eps = (le + qe + le * qe + kAccumSlack) * 1.00001f;
+  const float eps = (le + qe + le * qe + accum_slack(d / 16)) * 1.00001f;
   const float cut = sk - 2.0f * eps - 1e-7f;
   if (lib_stats[1] != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > tau)) return -1;
 
@@ -92,13 +96,13 @@ __global__ void __launch_bounds__(256)
 prune_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int t, int lists, int k,
              const float* __restrict__ q_err, const float* __restrict__ q_norm,
              const unsigned int* __restrict__ lib_stats, int r_max, int* __restrict__ sel_idx,
-             int* __restrict__ sel_n, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+             int* __restrict__ sel_n, int* __restrict__ fb_list, int* __restrict__ fb_count, int d) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= t) return;
   const size_t entries = static_cast<size_t>(lists) * kListLen;
   const int count = prune_query(cand_score + q * entries, cand_idx + q * entries, lists, k, q_err[q], q_norm[q],
-                                lib_stats, r_max, sel_idx + static_cast<size_t>(q) * r_max, lane);
+                                lib_stats, r_max, sel_idx + static_cast<size_t>(q) * r_max, lane, d);
   if (lane == 0) {
     sel_n[q] = count;
     if (count < 0) fb_list[atomicAdd(fb_count, 1)] = q;
@@ -286,9 +290,9 @@ constexpr int kFinishMaxStagedEntries = 6144;   // lists*8 entries staged in sha
 // exhaustive scan through fb2_list.
 struct CollectStage {
   const uint16_t* q_packed;   // [t, d] bf16 packed queries of this call
-  uint16_t* qc_packed;        // [rows_c, d] compact copy (NULL: stage disabled)
-  float* c_cut;               // [rows_c]
-  int* c_cnt;                 // [rows_c]
+  uint16_t* qc_packed;        // [items * rows_c, d] compact copy, rows_c slots per item (NULL: stage disabled)
+  float* c_cut;               // [items * rows_c]
+  int* c_cnt;                 // [items * rows_c]
   int rows_c;
 };
 
@@ -428,7 +432,7 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
       const float sk = sk_key == 0u ? -INFINITY : key_score(sk_key);
       const float t2 = t2k == 0u ? -INFINITY : key_score(t2k);
       const float le = __uint_as_float(le_bits);
-      const float eps = (le + qe + le * qe + kAccumSlack) * 1.00001f;
+      const float eps = (le + qe + le * qe + accum_slack(d / 16)) * 1.00001f;
       const float cut = sk - 2.0f * eps - 1e-7f;
       const bool fb = lib_bad != 0u || !(qn > 0.f) || !isfinite(qn) || !(sk > -INFINITY) || !(cut > t2);
       s_cut = cut;
@@ -471,11 +475,12 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
       // the cut.  One thread copies the 1.5 KB: anything heavier between here and the bare `return`
       // below (a block-wide copy behind a barrier was tried) costs the COMMON path 40% - measured.
       if (cs.qc_packed != nullptr && slot < cs.rows_c) {
+        const size_t cslot = static_cast<size_t>(item) * cs.rows_c + slot;          // the item's own block of slots
         const uint4* src = reinterpret_cast<const uint4*>(cs.q_packed + static_cast<size_t>(q) * d);
-        uint4* dst = reinterpret_cast<uint4*>(cs.qc_packed + static_cast<size_t>(slot) * d);
+        uint4* dst = reinterpret_cast<uint4*>(cs.qc_packed + cslot * d);
         for (int j = 0; j < d / 8; ++j) dst[j] = src[j];
-        cs.c_cut[slot] = s_ccut;
-        cs.c_cnt[slot] = 0;
+        cs.c_cut[cslot] = s_ccut;
+        cs.c_cnt[cslot] = 0;
       }
     }
   }
@@ -527,13 +532,132 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
 #endif
 }
 
-// One CTA per fallback slot: exact rescoring of the collected candidates, top-k, gather.
+// Refinement prologue of the collect pass (libraries packed with their second bf16 plane), one CTA per uncertified
+// query that got a slot.  finish_kernel left the query's first-pass cut S_k - 2 eps1 (eps1 ~ 4e-3: on a clustered
+// library thousands of frames sit above it).  Here the R best SCREENED entries of the query are rescored exactly;
+// the k-th best of those exact scores, L, is a lower bound of the exact k-th best similarity over the whole library
+// (k distinct frames reach it).  The refined tensor-core pass computes s2 = hi.hi + hi.lo + lo.hi with
+// |s2 - exact| <= eps2 (~4e-5), so every frame of the exact top-k has s2 >= L - eps2: that is the cut the collecting
+// epilogue applies - a band of eps2 around the true k-th score instead of 2 eps1 below the screened one.
+// Also moves the query's second plane into the compact matrix.
+constexpr int kPrepThreads = 256;
+constexpr int kPrepR = 64;                 // screened entries rescored for the bound (<= 2x with ties)
+__global__ void __launch_bounds__(kPrepThreads)
+refine_prep_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int lists, int k,
+                   const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
+                   const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
+                   const float* __restrict__ q_err2, const uint16_t* __restrict__ q_lo, uint16_t* __restrict__ qc_lo,
+                   const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
+                   const unsigned int* __restrict__ lib_stats, int d, float* __restrict__ c_cut) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qh = reinterpret_cast<float*>(smem_raw);            // [d] normalised query
+  int* sel = reinterpret_cast<int*>(qh + d);                 // [2 * kPrepR] frame indices
+  float* csc = reinterpret_cast<float*>(sel + 2 * kPrepR);   // [2 * kPrepR] exact scores
+  __shared__ int s_cnt[kPrepThreads / 32];
+  __shared__ int s_total;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int item = blockIdx.y, slot = blockIdx.x;
+  const int n_fb = min(fb_count[item], rows_c);
+  if (slot >= n_fb) return;
+  const int q = fb_list[static_cast<size_t>(item) * t_item + slot];
+  const size_t cslot = static_cast<size_t>(item) * rows_c + slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {  // the second plane of the query moves next to the first one (finish_kernel parked that)
+    const uint4* src = reinterpret_cast<const uint4*>(q_lo + static_cast<size_t>(q) * d);
+    uint4* dst = reinterpret_cast<uint4*>(qc_lo + cslot * d);
+    for (int j = threadIdx.x; j < d / 8; j += kPrepThreads) dst[j] = src[j];
+  }
+  if (!(c_cut[cslot] < INFINITY)) return;      // no usable screen (non-finite norms / rows): the exhaustive scan takes it
+  const float qn = q_norm[q];
+  for (int j = threadIdx.x; j < d; j += kPrepThreads) qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
+  if (threadIdx.x == 0) s_total = 0;
+  const int n_entries = lists * kListLen;
+  const float* sc = cand_score + static_cast<size_t>(q) * n_entries;
+  const int* ix = cand_idx + static_cast<size_t>(q) * n_entries;
+  // largest key threshold that still leaves >= R entries: bisection on the monotone uint32 key of the score
+  unsigned lo_key = 1u, hi_key = 0xFFFFFFFEu;                // (0 = padding / -inf lists never reach the count)
+  const int want = min(kPrepR, n_entries);
+  while (lo_key < hi_key) {
+    const unsigned mid = lo_key + ((hi_key - lo_key + 1u) >> 1);
+    int c = 0;
+    for (int e = threadIdx.x; e < n_entries; e += kPrepThreads) c += (ix[e] >= 0 && score_key(sc[e]) >= mid) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __syncthreads();
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) tot += s_cnt[w];
+    if (tot >= want) lo_key = mid;
+    else hi_key = mid - 1u;
+  }
+  __syncthreads();
+  for (int e0 = 0; e0 < n_entries; e0 += kPrepThreads) {
+    const int e = e0 + threadIdx.x;
+    const bool keep = e < n_entries && ix[e] >= 0 && score_key(sc[e]) >= lo_key;
+    if (keep) {
+      const int pos = atomicAdd(&s_total, 1);
+      if (pos < 2 * kPrepR) sel[pos] = ix[e];
+    }
+  }
+  __syncthreads();
+  const int n_sel = min(s_total, 2 * kPrepR);
+  for (int c = warp; c < n_sel; c += kPrepThreads / 32) {
+    const int idx = sel[c];
+    const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
+    if (lane == 0) csc[c] = static_cast<float>(acc);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // k-th largest exact score among the rescored entries (distinct frames; NaN cannot occur: the library is finite)
+    unsigned taken_lo = 0u, taken_hi = 0u, taken_2 = 0u, taken_3 = 0u;      // bit i: entry lane + 32*i used (n_sel <= 128)
+    float kth = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      float best = -INFINITY;
+      int bslot = -1;
+      for (int i = 0, c = lane; c < n_sel; ++i, c += 32) {
+        const unsigned used = i == 0 ? taken_lo : i == 1 ? taken_hi : i == 2 ? taken_2 : taken_3;
+        if (used & 1u) continue;
+        if (bslot < 0 || csc[c] > best) {
+          best = csc[c];
+          bslot = i;
+        }
+      }
+      const unsigned key = bslot >= 0 ? score_key(best) : 0u;
+      const unsigned m = __reduce_max_sync(0xffffffffu, key);
+      const unsigned has = __ballot_sync(0xffffffffu, bslot >= 0 && key == m);
+      if (m == 0u) {
+        kth = -INFINITY;                    // fewer than k rescored entries: no bound
+        break;
+      }
+      kth = key_score(m);
+      if (lane == __ffs(static_cast<int>(has)) - 1) {                          // exactly one lane retires its entry
+        if (bslot == 0) taken_lo = 1u;
+        else if (bslot == 1) taken_hi = 1u;
+        else if (bslot == 2) taken_2 = 1u;
+        else taken_3 = 1u;
+      }
+    }
+    if (lane == 0 && n_sel >= k && kth > -INFINITY) {
+      const float le = __uint_as_float(lib_stats[0]), le2 = __uint_as_float(lib_stats[2]);
+      const float qe = q_err[q], qe2 = q_err2[q];
+      // |refined - exact| <= |ql||rl| + |q2| |r^| + |qh + ql| |r2| + accumulation over 3 d/16 instructions (+ roundings)
+      const float eps2 = ((qe + qe2) * (le + le2) + qe2 * 1.001f + le2 * 1.003f + accum_slack(3 * (d / 16))) * 1.0001f + 2e-7f;
+      const float cut2 = kth - eps2;
+      // never looser than the first-pass cut (both are valid: a frame of the exact top-k clears each of them in ITS score)
+      c_cut[cslot] = cut2;
+    }
+  }
+}
+
+// One CTA per fallback slot: exact rescoring of the collected candidates, top-k, gather.  blockIdx.y = item.
 constexpr int kCollectThreads = 512;
 __global__ void __launch_bounds__(kCollectThreads, 2)
-collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, int rows_c,
+collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
                        const int* __restrict__ c_cnt, const int* __restrict__ c_idx, int c_cap, int k,
                        const float* __restrict__ q_raw, const float* __restrict__ q_norm,
-                       const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
+                       const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n_total, int d,
                        float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
                        long long* __restrict__ top_idx, long long idx_base, int* __restrict__ fb2_list,
                        int* __restrict__ fb2_count) {
@@ -544,23 +668,27 @@ collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ 
   constexpr int kWarps = kCollectThreads / 32;
   pdl_wait();
   pdl_launch_dependents();
-  const int n_fb = *fb_count;
+  const int item = blockIdx.y;
+  fb_list += static_cast<size_t>(item) * t_item;
+  fb2_list += static_cast<size_t>(item) * t_item;
+  const int n_fb = fb_count[item];
   const int slot = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // uncertified queries beyond the compact matrix go straight to the exhaustive scan
   if (threadIdx.x == 0)
-    for (int sl = rows_c + slot; sl < n_fb; sl += gridDim.x) fb2_list[atomicAdd(fb2_count, 1)] = fb_list[sl];
+    for (int sl = rows_c + slot; sl < n_fb; sl += gridDim.x) fb2_list[atomicAdd(&fb2_count[item], 1)] = fb_list[sl];
   if (slot >= n_fb || slot >= rows_c) return;
   const int q = fb_list[slot];
-  const int cnt = c_cnt[slot];
+  const size_t cslot = static_cast<size_t>(item) * rows_c + slot;
+  const int cnt = c_cnt[cslot];
   if (cnt > c_cap || cnt < k) {                             // overflow, or no usable cut: exhaustive scan
-    if (threadIdx.x == 0) fb2_list[atomicAdd(fb2_count, 1)] = q;
+    if (threadIdx.x == 0) fb2_list[atomicAdd(&fb2_count[item], 1)] = q;
     return;
   }
   const float qn = q_norm[q];
   for (int j = threadIdx.x; j < d; j += kCollectThreads) qh[j] = __fdiv_rn(q_raw[static_cast<size_t>(q) * d + j], qn);
   __syncthreads();
-  const int* cand = c_idx + static_cast<size_t>(slot) * c_cap;
+  const int* cand = c_idx + cslot * c_cap;
   for (int c = warp; c < cnt; c += kWarps) {
     const int idx = cand[c];
     const double acc = dot_norm_f64(qh, lib_raw + static_cast<size_t>(idx) * d, lib_norm[idx], d, lane);
@@ -598,7 +726,7 @@ collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ 
   }
   if (out == nullptr) return;
   __syncthreads();
-  gather_mean_row(lib_raw, n, d, s_top, 0, k, q_raw + static_cast<size_t>(q) * d, a0 != 0.f || !isfinite(qn), a1, a0,
+  gather_mean_row(lib_raw, n_total, d, s_top, 0, k, q_raw + static_cast<size_t>(q) * d, a0 != 0.f || !isfinite(qn), a1, a0,
                   out + static_cast<size_t>(q) * d, threadIdx.x, kCollectThreads);
 }
 
@@ -1057,19 +1185,19 @@ int exact_splits(int t, long long n, int k) {
 }  // namespace alive
 
 extern "C" int alive_knn_prune(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists,
-                               int32_t k, const float* q_err, const float* q_norm, const uint32_t* lib_stats,
+                               int32_t k, int32_t d, const float* q_err, const float* q_norm, const uint32_t* lib_stats,
                                int32_t r_max, int32_t* sel_idx, int32_t* sel_n, int32_t* fb_list,
                                int32_t* fb_count, alive_stream_t stream) {
   using namespace alive;
   ALIVE_REQUIRE(cand_score && cand_idx && q_err && q_norm && lib_stats && sel_idx && sel_n && fb_list && fb_count,
                 "alive_knn_prune: NULL argument");
-  ALIVE_REQUIRE(t >= 1 && lists >= 1, "alive_knn_prune: bad sizes");
+  ALIVE_REQUIRE(t >= 1 && lists >= 1 && d >= 16 && d <= 1536, "alive_knn_prune: bad sizes");
   ALIVE_REQUIRE(k >= 1 && k <= kListLen, "alive_knn_prune: k must be in [1,%d] for the screened path (got %d)", kListLen, k);
   ALIVE_REQUIRE(r_max >= k && r_max <= kMaxRMax, "alive_knn_prune: r_max must be in [k,%d]", kMaxRMax);
   ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), as_stream(stream)));
   const int wpb = 8;
   prune_kernel<<<(t + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(
-      cand_score, cand_idx, t, lists, k, q_err, q_norm, lib_stats, r_max, sel_idx, sel_n, fb_list, fb_count);
+      cand_score, cand_idx, t, lists, k, q_err, q_norm, lib_stats, r_max, sel_idx, sel_n, fb_list, fb_count, d);
   ALIVE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1223,7 +1351,7 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
   }
   ALIVE_REQUIRE(smem <= 100 * 1024, "alive_knn_finish: shared memory budget exceeded");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-  ALIVE_REQUIRE(qc_packed == nullptr || (items == 1 && q_packed && c_cut && c_cnt && rows_c >= 1 && d % 8 == 0),
+  ALIVE_REQUIRE(qc_packed == nullptr || (q_packed && c_cut && c_cnt && rows_c >= 1 && d % 8 == 0),
                 "alive_knn_finish: bad collect stage");
   CollectStage cs{q_packed, qc_packed, c_cut, c_cnt, rows_c};
 #define ALIVE_LAUNCH_FINISH(TH, B)                                                                                   \
@@ -1258,11 +1386,11 @@ extern "C" int alive_knn_finish(const float* cand_score, const int32_t* cand_idx
 }
 
 namespace alive {
-int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_t t, int32_t rows_c, const int32_t* c_cnt,
-                         const int32_t* c_idx, int32_t c_cap, int32_t k, const float* q_raw, const float* q_norm,
-                         const float* lib_raw, const float* lib_norm, int64_t n, int32_t d, float alpha, float* out,
-                         float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list, int32_t* fb2_count,
-                         alive_stream_t stream) {
+int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_t t_item, int32_t items, int32_t rows_c,
+                         const int32_t* c_cnt, const int32_t* c_idx, int32_t c_cap, int32_t k, const float* q_raw,
+                         const float* q_norm, const float* lib_raw, const float* lib_norm, int64_t n_total, int32_t d,
+                         float alpha, float* out, float* top_score, int64_t* top_idx, int64_t idx_base, int32_t* fb2_list,
+                         int32_t* fb2_count, alive_stream_t stream) {
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(c_cap) * 4;
   static PerDeviceOnce attr_once;
   {
@@ -1274,12 +1402,27 @@ int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_
   }
   ALIVE_REQUIRE(smem <= 64 * 1024, "collect pass: candidate buffer too large for shared memory");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-  (void)t;
-  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c), dim3(kCollectThreads), smem, as_stream(stream), fb_list,
-                                  fb_count, rows_c, c_cnt, c_idx, c_cap, k, q_raw, q_norm, lib_raw, lib_norm,
-                                  static_cast<long long>(n), d, a1, alpha, out, top_score,
+  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c, items), dim3(kCollectThreads), smem, as_stream(stream),
+                                  fb_list, fb_count, t_item, rows_c, c_cnt, c_idx, c_cap, k, q_raw, q_norm, lib_raw, lib_norm,
+                                  static_cast<long long>(n_total), d, a1, alpha, out, top_score,
                                   reinterpret_cast<long long*>(top_idx), static_cast<long long>(idx_base), fb2_list,
                                   fb2_count));
+  return 0;
+}
+
+int refine_prep_impl(const float* cand_score, const int32_t* cand_idx, int32_t lists, int32_t k, const int32_t* fb_list,
+                     const int32_t* fb_count, int32_t t_item, int32_t items, int32_t rows_c, const float* q_raw,
+                     const float* q_norm, const float* q_err, const float* q_err2, const uint16_t* q_lo, uint16_t* qc_lo,
+                     const float* lib_raw, const float* lib_norm, const uint32_t* lib_stats, int32_t d, float* c_cut,
+                     alive_stream_t stream) {
+  ALIVE_REQUIRE(cand_score && cand_idx && fb_list && fb_count && q_raw && q_norm && q_err && q_err2 && q_lo && qc_lo &&
+                    lib_raw && lib_norm && lib_stats && c_cut,
+                "collect pass (refine): NULL argument");
+  ALIVE_REQUIRE(d % 8 == 0 && k >= 1 && k <= kListLen, "collect pass (refine): bad sizes");
+  const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(2 * kPrepR) * 8;
+  ALIVE_CHECK_CUDA(launch_chained(refine_prep_kernel, dim3(rows_c, items), dim3(kPrepThreads), smem, as_stream(stream),
+                                  cand_score, cand_idx, lists, k, fb_list, fb_count, t_item, rows_c, q_raw, q_norm, q_err,
+                                  q_err2, q_lo, qc_lo, lib_raw, lib_norm, lib_stats, d, c_cut));
   return 0;
 }
 }  // namespace alive

@@ -70,9 +70,11 @@ class PackedFrames:
     norms: torch.Tensor      # [n]   float32
     packed: torch.Tensor     # [n,d] bfloat16, frames / norm
     err: torch.Tensor        # [n]   float32, ||bf16(x/|x|) - x/|x|||_2
-    stats: torch.Tensor      # [2]   int32 (uint32 bit patterns): max err, non-finite row count
+    stats: torch.Tensor      # [4]   int32 (uint32 bit patterns): max err, non-finite row count, max err2, reserved
     row_base: int = 0        # global index of frame 0 (sharded libraries)
     items: int = 1           # > 1: `items` independent libraries of n // items frames each, back to back
+    lo: Optional[torch.Tensor] = None     # [n,d] bfloat16 second plane bf16(x/|x| - packed): refined collect pass
+    err2: Optional[torch.Tensor] = None   # [n] float32 ||x/|x| - packed - lo||_2
     _handle: object = field(default=None, repr=False)
 
     @property
@@ -84,7 +86,8 @@ class PackedFrames:
         h = self._handle
         if h is None or h.row_base != self.row_base or h.items != self.items:
             h = _cabi.Library(self.packed.data_ptr(), self.raw.data_ptr(), self.norms.data_ptr(),
-                              self.stats.data_ptr(), self.n // self.items, self.d, self.row_base, self.items)
+                              self.stats.data_ptr(), self.n // self.items, self.d, self.row_base, self.items,
+                              self.lo.data_ptr() if self.lo is not None else None)
             self._handle = h
         return h
 
@@ -93,17 +96,51 @@ class PackedFrames:
         return self.raw.device
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.raw, self.norms, self.packed, self.err, self.stats))
+        return sum(t.numel() * t.element_size() for t in (self.raw, self.norms, self.packed, self.err, self.stats, self.lo,
+                                                          self.err2) if t is not None)
+
+    def rows(self, lo_row: int, hi_row: int) -> "PackedFrames":
+        """frames [lo_row, hi_row) as a row shard (views, global indices kept through row_base)"""
+        return PackedFrames(n=hi_row - lo_row, d=self.d, raw=self.raw[lo_row:hi_row], norms=self.norms[lo_row:hi_row],
+                            packed=self.packed[lo_row:hi_row], err=self.err[lo_row:hi_row], stats=self.stats,
+                            row_base=self.row_base + lo_row,
+                            lo=self.lo[lo_row:hi_row] if self.lo is not None else None,
+                            err2=self.err2[lo_row:hi_row] if self.err2 is not None else None)
 
 
-def alloc_packed(n: int, d: int, device) -> PackedFrames:
+# The second bf16 plane costs 2 B per element (+33 % of a packed library) and buys the refined collect pass: clustered
+# libraries (near-duplicate frames: silence, sustained vowels) stay off the exhaustive scan.  "auto": on for a single
+# library when the plane fits comfortably (at most a quarter of the free device memory), off for sets of per-speaker
+# libraries (pack_libraries: BASELINE cfg5 fills the GPU without it); True / False force it.
+REFINE_DEFAULT = "auto"
+
+
+def _want_refine(refine, n: int, d: int, device, items: int = 1) -> bool:
+    if refine is None:
+        refine = REFINE_DEFAULT
+    if refine == "auto":
+        if items > 1 or d % 64 != 0:
+            return False
+        try:
+            free, _ = torch.cuda.mem_get_info(device)
+        except Exception:
+            return True
+        return n * d * 2 <= free // 4
+    return bool(refine)
+
+
+def alloc_packed(n: int, d: int, device, refine=None, items: int = 1) -> PackedFrames:
+    want_lo = _want_refine(refine, n, d, device, items)
     return PackedFrames(
         n=n, d=d,
         raw=torch.empty((n, d), dtype=torch.float32, device=device),
         norms=torch.empty((n,), dtype=torch.float32, device=device),
         packed=torch.empty((n, d), dtype=torch.bfloat16, device=device),
         err=torch.empty((n,), dtype=torch.float32, device=device),
-        stats=torch.zeros((2,), dtype=torch.int32, device=device),
+        stats=torch.zeros((4,), dtype=torch.int32, device=device),
+        items=items,
+        lo=torch.empty((n, d), dtype=torch.bfloat16, device=device) if want_lo else None,
+        err2=torch.empty((n,), dtype=torch.float32, device=device) if want_lo else None,
     )
 
 
@@ -119,34 +156,37 @@ def pack_into(dst: PackedFrames, row0: int, frames_dn: torch.Tensor):
         rc = lib.alive_knn_pack(
             frames_dn.data_ptr(), n, d, frames_dn.stride(1), frames_dn.stride(0),
             dst.raw[row0:].data_ptr(), dst.norms[row0:].data_ptr(), dst.packed[row0:].data_ptr(),
-            dst.err[row0:].data_ptr(), dst.stats.data_ptr(), _stream_ptr(dst.device))
+            dst.err[row0:].data_ptr(), dst.stats.data_ptr(),
+            dst.lo[row0:].data_ptr() if dst.lo is not None else None,
+            dst.err2[row0:].data_ptr() if dst.err2 is not None else None, _stream_ptr(dst.device))
     _cabi.check(rc, "alive_knn_pack")
     _count(1)
 
 
-def pack_frames(frames_dn: torch.Tensor) -> PackedFrames:
+def pack_frames(frames_dn: torch.Tensor, refine=None) -> PackedFrames:
     """Normalise-and-pack a [D, N] float32 CUDA view (the reference's channel-major
     layout, any strides).  Done ONCE per library (generate_voice_library.py / load time)
-    instead of once per call as common.py:101-104 does."""
+    instead of once per call as common.py:101-104 does.  `refine`: also store the second bf16 plane
+    (True / False / None = REFINE_DEFAULT, see there)."""
     _require_cuda(frames_dn, "frames")
     if frames_dn.dtype != torch.float32:
         frames_dn = frames_dn.float()
     d, n = frames_dn.shape
-    out = alloc_packed(n, d, frames_dn.device)
+    out = alloc_packed(n, d, frames_dn.device, refine)
     pack_into(out, 0, frames_dn)
     return out
 
 
-def pack_library(reference: torch.Tensor) -> PackedFrames:
+def pack_library(reference: torch.Tensor, refine=None) -> PackedFrames:
     """[1, D, N] (or [D, N]) library tensor -> PackedFrames."""
     if reference.dim() == 3:
         if reference.shape[0] != 1:
             raise RuntimeError("pack_library expects a single library [1, D, N] (see pack_libraries)")
         reference = reference[0]
-    return pack_frames(reference)
+    return pack_frames(reference, refine)
 
 
-def pack_libraries(reference: torch.Tensor) -> PackedFrames:
+def pack_libraries(reference: torch.Tensor, refine=None) -> PackedFrames:
     """[B, D, N] -> ONE PackedFrames holding B independent libraries of N frames back to back
     (items = B): batch item b of a query tensor is matched against library b only, all of them in
     a single launch (BASELINE cfg5; train_decoder.py:134-135's per-utterance libraries)."""
@@ -156,8 +196,7 @@ def pack_libraries(reference: torch.Tensor) -> PackedFrames:
     if reference.dtype != torch.float32:
         reference = reference.float()
     B, D, N = reference.shape
-    out = alloc_packed(B * N, D, reference.device)
-    out.items = B
+    out = alloc_packed(B * N, D, reference.device, refine, items=B)
     for b in range(B):
         pack_into(out, b * N, reference[b])
     return out
@@ -196,6 +235,7 @@ def save_packed_library(lib: PackedFrames, path: str, include_legacy_tokens: boo
         "alive_knn_packed_version": PACKED_FORMAT_VERSION,
         "n": lib.n, "d": lib.d, "row_base": lib.row_base, "items": lib.items,
         "norms": lib.norms.cpu(), "packed": lib.packed.cpu(), "err": lib.err.cpu(), "stats": lib.stats.cpu(),
+        "lo": lib.lo.cpu() if lib.lo is not None else None, "err2": lib.err2.cpu() if lib.err2 is not None else None,
         "fingerprint": _fingerprint(lib.raw),
     }, path + SIDECAR_SUFFIX)
 
@@ -213,8 +253,10 @@ def load_packed_library(path: str, device="cuda") -> PackedFrames:
     if "alive_knn_packed_version" in blob:        # round-1 single-file format (packed arrays next to `tokens`)
         if blob["alive_knn_packed_version"] != 1:
             raise RuntimeError(f"{path}: unsupported packed format version {blob['alive_knn_packed_version']}")
+        stats = torch.zeros((4,), dtype=torch.int32)
+        stats[:2] = blob["stats"][:2]
         return PackedFrames(n=int(blob["n"]), d=int(blob["d"]), raw=blob["raw"].to(dev), norms=blob["norms"].to(dev),
-                            packed=blob["packed"].to(dev), err=blob["err"].to(dev), stats=blob["stats"].to(dev),
+                            packed=blob["packed"].to(dev), err=blob["err"].to(dev), stats=stats.to(dev),
                             row_base=int(blob["row_base"]))
     if "tokens" not in blob:
         raise RuntimeError(f"{path}: not a voice-library checkpoint (no `tokens` key)")
@@ -231,7 +273,8 @@ def load_packed_library(path: str, device="cuda") -> PackedFrames:
         if ok:
             return PackedFrames(n=items * n_item, d=d, raw=raw, norms=sc["norms"].to(dev), packed=sc["packed"].to(dev),
                                 err=sc["err"].to(dev), stats=sc["stats"].to(dev), row_base=int(sc["row_base"]),
-                                items=items)
+                                items=items, lo=sc["lo"].to(dev) if sc.get("lo") is not None else None,
+                                err2=sc["err2"].to(dev) if sc.get("err2") is not None else None)
         del raw      # stale sidecar (the tokens were edited since): pack again
     tok = tokens.to(dev)
     return pack_library(tok) if items == 1 else pack_libraries(tok)
@@ -441,7 +484,7 @@ def _search_topk_screen(c, q, lib, k, r_max, plan, dev):
     sel_n = torch.empty((t,), dtype=torch.int32, device=dev)
     fb_list = torch.empty((t,), dtype=torch.int32, device=dev)
     fb_count = torch.empty((1,), dtype=torch.int32, device=dev)
-    rc = c.alive_knn_prune(cand_score.data_ptr(), cand_idx.data_ptr(), t, plan.lists, k, q.err.data_ptr(),
+    rc = c.alive_knn_prune(cand_score.data_ptr(), cand_idx.data_ptr(), t, plan.lists, k, d, q.err.data_ptr(),
                            q.norms.data_ptr(), lib.stats.data_ptr(), r_max, sel_idx.data_ptr(), sel_n.data_ptr(),
                            fb_list.data_ptr(), fb_count.data_ptr(), stream)
     _cabi.check(rc, "alive_knn_prune")
@@ -483,6 +526,12 @@ def pack_queries(source: torch.Tensor) -> PackedFrames:
 _MODES = {"auto": 0, "screen": 1, "exact": 2}
 
 
+def _collect_launches(refined: bool) -> int:
+    """kernels of a screened call with the collect pass behind it (the query pack not counted): search, finish,
+    [refine_prep], collect search, collect_rescore, exact_partial / _rows / _final"""
+    return 7 if refined else 6
+
+
 _layout_cache: dict = {}
 
 
@@ -493,7 +542,7 @@ def _layout(rows: int, lib: PackedFrames, k: int, r_max: int, mode: int, variant
     hit = _layout_cache.get(key)
     if hit is not None:
         return hit
-    off = (ctypes.c_int64 * 12)()
+    off = (ctypes.c_int64 * 14)()
     rc = _cabi.load().alive_knn_match_layout(*key[:8], lib.items, off)
     _cabi.check(rc, "alive_knn_match_layout")
     if len(_layout_cache) > 256:
@@ -562,13 +611,14 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
                                ev0.cuda_event if ev0 is not None else None,
                                ev1.cuda_event if ev1 is not None else None, _stream_ptr(dev))
     _cabi.check(rc, "alive_knn_match")
-    _count(1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
+    n_launch = 1 + ((_collect_launches(lib.lo is not None) if off[7] > off[6] else 4) if m == 1 else 2)
+    _count(n_launch)
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
                            fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
-                           exact_count=workspace[off[9] + 4 * lib.items:off[9] + 4 * lib.items + 4].view(torch.int32),
+                           exact_count=workspace[off[9] + 4 * lib.items:off[9] + 8 * lib.items].view(torch.int32),
                            collect=m == 1 and off[7] > off[6],
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
-                           launches=1 + ((6 if off[7] > off[6] else 4) if m == 1 else 2))
+                           launches=n_launch)
     last_info._workspace = workspace
     last_info._offsets = off
     if info_sink is not None:          # callers on several threads cannot rely on the module-level last_info
@@ -624,16 +674,18 @@ def match_packed_queries(q: PackedFrames, lib: PackedFrames, k: int = 4, alpha: 
         top_idx = torch.empty((batch, T, k), dtype=torch.int64, device=dev)
         top_score = torch.empty((batch, T, k), dtype=torch.float32, device=dev)
     with _on(dev):
-        rc = c.alive_knn_match_packed(q.raw.data_ptr(), q.norms.data_ptr(), q.packed.data_ptr(), q.err.data_ptr(), batch, T,
+        q_lo = q.lo.data_ptr() if (q.lo is not None and q.err2 is not None) else None
+        rc = c.alive_knn_match_packed(q.raw.data_ptr(), q.norms.data_ptr(), q.packed.data_ptr(), q.err.data_ptr(),
+                                      q_lo, q.err2.data_ptr() if q_lo is not None else None, batch, T,
                                       ctypes.byref(lib.handle()), k, float(alpha), r_max, m, _num_sms(dev), variant,
                                       workspace.data_ptr(), workspace.numel(), out.data_ptr() if want_out else None,
                                       top_idx.data_ptr(), top_score.data_ptr(), _stream_ptr(dev))
     _cabi.check(rc, "alive_knn_match_packed")
-    launches = (6 if off[7] > off[6] else 4) if m == 1 else 2
+    launches = (_collect_launches(lib.lo is not None and q_lo is not None) if off[7] > off[6] else 4) if m == 1 else 2
     _count(launches)
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
                            fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
-                           exact_count=workspace[off[9] + 4 * lib.items:off[9] + 4 * lib.items + 4].view(torch.int32),
+                           exact_count=workspace[off[9] + 4 * lib.items:off[9] + 8 * lib.items].view(torch.int32),
                            collect=m == 1 and off[7] > off[6],
                            sel_n=workspace[off[7]:off[7] + 4 * rows].view(torch.int32) if m == 1 else None,
                            launches=launches)

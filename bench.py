@@ -385,8 +385,7 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         else:
             my_items = list(range(B))
         # all of this rank's per-speaker libraries packed back to back: ONE pipeline launch per step
-        lib = M.alloc_packed(len(my_items) * N, D, dev)
-        lib.items = len(my_items)
+        lib = M.alloc_packed(len(my_items) * N, D, dev, items=len(my_items))     # (no second plane: 147 GB fill the GPU)
         for i, b in enumerate(my_items):
             for c0 in range(0, N, 250_000):
                 c1 = min(N, c0 + 250_000)

@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* alive_stream_t; /* cudaStream_t */
 
-#define ALIVE_KNN_ABI_VERSION 4
+#define ALIVE_KNN_ABI_VERSION 5
 #define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
 #define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
 #define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
@@ -60,10 +60,12 @@ typedef struct alive_knn_plan {
                               *    lists = grid */
 } alive_knn_plan_t;
 
-/* Library statistics produced by alive_knn_pack (2 x uint32 on the device):
+/* Library statistics produced by alive_knn_pack (4 x uint32 on the device, zeroed by the caller):
  *   [0] bit pattern of max over rows of || bf16(x/|x|) - x/|x| ||_2   (float >= 0)
- *   [1] number of rows whose normalised form is not finite (zero or inf/nan rows) */
-#define ALIVE_KNN_STATS_WORDS 2
+ *   [1] number of rows whose normalised form is not finite (zero or inf/nan rows)
+ *   [2] bit pattern of max over rows of || x/|x| - hi - lo ||_2, the residual of the TWO-plane split
+ *       (hi = bf16(x/|x|), lo = bf16(x/|x| - hi)); [3] reserved */
+#define ALIVE_KNN_STATS_WORDS 4
 
 const char* alive_knn_last_error(void);
 int alive_knn_abi_version(void);
@@ -77,15 +79,19 @@ int alive_knn_abi_version(void);
  *   norms  [n]   float32 L2 norms (fp64 accumulation, rounded once)
  *   packed [n,d] bf16 row-major, frames divided by their norm (tensor-core operand, TMA friendly)
  *   err    [n]   float32 || bf16(x/|x|) - x/|x| ||_2 per row (may be NULL)
- *   stats  [2]   see above; must be zeroed by the caller before the FIRST pack
+ *   stats  [4]   see above; must be zeroed by the caller before the FIRST pack
  *                of a library (several packs may accumulate into one stats).
+ *   lo     [n,d] bf16 row-major, the SECOND plane bf16(x/|x| - packed) (may be NULL: 2 B per element that buy
+ *                the refined collect pass - hi.hi + hi.lo + lo.hi on the tensor cores, error ~4e-5 instead of
+ *                ~4e-3 - which keeps clustered libraries, e.g. thousands of near-identical silence frames, off the
+ *                exhaustive scan);  err2 [n] float32 || x/|x| - packed - lo ||_2 per row (may be NULL).
  * Also used per call for the query frames (common.py:100,102,104 lhs).
  * Any strides are accepted; the two layouts that matter have kernels of their own: the
  * reference's channel-major [D,N] (stride_n == 1) and a producer's row-major [N,D]
  * (stride_d == 1), both with 16-byte aligned rows.  Every variant writes the same bits. */
 int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
                    float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
-                   alive_stream_t stream);
+                   uint16_t* lo, float* err2, alive_stream_t stream);
 
 /* Fill `plan` for t queries against n library frames on a device with
  * `num_sms` SMs.  variant: 1 or 2 CTAs per unit, 3 = the skinny kernel (t <= 32, single item);
@@ -115,13 +121,14 @@ int alive_knn_search(const uint16_t* q_packed, const uint16_t* lib_packed,
 
 /* K2b - certificate + prune.  From the screened lists pick, per query, every
  * frame that can still belong to the exact top-k given the bf16 screening
- * error bound eps = lib_err + q_err[t] + lib_err*q_err[t] + slack; a query whose
+ * error bound eps = lib_err + q_err[t] + lib_err*q_err[t] + slack(d) (slack: the tensor core's
+ * float32 accumulation over d/16 instructions, select.cu accum_slack); a query whose
  * lists cannot prove completeness (or that needs more than r_max survivors,
  * or whose own norm is not finite, or when the library holds non-finite rows)
  * is appended to fb_list for the exact scan.
  *   sel_idx [t,r_max] int32, sel_n [t] int32, fb_list [t] int32, fb_count [1] int32 (zeroed here) */
 int alive_knn_prune(const float* cand_score, const int32_t* cand_idx, int32_t t, int32_t lists,
-                    int32_t k, const float* q_err, const float* q_norm, const uint32_t* lib_stats,
+                    int32_t k, int32_t d, const float* q_err, const float* q_norm, const uint32_t* lib_stats,
                     int32_t r_max, int32_t* sel_idx, int32_t* sel_n, int32_t* fb_list,
                     int32_t* fb_count, alive_stream_t stream);
 
@@ -238,11 +245,12 @@ typedef struct alive_knn_library {
   const uint16_t* packed;   /* [n,d] bf16 */
   const float* raw;         /* [n,d] f32  */
   const float* norms;       /* [n]   f32  */
-  const uint32_t* stats;    /* [2]   u32  */
+  const uint32_t* stats;    /* [4]   u32  */
   int64_t n;                /* frames per item */
   int32_t d;
   int64_t row_base;         /* global index of frame 0 (row-sharded libraries), else 0 */
   int32_t items;            /* >= 1: independent libraries of n frames each, stored back to back */
+  const uint16_t* lo;       /* [n,d] bf16 second plane (alive_knn_pack `lo`), or NULL */
 } alive_knn_library_t;
 
 /* One-call pipeline = module/common.py:96-109 for `batch` x `t` query frames against one
@@ -258,11 +266,15 @@ typedef struct alive_knn_library {
  *   ev_search_start/stop: optional cudaEvent_t recorded around the alive_knn_search launch
  *   (used by bench.py to time the dominant kernel inside the timed region), else NULL.
  * Everything is enqueued on `stream`; no host synchronisation (CUDA-graph capturable).
- * alive_knn_match_layout fills 12 byte offsets into the workspace:
- *   0 q_raw 1 q_norm 2 q_packed 3 q_err 4 cand_score 5 cand_idx 6 (unused) 7 sel_n
- *   8 fb_list 9 fb_count 10 exact scratch 11 TOTAL bytes. */
+ * Uncertified queries (device-side lists, no host sync): a second tensor-core pass collects every frame that
+ * reaches the query's cut - refined with the second bf16 planes when lib->lo is given - and rescores those
+ * exactly; what overflows goes to the exhaustive scan.  Works per item for batched libraries.
+ * alive_knn_match_layout fills 14 byte offsets into the workspace:
+ *   0 q_raw 1 q_norm 2 q_packed 3 q_err 4 cand_score 5 cand_idx 6 collect-pass area 7 sel_n
+ *   8 fb_list 9 fb_count (2*items words: uncertified after the screen | after the collect pass)
+ *   10 exact scratch 11 TOTAL bytes 12 q_lo 13 q_err2. */
 int alive_knn_match_layout(int32_t rows, int64_t n, int32_t d, int32_t k, int32_t r_max, int32_t mode,
-                           int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets12_host);
+                           int32_t num_sms, int32_t variant, int32_t items, int64_t* offsets14_host);
 int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
                     int64_t stride_d, const alive_knn_library_t* lib_host, int32_t k, float alpha,
                     int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
@@ -275,6 +287,7 @@ int alive_knn_match(const float* source, int32_t batch, int32_t t, int64_t strid
  * q_raw [batch*t, d] f32, q_norm [batch*t], q_packed [batch*t, d] bf16, q_err [batch*t] exactly as alive_knn_pack
  * wrote them.  No K1 launch; everything else (search, certificate, rescoring, fallbacks, gather) as alive_knn_match. */
 int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16_t* q_packed, const float* q_err,
+                           const uint16_t* q_lo, const float* q_err2,   /* second plane of the queries, or NULL / NULL */
                            int32_t batch, int32_t t, const alive_knn_library_t* lib_host, int32_t k, float alpha,
                            int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
                            size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,

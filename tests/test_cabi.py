@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     assert sorted(_cabi.EXPORTS) == declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in alive_knn.h but not exported"
-    assert lib.alive_knn_abi_version() == 4
+    assert lib.alive_knn_abi_version() == 5
 
 
 def test_sass_is_blackwell_native():
@@ -93,7 +93,7 @@ def test_plan_rejects_bad_arguments(lib):
 
 def test_argument_validation_without_gpu(lib):
     # NULL pointers are rejected before any CUDA call is made
-    assert lib.alive_knn_pack(None, 4, 768, 1, 4, None, None, None, None, None, None) != 0
+    assert lib.alive_knn_pack(None, 4, 768, 1, 4, None, None, None, None, None, None, None, None) != 0
     assert b"NULL" in lib.alive_knn_last_error()
     assert lib.alive_knn_exact_workspace_bytes(1000, 100000, 4, 1) > 0
 
@@ -101,13 +101,15 @@ def test_argument_validation_without_gpu(lib):
 @pytest.mark.parametrize("rows,n,k,mode", [(32, 200_000, 4, 1), (1000, 100_000, 4, 0), (10_000, 10_000_000, 4, 1),
                                            (24, 512, 4, 0), (7, 64, 16, 0), (450, 3512, 4, 2)])
 def test_match_workspace_layout_is_consistent(lib, rows, n, k, mode):
-    """alive_knn_match_layout is host-only: 12 ascending, 256-byte aligned offsets, large enough for
-    every buffer the pipeline carves out of the single workspace."""
-    off = (ctypes.c_int64 * 12)()
+    """alive_knn_match_layout is host-only: 14 256-byte aligned offsets (0..11 ascending, the second query plane
+    and its error norms - 12, 13 - sit between q_err and the candidate lists), large enough for every buffer the
+    pipeline carves out of the single workspace."""
+    off = (ctypes.c_int64 * 14)()
     assert lib.alive_knn_match_layout(rows, n, 768, k, 64, mode, 148, 0, 1, off) == 0
     o = list(off)
     assert o[0] == 0 and all(x % 256 == 0 for x in o)
     assert all(o[i] <= o[i + 1] for i in range(11))
+    assert o[3] < o[12] < o[13] < o[4] + 1 and o[13] - o[12] >= rows * 768 * 2 and o[4] - o[13] >= rows * 4
     assert o[1] - o[0] >= rows * 768 * 4          # q_raw
     assert o[2] - o[1] >= rows * 4                # q_norm
     assert o[3] - o[2] >= rows * 768 * 2          # q_packed
@@ -140,7 +142,7 @@ def test_batched_plan_and_layout(lib):
     units = 64 * p.m_units * p.segments
     waves = -(-units // 74)
     assert waves * p.tiles_per_segment * 74 <= 1.05 * 64 * p.m_units * p.n_tiles     # < 5 % idle tile slots
-    off = (ctypes.c_int64 * 12)()
+    off = (ctypes.c_int64 * 14)()
     assert lib.alive_knn_match_layout(64 * 1000, 500_000, 768, 4, 64, 1, 148, 0, 64, off) == 0
     o = list(off)
     assert o[10] - o[9] >= 64 * 4                          # one uncertified-query counter per item

@@ -228,10 +228,11 @@ def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
         "    for tag, v in (('cm', x), ('rm', x.t().contiguous().t())):\n"
         "        p = M.pack_frames(v)\n"
         "        h = hashlib.sha256()\n"
-        "        for f in ('raw', 'norms', 'packed'):\n"
+        "        for f in ('raw', 'norms', 'packed', 'lo'):\n"
         "            h.update(getattr(p, f).view(torch.uint8).cpu().numpy().tobytes())\n"
         "        res[f'{tag}{n}_hash'] = np.frombuffer(h.digest(), dtype=np.uint8)\n"
         "        res[f'{tag}{n}_err'] = p.err.cpu().numpy()\n"
+        "        res[f'{tag}{n}_err2_err'] = p.err2.cpu().numpy()\n"
         "        res[f'{tag}{n}_stats'] = p.stats.cpu().numpy()\n"
         "np.savez(sys.argv[1], **res)\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -148,6 +148,14 @@ def test_pack_kernel_layout_and_stats():
         st = p.stats.cpu().numpy().view(np.uint32)
         assert st[1] == 0
         assert abs(np.array([st[0]], np.uint32).view(np.float32)[0] - float(p.err.max())) < 1e-9
+        # the second plane: lo = bf16(x^ - hi), err2 = |x^ - hi - lo| (rounded up), stats[2] = its maximum
+        assert p.lo is not None and p.err2 is not None
+        r1 = xn - xn.bfloat16().float()
+        assert torch.equal(p.lo, r1.bfloat16())
+        err2 = (r1 - r1.bfloat16().float()).double().norm(dim=1).float()
+        assert torch.allclose(p.err2, err2, rtol=1e-3, atol=1e-11) and bool((p.err2 >= err2).all())
+        assert abs(np.array([st[2]], np.uint32).view(np.float32)[0] - float(p.err2.max())) < 1e-12
+        assert float(p.err2.max()) < 1.2e-5 and float(p.err.max()) < 3e-3
     x = torch.randn(500, 768, device="cuda", generator=g)      # already row-major frames
     assert torch.equal(M.pack_frames(x.t()).raw, x)
     x = torch.randn(768, 40, device="cuda", generator=g)
@@ -433,8 +441,7 @@ def test_planted_neighbours_at_large_n():
     half = N // 2
     tops = []
     for lo, hi in ((0, half), (half, N)):
-        shard = M.PackedFrames(n=hi - lo, d=D, raw=lib.raw[lo:hi], norms=lib.norms[lo:hi], packed=lib.packed[lo:hi],
-                               err=lib.err[lo:hi], stats=lib.stats, row_base=lo)
+        shard = lib.rows(lo, hi)
         _, i, s = M.run_match(src, shard, 4, 0.0, want_out=False)
         tops.append((s.view(T, 4), i.view(T, 4)))
     sc = torch.stack([t[0] for t in tops]).contiguous()
@@ -482,7 +489,9 @@ def test_batched_libraries_equal_per_item_matches():
             src[1, :, :10] = ref[1, :, 60:70]                      # ... queried exactly: exact ties
         s, r = _cuda(src), _cuda(ref)
         out, idx = A.match_features(s, r, k, alpha, return_indices=True, mode=mode)
-        assert M.last_info.launches == 1 + (4 if M.last_info.mode == "screen" else 2)      # one pipeline, one query pack
+        # one pipeline, one query pack (+ the two collect-pass launches once an item is large enough to have one)
+        assert M.last_info.launches == 1 + ((6 if M.last_info.collect else 4) if M.last_info.mode == "screen" else 2)
+        assert M.last_info.collect == (mode == "screen" and B * T * N >= 2 ** 24)
         for b in range(B):
             o1, i1 = A.match_features(s[b:b + 1], r[b:b + 1], k, alpha, return_indices=True, mode=mode)
             assert torch.equal(idx[b:b + 1], i1) and torch.equal(out[b:b + 1], o1)
@@ -526,35 +535,105 @@ def _clustered(T, N, nclus, noise, seed, dev="cuda"):
     return src, ref
 
 
+@pytest.mark.parametrize("refine", [True, False])
 @pytest.mark.parametrize("T,N,nclus,noise,expect", [
-    (300, 60_000, 60, 0.2, "collect"),        # ~1000 frames inside every query's band: collected and rescored
-    (300, 60_000, 12, 0.2, "overflow"),       # ~5000 per cluster: more than a candidate buffer holds -> exhaustive scan
-    (2500, 8_000, 8, 0.2, "no_slot"),         # more uncertified queries than slots; the rest skip the collect pass
+    (300, 60_000, 60, 0.2, "collect"),        # ~1000 frames inside every query's first-pass band
+    (300, 60_000, 12, 0.2, "overflow"),       # ~5000 per cluster: more than a candidate buffer holds WITHOUT refinement
+    (2500, 8_000, 8, 0.2, "many"),            # (nearly) every query of a large batch uncertified
     (400, 50_000, 50, 0.5, "mixed"),
     (32, 600_000, 600, 0.2, "collect"),       # a realtime chunk (skinny first screen) against a clustered library
+    (200, 100_000, 20, 0.05, "tight"),        # 5000 frames within ~3e-4 of each other per cluster
 ])
-def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect):
-    """Tight clusters defeat the bf16 certificate; the second (collecting) tensor-core pass must give
-    exactly what the exhaustive scan gives, whichever of its exits a query takes."""
+def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect, refine):
+    """Tight clusters defeat the bf16 certificate; the second (collecting) tensor-core pass must give exactly what the
+    exhaustive scan gives, whichever of its exits a query takes.  With the library's second bf16 plane (refine) the
+    pass runs hi.hi + hi.lo + lo.hi against a cut tightened by a few exact rescorings, and NOTHING is left for the
+    exhaustive scan on any of these libraries; without it the candidate buffers of the densest ones overflow."""
     src, ref = _clustered(T, N, nclus, noise, seed=T + N)
-    lib = A.pack_library(ref)
+    lib = A.pack_library(ref, refine=refine)
+    assert (lib.lo is not None) == refine
     out_s, idx_s, sc_s = M.run_match(src, lib, 4, 0.25, mode="screen")
     info = M.last_info
     fb, ex = info.fallback_queries(), info.exact_scan_queries()
-    assert info.collect
+    assert info.collect and info.launches == 1 + (7 if refine else 6)
     out_e, idx_e, sc_e = M.run_match(src, lib, 4, 0.25, mode="exact")
     assert torch.equal(idx_s, idx_e)
     assert torch.equal(out_s, out_e)
     assert torch.equal(sc_s, sc_e)
-    if expect == "collect":
-        assert fb > T // 2 and ex == 0
+    if expect in ("collect", "overflow", "many", "tight"):
+        assert fb > T // 2
+    if refine:
+        assert ex == 0, (fb, ex)
+    elif expect == "collect":
+        assert ex == 0
     elif expect == "overflow":
-        assert fb > T // 2 and ex > T // 2
-    elif expect == "no_slot":
-        assert fb > 2048 and ex >= fb - 2048
+        assert ex > T // 2
     # and against the oracle on a slice (the whole batch would take the CPU too long)
     sl = slice(0, 40)
     _assert_parity(out_s[:, sl].transpose(1, 2), idx_s[:, sl], src[:, :, sl].cpu().numpy(), ref.cpu().numpy(), 4, 0.25)
+
+
+def test_collect_pass_for_batched_libraries():
+    """per-speaker libraries (items > 1, BASELINE cfg5 / train_decoder.py:134-135) get the collect pass per item:
+    clustered items are resolved by it, clean items are untouched, everything equals the exhaustive scan"""
+    B, T, N = 3, 300, 30_000                       # B * T * N = 2.7e7 >= 2^24
+    srcs, refs = [], []
+    for b in range(B):
+        s, r = _clustered(T, N, 30, 0.2, seed=100 + b) if b != 1 else \
+            (torch.randn(1, 768, T, device="cuda"), torch.randn(1, 768, N, device="cuda"))
+        srcs.append(s)
+        refs.append(r)
+    src, ref = torch.cat(srcs), torch.cat(refs)
+    for refine in (False, True):
+        lib = A.pack_libraries(ref, refine=refine)
+        assert lib.items == B and (lib.lo is not None) == refine
+        out_s, idx_s, sc_s = M.run_match(src, lib, 4, 0.0, mode="screen")
+        info = M.last_info
+        assert info.collect
+        fbs = info.fb_count.cpu().tolist()
+        assert fbs[0] > T // 2 and fbs[1] == 0 and fbs[2] > T // 2
+        assert info.exact_scan_queries() == 0
+        out_e, idx_e, sc_e = M.run_match(src, lib, 4, 0.0, mode="exact")
+        assert torch.equal(idx_s, idx_e) and torch.equal(out_s, out_e) and torch.equal(sc_s, sc_e)
+    for b in (0, 2):
+        sl = slice(0, 16)
+        rel = idx_s[b:b + 1, sl] - b * N
+        _assert_parity(out_s[b:b + 1, sl].transpose(1, 2), rel, src[b:b + 1, :, sl].cpu().numpy(), ref[b:b + 1].cpu().numpy(), 4, 0.0)
+
+
+def test_tensor_core_accumulation_error_model():
+    """The certificate's accumulation slack (select.cu accum_slack: TWICE one float32 ulp of the accumulator per
+    tcgen05.mma) against the hardware: |screened score - float64 dot of the same bf16 operands| over every pair the
+    fused kernel kept, on i.i.d. frames and on near-duplicates (scores up to 1: the worst case for a truncating
+    accumulator).  The observed maximum must stay below HALF the slack, and the error must be one-sided (truncation)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for D in (768, 1536):
+        slack = (D // 16) * 2.0 ** -22 + 2e-7
+        T, N = 256, 40_000
+        cases = [(torch.randn(D, T, device="cuda", generator=g), torch.randn(D, N, device="cuda", generator=g))]
+        for noise in (0.2, 0.01):
+            cent = torch.randn(D, 20, device="cuda", generator=g)
+            cases.append((cent[:, torch.randint(0, 20, (T,), device="cuda", generator=g)] + noise * torch.randn(D, T, device="cuda", generator=g),
+                          cent[:, torch.randint(0, 20, (N,), device="cuda", generator=g)] + noise * torch.randn(D, N, device="cuda", generator=g)))
+        cases.append((torch.rand(D, T, device="cuda", generator=g) + 0.5, torch.rand(D, N, device="cuda", generator=g) + 0.5))
+        for src, ref in cases:
+            q, lib = M.pack_frames(src), M.pack_frames(ref)
+            for variant in (1, 2):
+                plan = M.make_plan(T, N, D, q.device, variant)
+                cs = torch.empty((T, plan.lists * 8), device="cuda")
+                ci = torch.empty((T, plan.lists * 8), dtype=torch.int32, device="cuda")
+                _cabi.check(_cabi.load().alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
+                                                          cs.data_ptr(), ci.data_ptr(), torch.cuda.current_stream().cuda_stream), "search")
+                ok = ci >= 0
+                worst, most_positive = 0.0, 0.0
+                for t0 in range(0, T, 64):
+                    rows = lib.packed[ci[t0:t0 + 64].clamp(min=0).long()].double()
+                    exact = (rows * q.packed[t0:t0 + 64].double()[:, None, :]).sum(dim=2)
+                    err = torch.where(ok[t0:t0 + 64], cs[t0:t0 + 64].double() - exact, torch.zeros_like(exact))
+                    worst = max(worst, float(err.abs().max()))
+                    most_positive = max(most_positive, float(err.max()))
+                assert worst <= 0.5 * slack, (D, variant, worst, slack)
+                assert most_positive <= 2.0 ** -23, (D, variant, most_positive)     # truncation: never above by more than a rounding
 
 
 def test_collect_pass_with_unusable_cut():
@@ -582,8 +661,8 @@ def test_collect_pass_on_a_row_shard():
     half = N // 2
     tops, uncertified = [], 0
     for lo, hi in ((0, half), (half, N)):
-        shard = M.PackedFrames(n=hi - lo, d=768, raw=lib.raw[lo:hi], norms=lib.norms[lo:hi], packed=lib.packed[lo:hi],
-                               err=lib.err[lo:hi], stats=lib.stats, row_base=lo)
+        shard = lib.rows(lo, hi)
+        assert shard.lo is not None
         _, i, s = M.run_match(src, shard, 4, 0.0, want_out=False)
         assert M.last_info.collect
         uncertified += M.last_info.fallback_queries()

@@ -162,8 +162,7 @@ def test_records_merge_and_fused_gather_entry_points():
     q = None
     for rnk in range(R):
         lo, hi = shard_bounds(N, R, rnk)
-        sh = M.PackedFrames(n=hi - lo, d=D, raw=full.raw[lo:hi], norms=full.norms[lo:hi], packed=full.packed[lo:hi],
-                            err=full.err[lo:hi], stats=full.stats, row_base=lo)
+        sh = full.rows(lo, hi)
         shards.append(sh)
         be = CudaShardBackend(sh)
         q = be.pack_queries(src)
