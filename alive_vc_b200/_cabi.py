@@ -29,6 +29,7 @@ EXPORTS = [
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
     "alive_knn_finish", "alive_knn_gather_mean_peers", "alive_knn_ipc_export", "alive_knn_ipc_open",
     "alive_knn_ipc_close", "alive_knn_merge_records", "alive_knn_merge_gather", "alive_knn_match_packed",
+    "alive_knn_graph_launch", "alive_knn_event_wait",
 ]
 
 
@@ -175,6 +176,10 @@ def _declare(lib):
     lib.alive_knn_ipc_close.argtypes = [_vp]
     lib.alive_knn_match_layout.restype = ctypes.c_int
     lib.alive_knn_match_layout.argtypes = [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64)]
+    lib.alive_knn_graph_launch.restype = ctypes.c_int
+    lib.alive_knn_graph_launch.argtypes = [_vp, _vp, _vp]
+    lib.alive_knn_event_wait.restype = ctypes.c_int
+    lib.alive_knn_event_wait.argtypes = [_vp]
     lib.alive_knn_match_packed.restype = ctypes.c_int
     lib.alive_knn_match_packed.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(Library), _i32, _f32,
                                            _i32, _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]

@@ -347,3 +347,31 @@ extern "C" int alive_knn_ipc_close(void* base) {
   if (base) ALIVE_CHECK_CUDA(cudaIpcCloseMemHandle(base));
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Chunk-loop runtime (realtime_inference.py:130-191): the per-chunk host work of a captured pipeline is one graph
+// launch and one wait.  Both as single C calls: the interpreter overhead of three framework calls per chunk is a
+// tenth of a 100 us chunk.
+// ---------------------------------------------------------------------------------------------
+extern "C" int alive_knn_graph_launch(void* graph_exec, alive_stream_t stream, void* event) {
+  using namespace alive;
+  ALIVE_REQUIRE(graph_exec != nullptr, "alive_knn_graph_launch: NULL graph");
+  ALIVE_CHECK_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+  if (event) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), as_stream(stream)));
+  return 0;
+}
+
+extern "C" int alive_knn_event_wait(void* event) {
+  using namespace alive;
+  ALIVE_REQUIRE(event != nullptr, "alive_knn_event_wait: NULL event");
+  // poll: the wake-up of a blocking wait costs more than the few microseconds this spins
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(static_cast<cudaEvent_t>(event));
+    if (e == cudaSuccess) return 0;
+    if (e != cudaErrorNotReady) {
+      set_error("cudaEventQuery failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+  }
+}
+

@@ -296,6 +296,12 @@ class HostStreamingMatcher:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=self.stream), torch.no_grad():
                 self._enqueue()
+            # per-chunk host work = two C calls (alive_knn_graph_launch: cudaGraphLaunch + cudaEventRecord;
+            # alive_knn_event_wait: poll) on raw handles
+            self.done.record(self.stream)
+            self._c = M._cabi.load()
+            self._exec = self.graph.raw_cuda_graph_exec()
+            self._stream_h, self._event_h, self._dev_index = self.stream.cuda_stream, self.done.cuda_event, dev.index
 
     def _device_step(self, out):
         """[pre ->] match [-> post]; `out`: where the match writes its [B, T, D] block (None = the device buffer).
@@ -323,10 +329,14 @@ class HostStreamingMatcher:
 
     def run(self):
         """Launch on the chunk already sitting in `self.src_host`; returns immediately (see `result`)."""
-        with torch.cuda.stream(self.stream):
-            self.graph.replay()
-            self.done.record(self.stream)
-        M._count(self.launches_per_call)
+        if self._dev_index is not None and torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self._dev_index):
+                rc = self._c.alive_knn_graph_launch(self._exec, self._stream_h, self._event_h)
+        else:
+            rc = self._c.alive_knn_graph_launch(self._exec, self._stream_h, self._event_h)
+        if rc:
+            M._cabi.check(rc, "alive_knn_graph_launch")
+        M.launch_count += self.launches_per_call
 
     def submit(self, chunk: torch.Tensor):
         """Stage `chunk` (CPU) and launch; returns immediately (see `result`)."""
@@ -334,7 +344,9 @@ class HostStreamingMatcher:
         self.run()
 
     def result(self) -> torch.Tensor:
-        self.done.synchronize()
+        rc = self._c.alive_knn_event_wait(self._event_h)
+        if rc:
+            M._cabi.check(rc, "alive_knn_event_wait")
         return self.out_host.transpose(1, 2) if self.post is None else self.out_host
 
     def __call__(self, chunk: torch.Tensor) -> torch.Tensor:

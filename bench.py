@@ -678,58 +678,68 @@ def gather_roofline(env, lib, src_dev, B, T):
 
 def pack_roofline(env):
     """K1 alone (once per library, generate_voice_library.py / load time): the pack kernel on a fresh
-    channel-major [D, n] chunk far larger than L2.  Algorithmic bytes per frame: D*(4 read + 4 raw
-    + 2 packed) + 8 (norm, err) = 7,688 B."""
+    channel-major [D, n] chunk far larger than L2.  Algorithmic bytes per frame: D*(4 read + 4 raw + 2 packed + 2 second
+    plane) + 12 (norm, err, err2) = 9,228 B with the second bf16 plane the product stores by default for a single
+    library (7,688 B without it, reported beside)."""
     import torch
     from alive_vc_b200 import matching as M
 
     dev, peaks = env.dev, env.peaks
     pn = 250_000
     px = torch.randn(D, pn, device=dev)
-    pdst = M.alloc_packed(pn, D, dev)
-    for _ in range(2):
-        M.pack_into(pdst, 0, px)
-    torch.cuda.synchronize()
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    pe0.record()
-    for _ in range(reps):
-        M.pack_into(pdst, 0, px)
-    pe1.record()
-    torch.cuda.synchronize()
-    p_ms = pe0.elapsed_time(pe1) / reps
-    p_bytes = pn * (D * 10 + 8)
-    # the same frames as a row-major producer would hand them over (pack_rows): pack_rm_kernel
     px_rows = px.t().contiguous()
-    for _ in range(2):
-        M.pack_into(pdst, 0, px_rows.t())
-    pe0.record()
-    for _ in range(reps):
-        M.pack_into(pdst, 0, px_rows.t())
-    pe1.record()
-    torch.cuda.synchronize()
-    p_ms_rows = pe0.elapsed_time(pe1) / reps
+    reps = 10
+
+    def timed(dst, view):
+        for _ in range(2):
+            M.pack_into(dst, 0, view)
+        torch.cuda.synchronize()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(reps):
+            M.pack_into(dst, 0, view)
+        pe1.record()
+        torch.cuda.synchronize()
+        return pe0.elapsed_time(pe1) / reps
+
+    out = {}
+    for refine in (True, False):
+        pdst = M.alloc_packed(pn, D, dev, refine=refine)
+        per_frame = D * (12 if refine else 10) + (12 if refine else 8)
+        ms_cm = timed(pdst, px)
+        ms_rm = timed(pdst, px_rows.t())       # the same frames as a row-major producer hands them over (pack_rows)
+        out[refine] = {"bytes_per_frame": per_frame,
+                       "channel_major": {"kernel": "pack_cm_kernel", "avg_kernel_ms": ms_cm,
+                                         "achieved": pn * per_frame / (ms_cm * 1e-3) / 1e9,
+                                         "frac": pn * per_frame / (ms_cm * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                       "row_major": {"kernel": "pack_rm_kernel", "avg_kernel_ms": ms_rm,
+                                     "achieved": pn * per_frame / (ms_rm * 1e-3) / 1e9,
+                                     "frac": pn * per_frame / (ms_rm * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+        del pdst
     # torch's own transposing copy of the same chunk ([768, n] -> [n, 768], read + write 4 B per element):
     # what a library kernel gets out of the channel-major access pattern
     t_out = torch.empty((pn, D), dtype=torch.float32, device=dev)
     for _ in range(2):
         t_out.copy_(px.t())
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
     for _ in range(reps):
         t_out.copy_(px.t())
     pe1.record()
     torch.cuda.synchronize()
     t_gbs = 2.0 * pn * D * 4 / (pe0.elapsed_time(pe1) / reps * 1e-3) / 1e9
-    del t_out, px, pdst, px_rows
+    del t_out, px, px_rows
     torch.cuda.empty_cache()
-    return {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": p_bytes / (p_ms * 1e-3) / 1e9,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": p_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-            "avg_kernel_ms": p_ms, "bytes_per_frame": D * 10 + 8, "frames": pn,
-            "row_major": {"kernel": "pack_rm_kernel", "achieved": p_bytes / (p_ms_rows * 1e-3) / 1e9,
-                          "frac": p_bytes / (p_ms_rows * 1e-3) / 1e9 / peaks["hbm_gbs"], "avg_kernel_ms": p_ms_rows},
+    main = out[True]
+    return {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": main["channel_major"]["achieved"],
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": main["channel_major"]["frac"],
+            "avg_kernel_ms": main["channel_major"]["avg_kernel_ms"], "bytes_per_frame": main["bytes_per_frame"], "frames": pn,
+            "row_major": main["row_major"],
+            "without_second_plane": {"bytes_per_frame": out[False]["bytes_per_frame"],
+                                     "channel_major": out[False]["channel_major"], "row_major": out[False]["row_major"]},
             "torch_transpose_copy_gbs": t_gbs,
-            "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB per launch, no L2 reuse); "
-                    "row_major = the same frames as [250k, 768] rows"}
+            "note": "standalone K1 on a channel-major [768, 250k] fp32 chunk (1.9 GB read per launch, no L2 reuse), writing raw "
+                    "fp32 rows + both bf16 planes + norms; row_major = the same frames as [250k, 768] rows"}
 
 
 def summary_of(res):

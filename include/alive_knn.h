@@ -293,6 +293,12 @@ int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16
                            size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
                            alive_stream_t stream);
 
+/* Chunk-loop runtime (realtime_inference.py:130-191; host-side, no kernels): launch an instantiated CUDA graph
+ * (cudaGraphExec_t) on `stream` and record `event` (cudaEvent_t, nullable) behind it - one call per chunk; wait for
+ * an event by polling (a blocking wait's wake-up costs more than a ~100 us chunk can spare). */
+int alive_knn_graph_launch(void* graph_exec, alive_stream_t stream, void* event);
+int alive_knn_event_wait(void* event);
+
 #ifdef __cplusplus
 }
 #endif
