@@ -22,6 +22,8 @@ NVCC_FLAGS = [
 ]
 
 # every symbol include/alive_knn.h declares
+FORMAT_BF16, FORMAT_FP16 = 0, 1      # ALIVE_KNN_FORMAT_*
+
 EXPORTS = [
     "alive_knn_last_error", "alive_knn_abi_version", "alive_knn_pack", "alive_knn_plan", "alive_knn_plan_batched",
     "alive_knn_search", "alive_knn_prune", "alive_knn_rescore", "alive_knn_exact_workspace_bytes",
@@ -39,7 +41,7 @@ class Plan(ctypes.Structure):
         ("t", ctypes.c_int32), ("n", ctypes.c_int64), ("d", ctypes.c_int32),
         ("ctas_per_unit", ctypes.c_int32), ("m_units", ctypes.c_int32), ("n_tiles", ctypes.c_int32),
         ("segments", ctypes.c_int32), ("tiles_per_segment", ctypes.c_int32), ("lists", ctypes.c_int32),
-        ("grid", ctypes.c_int32), ("items", ctypes.c_int32), ("kernel", ctypes.c_int32),
+        ("grid", ctypes.c_int32), ("items", ctypes.c_int32), ("format", ctypes.c_int32), ("kernel", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -51,7 +53,7 @@ class Library(ctypes.Structure):
     _fields_ = [
         ("packed", ctypes.c_void_p), ("raw", ctypes.c_void_p), ("norms", ctypes.c_void_p),
         ("stats", ctypes.c_void_p), ("n", ctypes.c_int64), ("d", ctypes.c_int32), ("row_base", ctypes.c_int64),
-        ("items", ctypes.c_int32), ("lo", ctypes.c_void_p),
+        ("items", ctypes.c_int32), ("lo", ctypes.c_void_p), ("format", ctypes.c_int32),
     ]
 
 
@@ -132,7 +134,7 @@ def _declare(lib):
     lib.alive_knn_abi_version.restype = ctypes.c_int
     lib.alive_knn_abi_version.argtypes = []
     lib.alive_knn_pack.restype = ctypes.c_int
-    lib.alive_knn_pack.argtypes = [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.alive_knn_pack.argtypes = [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]
     lib.alive_knn_plan.restype = ctypes.c_int
     lib.alive_knn_plan.argtypes = [_i32, _i64, _i32, _i32, _i32, ctypes.POINTER(Plan)]
     lib.alive_knn_plan_batched.restype = ctypes.c_int
@@ -202,7 +204,7 @@ def load():
             # ALIVE_KNN_LIB: an instrumented build of the same sources (tests/gpu_tools/finish_phases.py)
             lib = ctypes.CDLL(os.environ.get("ALIVE_KNN_LIB") or LIB_PATH)
             _declare(lib)
-            if lib.alive_knn_abi_version() != 5:
+            if lib.alive_knn_abi_version() != 6:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")
             _lib = lib
     return _lib

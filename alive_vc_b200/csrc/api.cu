@@ -215,6 +215,10 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
   CollectLayout cl;
   int rc = layout(rows, lib->n, d, k, r_max, num_sms, variant, mode, items, &plan, off, &cl);
   if (rc) return rc;
+  ALIVE_REQUIRE(lib->format == ALIVE_KNN_FORMAT_BF16 || lib->format == ALIVE_KNN_FORMAT_FP16, "alive_knn_match: unknown plane format %d",
+                lib->format);
+  plan.format = lib->format;
+  cl.plan.format = lib->format;
   ALIVE_REQUIRE(static_cast<size_t>(off[kOffTotal]) <= workspace_bytes,
                 "alive_knn_match: workspace too small (%zu < %lld)", workspace_bytes, static_cast<long long>(off[kOffTotal]));
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "alive_knn_match: workspace must be 256-byte aligned");
@@ -237,7 +241,7 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
     rc = pack_impl(source, rows, d, stride_t, stride_d, reinterpret_cast<float*>(ws + off[kOffQRaw]),
                    reinterpret_cast<float*>(ws + off[kOffQNorm]), reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]),
                    reinterpret_cast<float*>(ws + off[kOffQErr]), nullptr, fb_count, 2 * items, stream, t, stride_b,
-                   reinterpret_cast<uint16_t*>(ws + off[kOffQLo]), reinterpret_cast<float*>(ws + off[kOffQErr2]));
+                   reinterpret_cast<uint16_t*>(ws + off[kOffQLo]), reinterpret_cast<float*>(ws + off[kOffQErr2]), lib->format);
     if (rc) return rc;
   } else {
     // the producer packed the queries (K1 ran as ITS epilogue): only the fallback counters are left to reset

@@ -40,7 +40,7 @@ void set_error(const char* fmt, ...);
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
               alive_stream_t stream, int64_t item_frames = 0, int64_t stride_b = 0, uint16_t* lo = nullptr,
-              float* err2 = nullptr);
+              float* err2 = nullptr, int32_t format = ALIVE_KNN_FORMAT_BF16);
 // `after_query_pack`: the launch directly follows the query pack of the same call in `stream`; kernels
 // that can use it start early (programmatic dependent launch) and wait for the pack on the device
 int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const alive_knn_plan_t* plan, float* cand_score,

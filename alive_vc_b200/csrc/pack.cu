@@ -19,6 +19,7 @@
 //   pack_frame_kernel  <= 512 frames (a streaming chunk): one CTA per frame
 // All of them compute the same bits: fp64 norm, correctly rounded x/|x|, RN-even bf16.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -67,15 +68,42 @@ __device__ __forceinline__ void cta_stats_publish(const CtaStats* cs, unsigned i
 //   err2 [n]   f32  = || a - hi - lo ||_2 (rounded up); stats[2] = max of its bits over the finite rows
 // Both subtractions are exact in float32 (a value minus its own rounding).
 struct Refine {
-  __nv_bfloat16* lo;
+  uint16_t* lo;
   float* err2;
 };
-// lo bits of an element; fh = float(hi); *r2 = a - hi - lo
+
+// The 16-bit format of the two planes (alive_knn.h ALIVE_KNN_FORMAT_*): bf16 (what the north-star text names) or
+// IEEE fp16.  Normalised frames live in [-1, 1], so fp16's range is no constraint and its 11-bit significand rounds
+// 8x finer than bf16's 8 bits at the same tensor-core rate (kind::f16 takes either): the certificate's band shrinks
+// 8x.  Everything downstream is format-agnostic - the error norms are measured from the values actually stored.
+template <bool kHalf> struct Plane;
+template <> struct Plane<false> {
+  static __device__ __forceinline__ unsigned short one(float a) { return __bfloat16_as_ushort(__float2bfloat16_rn(a)); }
+  static __device__ __forceinline__ float val(unsigned short h) { return __uint_as_float(static_cast<unsigned>(h) << 16); }
+  static __device__ __forceinline__ unsigned pack2(float a, float b) {      // low half = a
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const unsigned*>(&p);
+  }
+  static __device__ __forceinline__ float lo_val(unsigned w) { return __uint_as_float(w << 16); }
+  static __device__ __forceinline__ float hi_val(unsigned w) { return __uint_as_float(w & 0xffff0000u); }
+};
+template <> struct Plane<true> {
+  static __device__ __forceinline__ unsigned short one(float a) { return __half_as_ushort(__float2half_rn(a)); }
+  static __device__ __forceinline__ float val(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+  static __device__ __forceinline__ unsigned pack2(float a, float b) {
+    const __half2 p = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const unsigned*>(&p);
+  }
+  static __device__ __forceinline__ float lo_val(unsigned w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+  static __device__ __forceinline__ float hi_val(unsigned w) { return __high2float(*reinterpret_cast<const __half2*>(&w)); }
+};
+// second-plane bits of an element; fh = float(hi); *r2 = a - hi - lo
+template <bool kHalf>
 __device__ __forceinline__ unsigned short split_lo(float a, float fh, float* r2) {
   const float r1 = a - fh;
-  const __nv_bfloat16 l = __float2bfloat16_rn(r1);
-  *r2 = r1 - __bfloat162float(l);
-  return __bfloat16_as_ushort(l);
+  const unsigned short l = Plane<kHalf>::one(r1);
+  *r2 = r1 - Plane<kHalf>::val(l);
+  return l;
 }
 __device__ __forceinline__ float round_up_norm2(float sumsq) { return sqrtf(sumsq) * 1.0001f + 1e-12f; }
 
@@ -93,10 +121,10 @@ __device__ __forceinline__ const float* frame_ptr(const float* __restrict__ x, c
 
 // kFrames = frames per CTA: 32 for libraries (128-byte coalesced reads of the channel-major
 // input), 8 for small query batches (more CTAs; 32-byte sectors are still fully used).
-template <int kFrames>
+template <int kFrames, bool kHalf>
 __global__ void __launch_bounds__(kPackThreads)
 pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, long long stride_d,
-            float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
+            float* __restrict__ raw, float* __restrict__ norms, uint16_t* __restrict__ packed,
             float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero,
             int async_stage, const Refine rf) {
   extern __shared__ float tile[];          // [d][kFrames + 1]
@@ -168,16 +196,14 @@ pack_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, 
     for (int j = 2 * lane; j < d; j += 64) {
       const float a = __fdiv_rn(tile[j * ld + f], nrm);
       const float b = __fdiv_rn(tile[(j + 1) * ld + f], nrm);
-      const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-      const float da = __bfloat162float(ha) - a, db = __bfloat162float(hb) - b;
+      const unsigned short ha = Plane<kHalf>::one(a), hb = Plane<kHalf>::one(b);
+      const float fa = Plane<kHalf>::val(ha), fb = Plane<kHalf>::val(hb);
+      const float da = fa - a, db = fb - b;
       e2 += static_cast<double>(da) * da + static_cast<double>(db) * db;
       finite = finite && isfinite(a) && isfinite(b);
-      __nv_bfloat162 h2;
-      h2.x = ha;
-      h2.y = hb;
-      *reinterpret_cast<__nv_bfloat162*>(packed + row * d + j) = h2;
+      *reinterpret_cast<unsigned*>(packed + row * d + j) = static_cast<unsigned>(ha) | (static_cast<unsigned>(hb) << 16);
       float ra, rb;
-      const unsigned la = split_lo(a, __bfloat162float(ha), &ra), lb = split_lo(b, __bfloat162float(hb), &rb);
+      const unsigned la = split_lo<kHalf>(a, fa, &ra), lb = split_lo<kHalf>(b, fb, &rb);
       e22 += static_cast<double>(ra) * ra + static_cast<double>(rb) * rb;
       if (rf.lo) *reinterpret_cast<unsigned*>(rf.lo + row * d + j) = la | (lb << 16);
     }
@@ -275,8 +301,9 @@ __device__ __forceinline__ void cm_stage(float* tile, const float* __restrict__ 
 }
 
 // warp w: frames 4w..4w+3 of the tile, lane: channels lane, lane+32, ...
+template <bool kHalf>
 __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int nf, int d, float* __restrict__ raw,
-                                           float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
+                                           float* __restrict__ norms, uint16_t* __restrict__ packed,
                                            float* __restrict__ err, const Refine& rf, CtaStats* cta_stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fw = 4 * warp;
@@ -360,13 +387,11 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
           else if (!(fabsf(a[c]) >= 0x1p-40f)) a[c] = __fdiv_rn(xs[c], nrm[c]);
         }
       }
-      // two F2FP.PACK_AB: (frame 0, frame 1) and (frame 2, frame 3) of MY channel, low half = first frame
-      const __nv_bfloat162 p01 = __floats2bfloat162_rn(a[0], a[1]);
-      const __nv_bfloat162 p23 = __floats2bfloat162_rn(a[2], a[3]);
-      const unsigned w01 = *reinterpret_cast<const unsigned*>(&p01), w23 = *reinterpret_cast<const unsigned*>(&p23);
-      // a - hi per frame (exact), negated: what the second plane has to carry
-      const float r0 = a[0] - __uint_as_float(w01 << 16), r1 = a[1] - __uint_as_float(w01 & 0xffff0000u);
-      const float r2 = a[2] - __uint_as_float(w23 << 16), r3 = a[3] - __uint_as_float(w23 & 0xffff0000u);
+      // two packing conversions: (frame 0, frame 1) and (frame 2, frame 3) of MY channel, low half = first frame
+      const unsigned w01 = Plane<kHalf>::pack2(a[0], a[1]), w23 = Plane<kHalf>::pack2(a[2], a[3]);
+      // a - hi per frame (exact): what the second plane has to carry
+      const float r0 = a[0] - Plane<kHalf>::lo_val(w01), r1 = a[1] - Plane<kHalf>::hi_val(w01);
+      const float r2 = a[2] - Plane<kHalf>::lo_val(w23), r3 = a[3] - Plane<kHalf>::hi_val(w23);
       if (live) {
         e2[0] = fmaf(r0, r0, e2[0]);
         e2[1] = fmaf(r1, r1, e2[1]);
@@ -381,12 +406,10 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
       if (okB && live) pkB[w] = __byte_perm(ev, od, 0x7632);                        // frame B
       {
         // second plane: lo = bf16_rn(a - hi), residual a - hi - lo feeds err2 (always) and the plane is stored on request
-        const __nv_bfloat162 q01 = __floats2bfloat162_rn(r0, r1);
-        const __nv_bfloat162 q23 = __floats2bfloat162_rn(r2, r3);
-        const unsigned l01 = *reinterpret_cast<const unsigned*>(&q01), l23 = *reinterpret_cast<const unsigned*>(&q23);
+        const unsigned l01 = Plane<kHalf>::pack2(r0, r1), l23 = Plane<kHalf>::pack2(r2, r3);
         if (live) {
-          const float s0 = r0 - __uint_as_float(l01 << 16), s1 = r1 - __uint_as_float(l01 & 0xffff0000u);
-          const float s2 = r2 - __uint_as_float(l23 << 16), s3 = r3 - __uint_as_float(l23 & 0xffff0000u);
+          const float s0 = r0 - Plane<kHalf>::lo_val(l01), s1 = r1 - Plane<kHalf>::hi_val(l01);
+          const float s2 = r2 - Plane<kHalf>::lo_val(l23), s3 = r3 - Plane<kHalf>::hi_val(l23);
           e22[0] = fmaf(s0, s0, e22[0]);
           e22[1] = fmaf(s1, s1, e22[1]);
           e22[2] = fmaf(s2, s2, e22[2]);
@@ -420,14 +443,15 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
           a = __fdiv_rn(xs[c], nrm[c]);
           finite[c] = finite[c] && isfinite(a);
         }
-        const __nv_bfloat16 hb = __float2bfloat16_rn(a);
-        const float da = __bfloat162float(hb) - a;
+        const unsigned short hb = Plane<kHalf>::one(a);
+        const float fh = Plane<kHalf>::val(hb);
+        const float da = fh - a;
         e2[c] = fmaf(da, da, e2[c]);
-        if (c < nv) pk16[(row0 + c) * d + j] = __bfloat16_as_ushort(hb);
+        if (c < nv) pk16[(row0 + c) * d + j] = hb;
         float r2nd;
-        const unsigned short lb = split_lo(a, __bfloat162float(hb), &r2nd);
+        const unsigned short lb = split_lo<kHalf>(a, fh, &r2nd);
         e22[c] = fmaf(r2nd, r2nd, e22[c]);
-        if (rf.lo && c < nv) reinterpret_cast<unsigned short*>(rf.lo)[(row0 + c) * d + j] = lb;
+        if (rf.lo && c < nv) rf.lo[(row0 + c) * d + j] = lb;
       }
     }
   }
@@ -443,10 +467,10 @@ __device__ __forceinline__ void cm_compute(const float* tile, long long f0, int 
   }
 }
 
-template <bool kDouble>
+template <bool kDouble, bool kHalf>
 __global__ void __launch_bounds__(kPackThreads)
 pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride_d, float* __restrict__ raw,
-               float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
+               float* __restrict__ norms, uint16_t* __restrict__ packed, float* __restrict__ err,
                unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
   extern __shared__ __align__(16) float tile[];   // [kDouble ? 2 : 1][d][36]
   __shared__ CtaStats cta_stats;
@@ -468,7 +492,7 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    cm_compute(cur, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, raw, norms, packed, err, rf, &cta_stats);
+    cm_compute<kHalf>(cur, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, raw, norms, packed, err, rf, &cta_stats);
     __syncthreads();                 // every warp is done with `cur` before it is refilled
     if (!kDouble && tn < n_tiles)
       cm_stage(tile, x, tn * 32, static_cast<int>(min(32ll, n - tn * 32)), d, stride_d);
@@ -479,9 +503,10 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
 // Row-major input (a producer's [n, D]: stride_d == 1, 16-byte aligned rows, d % 4 == 0): nothing to
 // transpose - one warp per frame, the 3 KB row lives in registers between the norm and the division.
 constexpr int kRmMaxV = 12;                         // float4 per lane: d <= 1536
+template <bool kHalf>
 __global__ void __launch_bounds__(kPackThreads)
 pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, float* __restrict__ raw,
-               float* __restrict__ norms, __nv_bfloat16* __restrict__ packed, float* __restrict__ err,
+               float* __restrict__ norms, uint16_t* __restrict__ packed, float* __restrict__ err,
                unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
   pdl_launch_dependents();
   if (blockIdx.x == 0)
@@ -535,12 +560,12 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
           a = __fdiv_rn(xs[c], nrm);
           finite = finite && isfinite(a);
         }
-        const __nv_bfloat16 h = __float2bfloat16_rn(a);
-        const float da = __bfloat162float(h) - a;
+        hb[c] = Plane<kHalf>::one(a);
+        const float fh = Plane<kHalf>::val(hb[c]);
+        const float da = fh - a;
         e2 = fmaf(da, da, e2);
-        hb[c] = __bfloat16_as_ushort(h);
         float r2nd;
-        lb[c] = split_lo(a, __bfloat162float(h), &r2nd);
+        lb[c] = split_lo<kHalf>(a, fh, &r2nd);
         e22 = fmaf(r2nd, r2nd, e22);
       }
       dst_pk[q] = make_uint2(static_cast<unsigned>(hb[0]) | (static_cast<unsigned>(hb[1]) << 16),
@@ -564,9 +589,10 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
 
 // Tiny batches (streaming chunks, T <= 512): one CTA per frame, three channels per thread, two
 // block reductions - one load round trip instead of a 768-row staging loop on a handful of CTAs.
+template <bool kHalf>
 __global__ void __launch_bounds__(kPackThreads)
 pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, long long stride_d,
-                  float* __restrict__ raw, float* __restrict__ norms, __nv_bfloat16* __restrict__ packed,
+                  float* __restrict__ raw, float* __restrict__ norms, uint16_t* __restrict__ packed,
                   float* __restrict__ err, unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero,
                   const Refine rf) {
   __shared__ double red[kPackThreads / 32];
@@ -603,15 +629,16 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMa
     const int j = threadIdx.x + i * kPackThreads;
     if (j < d) {
       const float a = __fdiv_rn(v[i], nrm);
-      const __nv_bfloat16 h = __float2bfloat16_rn(a);
-      const float da = __bfloat162float(h) - a;
+      const unsigned short h = Plane<kHalf>::one(a);
+      const float fh = Plane<kHalf>::val(h);
+      const float da = fh - a;
       e2 += static_cast<double>(da) * da;
       finite = finite && isfinite(a);
       packed[row * d + j] = h;
       float r2nd;
-      const unsigned short lb = split_lo(a, __bfloat162float(h), &r2nd);
+      const unsigned short lb = split_lo<kHalf>(a, fh, &r2nd);
       e22 += static_cast<double>(r2nd) * r2nd;
-      if (rf.lo) reinterpret_cast<unsigned short*>(rf.lo)[row * d + j] = lb;
+      if (rf.lo) rf.lo[row * d + j] = lb;
     }
   }
   e2 = warp_sum_f64(e2);
@@ -650,12 +677,75 @@ pack_frame_kernel(const float* __restrict__ x, long long n, int d, const FrameMa
 }  // namespace alive
 
 namespace alive {
+namespace {
+template <bool kHalf>
+int pack_dispatch(const float* x, int64_t n, int32_t d, const FrameMap& fm, bool uniform, int64_t stride_n, int64_t stride_d,
+                  int64_t stride_b, float* raw, float* norms, uint16_t* pk, float* err, uint32_t* stats, int32_t* zero_words,
+                  int32_t n_zero, const Refine& rf, cudaStream_t stream) {
+  static PerDeviceOnce attr_once;
+  {
+    const int rc_attr = attr_once.run([]() -> int {
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(pack_kernel<32, kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(pack_kernel<8, kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(pack_cm_kernel<false, kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(pack_cm_kernel<true, kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 768 * kCmLd * 4)));
+      return 0;
+    });
+    if (rc_attr) return rc_attr;
+  }
+  // ALIVE_KNN_PACK_ASYNC=0: register-staged loads (the first version; kept for A/B runs)
+  static const int async_stage = !(getenv("ALIVE_KNN_PACK_ASYNC") && atoi(getenv("ALIVE_KNN_PACK_ASYNC")) == 0);
+  // layout-specific kernels (ALIVE_KNN_PACK_FAST=0: the generic kernel everywhere, for A/B runs)
+  static const int fast = !(getenv("ALIVE_KNN_PACK_FAST") && atoi(getenv("ALIVE_KNN_PACK_FAST")) == 0);
+  const bool x16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const bool out16 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(pk) & 7) == 0;
+  if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && (uniform || stride_b % 4 == 0) && x16 && out16) {
+    pack_rm_kernel<kHalf><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, stream>>>(
+        x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
+  } else if (fast && uniform && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
+    const size_t smem = static_cast<size_t>(d) * kCmLd * sizeof(float);
+    const long long n_tiles = (n + 31) / 32;
+    // ALIVE_KNN_PACK_DOUBLE=1: the persistent double-buffered variant (an experiment that lost: with one
+    // 8-warp CTA per SM the finishing pass cannot hide its arithmetic latency - 55 % of the HBM peak
+    // against 73-77 % for two independent CTAs per SM)
+    static const int dbl = getenv("ALIVE_KNN_PACK_DOUBLE") && atoi(getenv("ALIVE_KNN_PACK_DOUBLE")) == 1;
+    int num_sms = 148;
+    if (dbl) {      // (per device: only the experiment needs it)
+      int dev = 0;
+      ALIVE_CHECK_CUDA(cudaGetDevice(&dev));
+      ALIVE_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (dbl && d <= 768 && n_tiles >= 4ll * num_sms) {
+      pack_cm_kernel<true, kHalf><<<static_cast<unsigned>(num_sms), kPackThreads, 2 * smem, stream>>>(
+          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
+    } else {
+      pack_cm_kernel<false, kHalf><<<static_cast<unsigned>(n_tiles), kPackThreads, smem, stream>>>(
+          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
+    }
+  } else if (n <= 512) {
+    pack_frame_kernel<kHalf><<<static_cast<unsigned>(n), kPackThreads, 0, stream>>>(x, n, d, fm, stride_d, raw, norms, pk, err,
+                                                                                   stats, zero_words, n_zero, rf);
+  } else if (n <= 8192) {
+    const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
+    pack_kernel<8, kHalf><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, stream>>>(
+        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage, rf);
+  } else {
+    const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
+    pack_kernel<32, kHalf><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, stream>>>(
+        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage, rf);
+  }
+  ALIVE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
 int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d, float* raw, float* norms,
               uint16_t* packed, float* err, uint32_t* stats, int32_t* zero_words, int32_t n_zero,
-              alive_stream_t stream, int64_t item_frames, int64_t stride_b, uint16_t* lo, float* err2) {
+              alive_stream_t stream, int64_t item_frames, int64_t stride_b, uint16_t* lo, float* err2, int32_t format) {
   ALIVE_REQUIRE(x && raw && norms && packed, "alive_knn_pack: NULL argument");
   ALIVE_REQUIRE(lo == nullptr || (reinterpret_cast<uintptr_t>(lo) & 7) == 0, "alive_knn_pack: lo must be 8-byte aligned");
-  const Refine rf{reinterpret_cast<__nv_bfloat16*>(lo), err2};
+  ALIVE_REQUIRE(format == ALIVE_KNN_FORMAT_BF16 || format == ALIVE_KNN_FORMAT_FP16, "alive_knn_pack: unknown plane format %d", format);
+  const Refine rf{lo, err2};
   if (item_frames <= 0 || item_frames >= n) {       // one item: the plain [n] frame sequence
     item_frames = n > 0 ? n : 1;
     stride_b = 0;
@@ -672,66 +762,17 @@ int pack_impl(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t st
     if (n_zero > 0) ALIVE_CHECK_CUDA(cudaMemsetAsync(zero_words, 0, sizeof(int32_t) * n_zero, as_stream(stream)));
     return 0;
   }
-  static PerDeviceOnce attr_once;
-  {
-    const int rc_attr = attr_once.run([]() -> int {
-      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 33 * 4));
-      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 9 * 4));
-      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4));
-      ALIVE_CHECK_CUDA(cudaFuncSetAttribute(pack_cm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 768 * kCmLd * 4));
-      return 0;
-    });
-    if (rc_attr) return rc_attr;
-  }
-  __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
-  // ALIVE_KNN_PACK_ASYNC=0: register-staged loads (the first version; kept for A/B runs)
-  static const int async_stage = !(getenv("ALIVE_KNN_PACK_ASYNC") && atoi(getenv("ALIVE_KNN_PACK_ASYNC")) == 0);
-  // layout-specific kernels (ALIVE_KNN_PACK_FAST=0: the generic kernel everywhere, for A/B runs)
-  static const int fast = !(getenv("ALIVE_KNN_PACK_FAST") && atoi(getenv("ALIVE_KNN_PACK_FAST")) == 0);
-  const bool x16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  const bool out16 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
-  if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && (uniform || stride_b % 4 == 0) && x16 && out16) {
-    pack_rm_kernel<<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, as_stream(stream)>>>(
-        x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
-  } else if (fast && uniform && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
-    const size_t smem = static_cast<size_t>(d) * kCmLd * sizeof(float);
-    const long long n_tiles = (n + 31) / 32;
-    // ALIVE_KNN_PACK_DOUBLE=1: the persistent double-buffered variant (an experiment that lost: with one
-    // 8-warp CTA per SM the finishing pass cannot hide its arithmetic latency - 55 % of the HBM peak
-    // against 73-77 % for two independent CTAs per SM)
-    static const int dbl = getenv("ALIVE_KNN_PACK_DOUBLE") && atoi(getenv("ALIVE_KNN_PACK_DOUBLE")) == 1;
-    int num_sms = 148;
-    if (dbl) {      // (per device: only the experiment needs it)
-      int dev = 0;
-      ALIVE_CHECK_CUDA(cudaGetDevice(&dev));
-      ALIVE_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (dbl && d <= 768 && n_tiles >= 4ll * num_sms) {
-      pack_cm_kernel<true><<<static_cast<unsigned>(num_sms), kPackThreads, 2 * smem, as_stream(stream)>>>(
-          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
-    } else {
-      pack_cm_kernel<false><<<static_cast<unsigned>(n_tiles), kPackThreads, smem, as_stream(stream)>>>(
-          x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
-    }
-  } else if (n <= 512) {
-    pack_frame_kernel<<<static_cast<unsigned>(n), kPackThreads, 0, as_stream(stream)>>>(x, n, d, fm, stride_d, raw,
-                                                                                       norms, pk, err, stats, zero_words, n_zero, rf);
-  } else if (n <= 8192) {
-    const size_t smem = static_cast<size_t>(d) * 9 * sizeof(float);
-    pack_kernel<8><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage, rf);
-  } else {
-    const size_t smem = static_cast<size_t>(d) * 33 * sizeof(float);
-    pack_kernel<32><<<static_cast<unsigned>((n + 31) / 32), kPackThreads, smem, as_stream(stream)>>>(
-        x, n, d, fm, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, async_stage, rf);
-  }
-  ALIVE_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  if (format == ALIVE_KNN_FORMAT_FP16)
+    return pack_dispatch<true>(x, n, d, fm, uniform, stride_n, stride_d, stride_b, raw, norms, packed, err, stats, zero_words,
+                               n_zero, rf, as_stream(stream));
+  return pack_dispatch<false>(x, n, d, fm, uniform, stride_n, stride_d, stride_b, raw, norms, packed, err, stats, zero_words,
+                              n_zero, rf, as_stream(stream));
 }
 }  // namespace alive
 
 extern "C" int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
                               float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
-                              uint16_t* lo, float* err2, alive_stream_t stream) {
-  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream, 0, 0, lo, err2);
+                              uint16_t* lo, float* err2, int32_t format, alive_stream_t stream) {
+  return alive::pack_impl(x, n, d, stride_n, stride_d, raw, norms, packed, err, stats, nullptr, 0, stream, 0, 0, lo, err2,
+                          format);
 }

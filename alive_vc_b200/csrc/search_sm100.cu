@@ -78,6 +78,7 @@ struct SearchParams {
   int lists;
   float* cand_score;
   int* cand_idx;
+  int half;            // operands are fp16 (else bf16)
   int debug;           // diagnostics only: 1 = epilogue skips the scan, 2 = also skips the TMEM loads
   unsigned long long hint_q;     // L2 eviction policy of the query-tile loads
   unsigned long long hint_lib;   // L2 eviction policy of the library-tile loads
@@ -224,10 +225,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major,
-// N>>3 at bit 17, M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// Instruction descriptor, kind::f16: D=f32 (bit 4), A and B formats at bits 7 and 10 (0 = fp16, 1 = bf16), both
+// K-major, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool half) {
+  return (1u << 4) | ((half ? 0u : 1u) << 7) | ((half ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 template <int kCtas>
@@ -478,7 +479,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ====================================== MMA issuer ======================================
     // leader CTA only; warp-uniform loop, one elected lane issues the tcgen05 instructions
     if (leader) {
-      constexpr uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN);
+      const uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN, p.half != 0);
       uint32_t it = 0, tile_count = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
         if (kCollect && (unit % units_per_item) % p.m_units >= m_active_of(unit / units_per_item)) continue;
@@ -655,7 +656,7 @@ constexpr uint32_t kSkinnyTbFloats = 32 * 33;                  // transpose buff
 constexpr uint32_t kSkinnySmemMax = 227 * 1024;
 
 struct SkinnyParams {
-  int t, n, k_blocks, n_tiles, stages, lists, contig;
+  int t, n, k_blocks, n_tiles, stages, lists, contig, half;
   float* cand_score;
   int* cand_idx;
 };
@@ -736,7 +737,7 @@ knn_search_skinny_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    constexpr uint32_t idesc = make_idesc(kBlockM, kSkinnyQ);
+    const uint32_t idesc = make_idesc(kBlockM, kSkinnyQ, p.half != 0);
     mbar_wait(bar_q, 0);
     tcgen05_fence_after();
     uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0;
@@ -949,6 +950,7 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   p.items = static_cast<int>(items);
   p.t = plan.t;
   p.n = static_cast<int>(plan.n);
+  p.half = plan.format == ALIVE_KNN_FORMAT_FP16 ? 1 : 0;
   p.k_blocks = plan.d / kBlockK;
   p.m_units = plan.m_units;
   p.segments = plan.segments;
@@ -1046,6 +1048,7 @@ int launch_skinny(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
   }
   SkinnyParams p;
   p.contig = contig_exp ? 1 : 0;
+  p.half = plan.format == ALIVE_KNN_FORMAT_FP16 ? 1 : 0;
   p.t = plan.t;
   p.n = static_cast<int>(plan.n);
   p.k_blocks = plan.d / kBlockK;
@@ -1113,6 +1116,7 @@ extern "C" int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32
   }
   ALIVE_REQUIRE(variant >= 1 && variant <= 3, "alive_knn_plan: variant must be 0, 1, 2 or 3");
   plan->kernel = 0;
+  plan->format = ALIVE_KNN_FORMAT_BF16;      // the caller sets the format of ITS operands
   if (variant == 3) {
     ALIVE_REQUIRE(skinny_ok, "alive_knn_plan: the skinny kernel needs one item, t <= %d and d <= %d (got t=%d d=%d items=%d)",
                   kSkinnyQ, 2048, t, d, items);
@@ -1213,6 +1217,7 @@ int search_impl(const uint16_t* q_packed, const uint16_t* lib_packed, const aliv
   ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(cand_score) & 15) == 0 && (reinterpret_cast<uintptr_t>(cand_idx) & 15) == 0,
                 "alive_knn_search: candidate buffers must be 16-byte aligned");
   ALIVE_REQUIRE(plan->d % 64 == 0 && plan->grid > 0 && plan->grid % plan->ctas_per_unit == 0, "alive_knn_search: bad plan");
+  ALIVE_REQUIRE(plan->format == ALIVE_KNN_FORMAT_BF16 || plan->format == ALIVE_KNN_FORMAT_FP16, "alive_knn_search: bad plan format");
   if (plan->kernel == 1) return launch_skinny(q_packed, lib_packed, *plan, cand_score, cand_idx, after_query_pack, as_stream(stream));
   ALIVE_REQUIRE(plan->kernel == 0, "alive_knn_search: unknown plan kernel %d", plan->kernel);
   if (plan->ctas_per_unit == 1) return launch_search<1>(q_packed, lib_packed, *plan, cand_score, cand_idx, after_query_pack, as_stream(stream));

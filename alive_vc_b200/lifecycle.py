@@ -377,8 +377,10 @@ class RowsContentEncoder(torch.nn.Module):
             return torch.nn.functional.linear(x.transpose(1, 2), out_layer.weight[:, :, 0], out_layer.bias)   # :24
         return enc(spec).transpose(1, 2)
 
-    def forward(self, spec: torch.Tensor) -> M.PackedFrames:
+    def forward(self, spec: torch.Tensor, fmt=None) -> M.PackedFrames:
+        """`fmt`: the 16-bit format of the libraries the frames will be matched against (None = matching.SCREEN_FORMAT)"""
         with torch.no_grad():
             rows = self.rows(spec)
             B, T, D = rows.shape
-            return M.pack_frames(rows.reshape(B * T, D).float().t())     # [D, B*T] view with stride_d == 1: K1's row-major kernel
+            # [D, B*T] view with stride_d == 1: K1's row-major kernel; both planes (queries are small)
+            return M.pack_frames(rows.reshape(B * T, D).float().t(), refine=True, fmt=fmt)

@@ -73,8 +73,9 @@ class PackedFrames:
     stats: torch.Tensor      # [4]   int32 (uint32 bit patterns): max err, non-finite row count, max err2, reserved
     row_base: int = 0        # global index of frame 0 (sharded libraries)
     items: int = 1           # > 1: `items` independent libraries of n // items frames each, back to back
-    lo: Optional[torch.Tensor] = None     # [n,d] bfloat16 second plane bf16(x/|x| - packed): refined collect pass
+    lo: Optional[torch.Tensor] = None     # [n,d] second plane rn16(x/|x| - packed): refined collect pass
     err2: Optional[torch.Tensor] = None   # [n] float32 ||x/|x| - packed - lo||_2
+    format: int = _cabi.FORMAT_BF16       # 16-bit format of packed / lo (see SCREEN_FORMAT)
     _handle: object = field(default=None, repr=False)
 
     @property
@@ -87,7 +88,7 @@ class PackedFrames:
         if h is None or h.row_base != self.row_base or h.items != self.items:
             h = _cabi.Library(self.packed.data_ptr(), self.raw.data_ptr(), self.norms.data_ptr(),
                               self.stats.data_ptr(), self.n // self.items, self.d, self.row_base, self.items,
-                              self.lo.data_ptr() if self.lo is not None else None)
+                              self.lo.data_ptr() if self.lo is not None else None, self.format)
             self._handle = h
         return h
 
@@ -105,7 +106,7 @@ class PackedFrames:
                             packed=self.packed[lo_row:hi_row], err=self.err[lo_row:hi_row], stats=self.stats,
                             row_base=self.row_base + lo_row,
                             lo=self.lo[lo_row:hi_row] if self.lo is not None else None,
-                            err2=self.err2[lo_row:hi_row] if self.err2 is not None else None)
+                            err2=self.err2[lo_row:hi_row] if self.err2 is not None else None, format=self.format)
 
 
 # The second bf16 plane costs 2 B per element (+33 % of a packed library) and buys the refined collect pass: clustered
@@ -113,6 +114,19 @@ class PackedFrames:
 # library when the plane fits comfortably (at most a quarter of the free device memory), off for sets of per-speaker
 # libraries (pack_libraries: BASELINE cfg5 fills the GPU without it); True / False force it.
 REFINE_DEFAULT = "auto"
+
+# 16-bit format of the packed planes (the tensor-core operands).  "fp16" (default): normalised frames live in [-1, 1],
+# IEEE half rounds them 8x finer than bfloat16 at the same tensor-core rate, so the certificate's band is 8x
+# narrower (clustered libraries certify in the first pass).  "bf16": the format the project brief names; same
+# throughput, same results (everything after the screen is exact either way).
+SCREEN_FORMAT = "fp16"
+_FORMATS = {"bf16": _cabi.FORMAT_BF16, "fp16": _cabi.FORMAT_FP16, _cabi.FORMAT_BF16: _cabi.FORMAT_BF16,
+            _cabi.FORMAT_FP16: _cabi.FORMAT_FP16}
+_PLANE_DTYPE = {_cabi.FORMAT_BF16: torch.bfloat16, _cabi.FORMAT_FP16: torch.float16}
+
+
+def _format_of(fmt) -> int:
+    return _FORMATS[SCREEN_FORMAT if fmt is None else fmt]
 
 
 def _want_refine(refine, n: int, d: int, device, items: int = 1) -> bool:
@@ -129,18 +143,20 @@ def _want_refine(refine, n: int, d: int, device, items: int = 1) -> bool:
     return bool(refine)
 
 
-def alloc_packed(n: int, d: int, device, refine=None, items: int = 1) -> PackedFrames:
+def alloc_packed(n: int, d: int, device, refine=None, items: int = 1, fmt=None) -> PackedFrames:
     want_lo = _want_refine(refine, n, d, device, items)
+    f = _format_of(fmt)
     return PackedFrames(
         n=n, d=d,
         raw=torch.empty((n, d), dtype=torch.float32, device=device),
         norms=torch.empty((n,), dtype=torch.float32, device=device),
-        packed=torch.empty((n, d), dtype=torch.bfloat16, device=device),
+        packed=torch.empty((n, d), dtype=_PLANE_DTYPE[f], device=device),
         err=torch.empty((n,), dtype=torch.float32, device=device),
         stats=torch.zeros((4,), dtype=torch.int32, device=device),
         items=items,
-        lo=torch.empty((n, d), dtype=torch.bfloat16, device=device) if want_lo else None,
+        lo=torch.empty((n, d), dtype=_PLANE_DTYPE[f], device=device) if want_lo else None,
         err2=torch.empty((n,), dtype=torch.float32, device=device) if want_lo else None,
+        format=f,
     )
 
 
@@ -158,35 +174,35 @@ def pack_into(dst: PackedFrames, row0: int, frames_dn: torch.Tensor):
             dst.raw[row0:].data_ptr(), dst.norms[row0:].data_ptr(), dst.packed[row0:].data_ptr(),
             dst.err[row0:].data_ptr(), dst.stats.data_ptr(),
             dst.lo[row0:].data_ptr() if dst.lo is not None else None,
-            dst.err2[row0:].data_ptr() if dst.err2 is not None else None, _stream_ptr(dst.device))
+            dst.err2[row0:].data_ptr() if dst.err2 is not None else None, dst.format, _stream_ptr(dst.device))
     _cabi.check(rc, "alive_knn_pack")
     _count(1)
 
 
-def pack_frames(frames_dn: torch.Tensor, refine=None) -> PackedFrames:
+def pack_frames(frames_dn: torch.Tensor, refine=None, fmt=None) -> PackedFrames:
     """Normalise-and-pack a [D, N] float32 CUDA view (the reference's channel-major
     layout, any strides).  Done ONCE per library (generate_voice_library.py / load time)
     instead of once per call as common.py:101-104 does.  `refine`: also store the second bf16 plane
-    (True / False / None = REFINE_DEFAULT, see there)."""
+    (True / False / None = REFINE_DEFAULT, see there); `fmt`: "fp16" / "bf16" (None = SCREEN_FORMAT)."""
     _require_cuda(frames_dn, "frames")
     if frames_dn.dtype != torch.float32:
         frames_dn = frames_dn.float()
     d, n = frames_dn.shape
-    out = alloc_packed(n, d, frames_dn.device, refine)
+    out = alloc_packed(n, d, frames_dn.device, refine, fmt=fmt)
     pack_into(out, 0, frames_dn)
     return out
 
 
-def pack_library(reference: torch.Tensor, refine=None) -> PackedFrames:
+def pack_library(reference: torch.Tensor, refine=None, fmt=None) -> PackedFrames:
     """[1, D, N] (or [D, N]) library tensor -> PackedFrames."""
     if reference.dim() == 3:
         if reference.shape[0] != 1:
             raise RuntimeError("pack_library expects a single library [1, D, N] (see pack_libraries)")
         reference = reference[0]
-    return pack_frames(reference, refine)
+    return pack_frames(reference, refine, fmt)
 
 
-def pack_libraries(reference: torch.Tensor, refine=None) -> PackedFrames:
+def pack_libraries(reference: torch.Tensor, refine=None, fmt=None) -> PackedFrames:
     """[B, D, N] -> ONE PackedFrames holding B independent libraries of N frames back to back
     (items = B): batch item b of a query tensor is matched against library b only, all of them in
     a single launch (BASELINE cfg5; train_decoder.py:134-135's per-utterance libraries)."""
@@ -196,7 +212,7 @@ def pack_libraries(reference: torch.Tensor, refine=None) -> PackedFrames:
     if reference.dtype != torch.float32:
         reference = reference.float()
     B, D, N = reference.shape
-    out = alloc_packed(B * N, D, reference.device, refine, items=B)
+    out = alloc_packed(B * N, D, reference.device, refine, items=B, fmt=fmt)
     for b in range(B):
         pack_into(out, b * N, reference[b])
     return out
@@ -233,7 +249,7 @@ def save_packed_library(lib: PackedFrames, path: str, include_legacy_tokens: boo
         torch.save({"tokens": tokens}, path)
     torch.save({
         "alive_knn_packed_version": PACKED_FORMAT_VERSION,
-        "n": lib.n, "d": lib.d, "row_base": lib.row_base, "items": lib.items,
+        "n": lib.n, "d": lib.d, "row_base": lib.row_base, "items": lib.items, "format": lib.format,
         "norms": lib.norms.cpu(), "packed": lib.packed.cpu(), "err": lib.err.cpu(), "stats": lib.stats.cpu(),
         "lo": lib.lo.cpu() if lib.lo is not None else None, "err2": lib.err2.cpu() if lib.err2 is not None else None,
         "fingerprint": _fingerprint(lib.raw),
@@ -274,7 +290,8 @@ def load_packed_library(path: str, device="cuda") -> PackedFrames:
             return PackedFrames(n=items * n_item, d=d, raw=raw, norms=sc["norms"].to(dev), packed=sc["packed"].to(dev),
                                 err=sc["err"].to(dev), stats=sc["stats"].to(dev), row_base=int(sc["row_base"]),
                                 items=items, lo=sc["lo"].to(dev) if sc.get("lo") is not None else None,
-                                err2=sc["err2"].to(dev) if sc.get("err2") is not None else None)
+                                err2=sc["err2"].to(dev) if sc.get("err2") is not None else None,
+                                format=int(sc.get("format", _cabi.FORMAT_BF16)))
         del raw      # stale sidecar (the tokens were edited since): pack again
     tok = tokens.to(dev)
     return pack_library(tok) if items == 1 else pack_libraries(tok)
@@ -403,10 +420,13 @@ def _count(n: int):
     launch_count += n
 
 
-def make_plan(t: int, n: int, d: int, device, variant: int = 0) -> _cabi.Plan:
+def make_plan(t: int, n: int, d: int, device, variant: int = 0, fmt=None) -> _cabi.Plan:
+    """`fmt`: the 16-bit format of the operands the plan will be launched on (PackedFrames.format; None = SCREEN_FORMAT,
+    what freshly packed frames have)"""
     plan = _cabi.Plan()
     rc = _cabi.load().alive_knn_plan(t, n, d, _num_sms(device), variant, ctypes.byref(plan))
     _cabi.check(rc, "alive_knn_plan")
+    plan.format = _format_of(fmt)
     return plan
 
 
@@ -458,7 +478,9 @@ def search_topk(q: PackedFrames, lib: PackedFrames, k: int, mode: str = "auto",
     if k > LIST_LEN:
         raise RuntimeError(f"the screened path needs k <= {LIST_LEN}")
 
-    plan = make_plan(t, n, d, dev, variant)
+    if q.format != lib.format:
+        raise RuntimeError("queries and library must be packed in the same 16-bit format")
+    plan = make_plan(t, n, d, dev, variant, lib.format)
     with _on(dev):
         return _search_topk_screen(c, q, lib, k, r_max, plan, dev)
 
@@ -514,10 +536,11 @@ def gather_mean(lib: PackedFrames, top_idx: torch.Tensor, q: PackedFrames, alpha
     return out
 
 
-def pack_queries(source: torch.Tensor) -> PackedFrames:
-    """[B, D, T] float32 CUDA -> PackedFrames with B*T rows (row b*T + t)."""
+def pack_queries(source: torch.Tensor, fmt=None) -> PackedFrames:
+    """[B, D, T] float32 CUDA -> PackedFrames with B*T rows (row b*T + t), both planes; `fmt` = the format of the
+    library they will be matched against (None = SCREEN_FORMAT)."""
     B, D, T = source.shape
-    out = alloc_packed(B * T, D, source.device)
+    out = alloc_packed(B * T, D, source.device, refine=True, fmt=fmt)
     for b in range(B):
         pack_into(out, b * T, source[b])
     return out
@@ -661,6 +684,8 @@ def match_packed_queries(q: PackedFrames, lib: PackedFrames, k: int = 4, alpha: 
     dev = q.device
     if dev != lib.device:
         raise RuntimeError(f"the packed queries are on {dev} but the packed library is on {lib.device}")
+    if q.format != lib.format:
+        raise RuntimeError("queries and library must be packed in the same 16-bit format (pack_frames(..., fmt=lib.format))")
     rows, D, T = q.n, q.d, q.n // batch
     m = _MODES[mode]
     if m == 0:

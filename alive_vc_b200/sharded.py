@@ -228,7 +228,7 @@ class CudaShardBackend:
 
     def _ensure_raw(self, q):
         if q.raw is None:       # this shard held no frames, so alive_knn_match never packed the queries
-            p = M.pack_queries(q.source)
+            p = M.pack_queries(q.source, fmt=self.local.format)
             q.raw, q.norms = p.raw, p.norms
 
     def local_topk(self, q, k, out_score=None, out_idx=None):

@@ -424,6 +424,7 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         exchange = "one fused merge + peer-memory (NVLink, CUDA IPC) gather kernel" if sharded.peers is not None else \
             "merge + reduce-scatter of the owned rows + all-gather of the result (NCCL)"
         parallelism = f"library rows sharded x{world}" + ("" if world == 1 else f", one all-gather of the top-k records, {exchange}")
+    lib_two_planes = lib.lo is not None
     streaming = workload in GRAPH_WORKLOADS and world == 1 and not args.no_graph and not batched
     if streaming:
         # fixed-shape chunks (inference.py / realtime_inference.py call the match once per chunk with
@@ -587,7 +588,8 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
                        "l2": "library (bf16 %.1f GB per GPU) is far larger than L2, no flush needed"
                              % (n_local * D * 2 / 1e9) if n_local * D * 2 > 256e6 else
                              "library smaller than 2x L2: numbers are warm-L2 steady state of a resident library",
-                       "variant": variant, "fallback_queries_last_step": fallback, "exact_scan_queries_last_step": exact_scan,
+                       "variant": variant, "planes": f"{args.format} ({'two planes' if lib_two_planes else 'one plane'})",
+                       "fallback_queries_last_step": fallback, "exact_scan_queries_last_step": exact_scan,
                        "api": "StreamingMatcher (one CUDA graph per chunk)" if streaming else
                               ("match_packed on pack_libraries (one launch for all speakers)" if batched else "ShardedLibrary.match")},
             "clocks": clocks,
@@ -782,6 +784,8 @@ def gpu_arm(args):
         dist.barrier()         # nobody loads the library before rank 0 has (re)built it
     env.peaks = load_peaks()
     env.variant = args.variant
+    from alive_vc_b200 import matching as _M
+    _M.SCREEN_FORMAT = args.format
 
     res = measure(env, args.workload, args.steps, args.warmup, headline=True)
     ok = True
@@ -791,7 +795,8 @@ def gpu_arm(args):
         line = {
             "metric": "query_frames_per_sec_matched_k4", "value": res["value"], "unit": "query_frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-            "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None, "dtype": "bf16",
+            "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
+            "dtype": "f16" if args.format == "fp16" else "bf16",
             "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],
             "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "parity": res["parity"],
         }
@@ -856,6 +861,9 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="multi-GPU row exchange: one fused merge+gather kernel over CUDA-IPC peer memory (falls back "
                          "to NCCL when the mapping fails), or always the NCCL reduce-scatter/all-gather")
+    ap.add_argument("--format", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit format of the packed planes (tensor-core operands): IEEE fp16 (default: same tensor-core rate, "
+                         "8x finer rounding of the normalised frames) or the bf16 the brief names")
     ap.add_argument("--torch-eager", action="store_true",
                     help="also time the reference's torch ops on the GPU (secondary line, where it fits)")
     args = ap.parse_args()

@@ -33,11 +33,17 @@ extern "C" {
 
 typedef void* alive_stream_t; /* cudaStream_t */
 
-#define ALIVE_KNN_ABI_VERSION 5
+#define ALIVE_KNN_ABI_VERSION 6
 #define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
 #define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
 #define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
 #define ALIVE_KNN_MAX_K 64        /* largest k supported by the exact selectors */
+/* 16-bit format of the packed planes (tensor-core operands).  bf16 is what the project brief names; IEEE fp16 runs
+ * at the same tensor-core rate (tcgen05.mma kind::f16 takes either) and, normalised frames living in [-1, 1], rounds
+ * 8x finer: the screening error bound - and with it the band the certificate has to clear - shrinks 8x.  Queries
+ * must be packed in the format of the library they are matched against. */
+#define ALIVE_KNN_FORMAT_BF16 0
+#define ALIVE_KNN_FORMAT_FP16 1
 
 /* Work decomposition of one alive_knn_search launch (filled by alive_knn_plan). */
 typedef struct alive_knn_plan {
@@ -52,6 +58,7 @@ typedef struct alive_knn_plan {
   int32_t lists;             /* running lists per query = 2 * segments */
   int32_t grid;              /* CTAs launched (multiple of ctas_per_unit) */
   int32_t items;             /* independent (query batch, library) pairs laid out back to back; 1 = plain */
+  int32_t format;            /* ALIVE_KNN_FORMAT_* of BOTH packed operands (set by the caller; the planners write BF16) */
   int32_t kernel;            /* 0: tiled kernel (fields as described above)
                               * 1: "skinny" kernel for t <= 32 (one realtime chunk): 128-frame library tiles on
                               *    the M side of the MMA, the query chunk resident in shared memory; n_tiles =
@@ -77,7 +84,8 @@ int alive_knn_abi_version(void);
  * writes
  *   raw    [n,d] float32 row-major copy of the UN-normalised frames (gather + rescoring)
  *   norms  [n]   float32 L2 norms (fp64 accumulation, rounded once)
- *   packed [n,d] bf16 row-major, frames divided by their norm (tensor-core operand, TMA friendly)
+ *   packed [n,d] 16-bit row-major (bf16 or fp16, `format`), frames divided by their norm (tensor-core operand,
+ *                TMA friendly)
  *   err    [n]   float32 || bf16(x/|x|) - x/|x| ||_2 per row (may be NULL)
  *   stats  [4]   see above; must be zeroed by the caller before the FIRST pack
  *                of a library (several packs may accumulate into one stats).
@@ -91,7 +99,7 @@ int alive_knn_abi_version(void);
  * (stride_d == 1), both with 16-byte aligned rows.  Every variant writes the same bits. */
 int alive_knn_pack(const float* x, int64_t n, int32_t d, int64_t stride_n, int64_t stride_d,
                    float* raw, float* norms, uint16_t* packed, float* err, uint32_t* stats,
-                   uint16_t* lo, float* err2, alive_stream_t stream);
+                   uint16_t* lo, float* err2, int32_t format, alive_stream_t stream);
 
 /* Fill `plan` for t queries against n library frames on a device with
  * `num_sms` SMs.  variant: 1 or 2 CTAs per unit, 3 = the skinny kernel (t <= 32, single item);
@@ -250,7 +258,8 @@ typedef struct alive_knn_library {
   int32_t d;
   int64_t row_base;         /* global index of frame 0 (row-sharded libraries), else 0 */
   int32_t items;            /* >= 1: independent libraries of n frames each, stored back to back */
-  const uint16_t* lo;       /* [n,d] bf16 second plane (alive_knn_pack `lo`), or NULL */
+  const uint16_t* lo;       /* [n,d] second plane (alive_knn_pack `lo`), or NULL */
+  int32_t format;           /* ALIVE_KNN_FORMAT_* of packed / lo */
 } alive_knn_library_t;
 
 /* One-call pipeline = module/common.py:96-109 for `batch` x `t` query frames against one

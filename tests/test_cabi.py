@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     assert sorted(_cabi.EXPORTS) == declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in alive_knn.h but not exported"
-    assert lib.alive_knn_abi_version() == 5
+    assert lib.alive_knn_abi_version() == 6
 
 
 def test_sass_is_blackwell_native():
@@ -93,7 +93,7 @@ def test_plan_rejects_bad_arguments(lib):
 
 def test_argument_validation_without_gpu(lib):
     # NULL pointers are rejected before any CUDA call is made
-    assert lib.alive_knn_pack(None, 4, 768, 1, 4, None, None, None, None, None, None, None, None) != 0
+    assert lib.alive_knn_pack(None, 4, 768, 1, 4, None, None, None, None, None, None, None, 0, None) != 0
     assert b"NULL" in lib.alive_knn_last_error()
     assert lib.alive_knn_exact_workspace_bytes(1000, 100000, 4, 1) > 0
 

@@ -48,9 +48,20 @@ def _assert_parity(out, idx, src, ref_b, k, alpha, want_idx=None, want_out=None)
     return n_exact, n_tie
 
 
+@pytest.fixture
+def screen_format(request, monkeypatch):
+    """the 16-bit format of the packed planes for this test (matching.SCREEN_FORMAT)"""
+    monkeypatch.setattr(M, "SCREEN_FORMAT", request.param)
+    M.clear_pack_cache()
+    yield request.param
+    M.clear_pack_cache()
+
+
+@pytest.mark.parametrize("screen_format", ["fp16", "bf16"], indirect=True)
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_golden_vectors_from_reference(name):
-    """Replays every fixture generated from the unmodified reference (tests/golden)."""
+def test_golden_vectors_from_reference(name, screen_format):
+    """Replays every fixture generated from the unmodified reference (tests/golden), with the planes stored as fp16
+    (default) and as bf16."""
     spec = CASES[name]
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     src, ref = make_case_inputs(spec)
@@ -82,12 +93,13 @@ def test_golden_vectors_from_reference(name):
         assert tuple(out.stride()) == tuple(g["out_strides"])      # transposed view of [B,T,D]
 
 
+@pytest.mark.parametrize("screen_format", ["fp16", "bf16"], indirect=True)
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,T,N,k,alpha", [
     (1, 50, 3000, 4, 0.0), (1, 200, 20000, 4, 0.0), (2, 33, 1517, 4, 0.25), (1, 96, 50000, 8, 0.0),
     (1, 1, 2049, 1, 0.0), (1, 129, 4097, 4, 0.0), (1, 300, 257, 4, 0.0), (3, 7, 256, 2, 1.0),
 ])
-def test_screened_path_against_oracle(variant, B, T, N, k, alpha):
+def test_screened_path_against_oracle(variant, B, T, N, k, alpha, screen_format):
     """tensor-core screen + certificate + exact rescoring == oracle, both kernel variants"""
     rng = np.random.default_rng(1000 * T + N + k)
     src = rng.standard_normal((B, 768, T), dtype=np.float32)
@@ -128,7 +140,8 @@ def test_full_size_cfg2_against_oracle():
     _assert_parity(out, idx, src, ref, 4, 0.0)
 
 
-def test_pack_kernel_layout_and_stats():
+@pytest.mark.parametrize("fmt,dtype,err_max,err2_max", [("bf16", torch.bfloat16, 3e-3, 1.2e-5), ("fp16", torch.float16, 4e-4, 2e-6)])
+def test_pack_kernel_layout_and_stats(fmt, dtype, err_max, err2_max):
     g = torch.Generator(device="cuda").manual_seed(1)
     # (n, row_major): every kernel of K1 - per-frame, 8-frame, generic 32-frame (n % 4 != 0), the 16-byte
     # cp.async channel-major kernel (ragged and full last CTA) and the register-resident row-major kernel
@@ -137,25 +150,26 @@ def test_pack_kernel_layout_and_stats():
         x = torch.randn(768, n, device="cuda", generator=g)
         if row_major:
             x = x.t().contiguous().t()
-        p = M.pack_frames(x)
+        p = M.pack_frames(x, fmt=fmt)
+        assert p.packed.dtype == dtype and p.format == M._FORMATS[fmt]
         assert torch.equal(p.raw, x.t().contiguous())
         nrm = torch.linalg.vector_norm(x.double(), dim=0).float()
         assert torch.allclose(p.norms, nrm, rtol=2e-7, atol=0)
         xn = (x / p.norms[None, :]).t()
-        assert torch.equal(p.packed, xn.bfloat16())
-        err = (xn.bfloat16().float() - xn).double().norm(dim=1).float()
+        assert torch.equal(p.packed, xn.to(dtype))
+        err = (xn.to(dtype).float() - xn).double().norm(dim=1).float()
         assert torch.allclose(p.err, err, rtol=1e-3, atol=1e-8)
         st = p.stats.cpu().numpy().view(np.uint32)
         assert st[1] == 0
         assert abs(np.array([st[0]], np.uint32).view(np.float32)[0] - float(p.err.max())) < 1e-9
         # the second plane: lo = bf16(x^ - hi), err2 = |x^ - hi - lo| (rounded up), stats[2] = its maximum
         assert p.lo is not None and p.err2 is not None
-        r1 = xn - xn.bfloat16().float()
-        assert torch.equal(p.lo, r1.bfloat16())
-        err2 = (r1 - r1.bfloat16().float()).double().norm(dim=1).float()
+        r1 = xn - xn.to(dtype).float()
+        assert torch.equal(p.lo, r1.to(dtype))
+        err2 = (r1 - r1.to(dtype).float()).double().norm(dim=1).float()
         assert torch.allclose(p.err2, err2, rtol=1e-3, atol=1e-11) and bool((p.err2 >= err2).all())
         assert abs(np.array([st[2]], np.uint32).view(np.float32)[0] - float(p.err2.max())) < 1e-12
-        assert float(p.err2.max()) < 1.2e-5 and float(p.err.max()) < 3e-3
+        assert float(p.err2.max()) < err2_max and float(p.err.max()) < err_max
     x = torch.randn(500, 768, device="cuda", generator=g)      # already row-major frames
     assert torch.equal(M.pack_frames(x.t()).raw, x)
     x = torch.randn(768, 40, device="cuda", generator=g)
@@ -535,6 +549,7 @@ def _clustered(T, N, nclus, noise, seed, dev="cuda"):
     return src, ref
 
 
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
 @pytest.mark.parametrize("refine", [True, False])
 @pytest.mark.parametrize("T,N,nclus,noise,expect", [
     (300, 60_000, 60, 0.2, "collect"),        # ~1000 frames inside every query's first-pass band
@@ -544,14 +559,16 @@ def _clustered(T, N, nclus, noise, seed, dev="cuda"):
     (32, 600_000, 600, 0.2, "collect"),       # a realtime chunk (skinny first screen) against a clustered library
     (200, 100_000, 20, 0.05, "tight"),        # 5000 frames within ~3e-4 of each other per cluster
 ])
-def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect, refine):
+def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect, refine, fmt, monkeypatch):
     """Tight clusters defeat the bf16 certificate; the second (collecting) tensor-core pass must give exactly what the
     exhaustive scan gives, whichever of its exits a query takes.  With the library's second bf16 plane (refine) the
     pass runs hi.hi + hi.lo + lo.hi against a cut tightened by a few exact rescorings, and NOTHING is left for the
-    exhaustive scan on any of these libraries; without it the candidate buffers of the densest ones overflow."""
+    exhaustive scan on any of these libraries; without it the candidate buffers of the densest ones overflow.
+    With fp16 planes (the default) the first-pass band is 8x narrower: most of these libraries certify at once."""
+    monkeypatch.setattr(M, "SCREEN_FORMAT", fmt)
     src, ref = _clustered(T, N, nclus, noise, seed=T + N)
     lib = A.pack_library(ref, refine=refine)
-    assert (lib.lo is not None) == refine
+    assert (lib.lo is not None) == refine and lib.format == M._FORMATS[fmt]
     out_s, idx_s, sc_s = M.run_match(src, lib, 4, 0.25, mode="screen")
     info = M.last_info
     fb, ex = info.fallback_queries(), info.exact_scan_queries()
@@ -560,13 +577,15 @@ def test_collect_pass_on_clustered_libraries(T, N, nclus, noise, expect, refine)
     assert torch.equal(idx_s, idx_e)
     assert torch.equal(out_s, out_e)
     assert torch.equal(sc_s, sc_e)
-    if expect in ("collect", "overflow", "many", "tight"):
+    if fmt == "bf16" and expect in ("collect", "overflow", "many", "tight"):
         assert fb > T // 2
+    if fmt == "fp16" and expect == "tight":
+        assert fb > T // 2                     # ~5000 frames within 3e-4: beyond any 16-bit screen
     if refine:
         assert ex == 0, (fb, ex)
     elif expect == "collect":
         assert ex == 0
-    elif expect == "overflow":
+    elif expect == "overflow" and fmt == "bf16":
         assert ex > T // 2
     # and against the oracle on a slice (the whole batch would take the CPU too long)
     sl = slice(0, 40)
@@ -585,7 +604,7 @@ def test_collect_pass_for_batched_libraries():
         refs.append(r)
     src, ref = torch.cat(srcs), torch.cat(refs)
     for refine in (False, True):
-        lib = A.pack_libraries(ref, refine=refine)
+        lib = A.pack_libraries(ref, refine=refine, fmt="bf16")      # (bf16: the clustered items need the collect pass)
         assert lib.items == B and (lib.lo is not None) == refine
         out_s, idx_s, sc_s = M.run_match(src, lib, 4, 0.0, mode="screen")
         info = M.last_info
@@ -607,7 +626,7 @@ def test_tensor_core_accumulation_error_model():
     fused kernel kept, on i.i.d. frames and on near-duplicates (scores up to 1: the worst case for a truncating
     accumulator).  The observed maximum must stay below HALF the slack, and the error must be one-sided (truncation)."""
     g = torch.Generator(device="cuda").manual_seed(1)
-    for D in (768, 1536):
+    for D, fmt in ((768, "bf16"), (768, "fp16"), (1536, "bf16"), (1536, "fp16")):
         slack = (D // 16) * 2.0 ** -22 + 2e-7
         T, N = 256, 40_000
         cases = [(torch.randn(D, T, device="cuda", generator=g), torch.randn(D, N, device="cuda", generator=g))]
@@ -617,9 +636,9 @@ def test_tensor_core_accumulation_error_model():
                           cent[:, torch.randint(0, 20, (N,), device="cuda", generator=g)] + noise * torch.randn(D, N, device="cuda", generator=g)))
         cases.append((torch.rand(D, T, device="cuda", generator=g) + 0.5, torch.rand(D, N, device="cuda", generator=g) + 0.5))
         for src, ref in cases:
-            q, lib = M.pack_frames(src), M.pack_frames(ref)
+            q, lib = M.pack_frames(src, fmt=fmt), M.pack_frames(ref, fmt=fmt)
             for variant in (1, 2):
-                plan = M.make_plan(T, N, D, q.device, variant)
+                plan = M.make_plan(T, N, D, q.device, variant, fmt)
                 cs = torch.empty((T, plan.lists * 8), device="cuda")
                 ci = torch.empty((T, plan.lists * 8), dtype=torch.int32, device="cuda")
                 _cabi.check(_cabi.load().alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan),
@@ -656,7 +675,7 @@ def test_collect_pass_on_a_row_shard():
     indices, and the two shards merged must equal the unsharded answer."""
     T, N = 500, 80_000                     # per shard T * N/2 = 2e7 >= 2^24: the collect pass is on
     src, ref = _clustered(T, N, 40, 0.2, seed=17)
-    lib = A.pack_library(ref)
+    lib = A.pack_library(ref, fmt="bf16")  # (bf16 planes: at this cluster width nothing certifies in the first pass)
     _, want_idx, want_sc = M.run_match(src, lib, 4, 0.0, mode="exact")
     half = N // 2
     tops, uncertified = [], 0
