@@ -115,18 +115,48 @@ class PackedFrames:
 # libraries (pack_libraries: BASELINE cfg5 fills the GPU without it); True / False force it.
 REFINE_DEFAULT = "auto"
 
-# 16-bit format of the packed planes (the tensor-core operands).  "fp16" (default): normalised frames live in [-1, 1],
-# IEEE half rounds them 8x finer than bfloat16 at the same tensor-core rate, so the certificate's band is 8x
-# narrower (clustered libraries certify in the first pass).  "bf16": the format the project brief names; same
-# throughput, same results (everything after the screen is exact either way).
-SCREEN_FORMAT = "fp16"
-_FORMATS = {"bf16": _cabi.FORMAT_BF16, "fp16": _cabi.FORMAT_FP16, _cabi.FORMAT_BF16: _cabi.FORMAT_BF16,
-            _cabi.FORMAT_FP16: _cabi.FORMAT_FP16}
+# 16-bit format of the packed planes (the tensor-core operands); results are identical either way (everything after
+# the screen is exact), only the speed differs:
+#   "bf16"  the format the project brief names, and the faster one on well-spread libraries: fp16 multipliers draw more
+#           power, and under the 1 kW cap the fp16 screen of BASELINE cfg4 runs 7 % slower (1340 vs 1440 TFLOP/s, SM
+#           clock 1230 vs 1350 MHz - measured);
+#   "fp16"  normalised frames live in [-1, 1], IEEE half rounds them 8x finer at the same tensor-core rate: the
+#           certificate's band is 8x narrower, so CLUSTERED libraries (near-duplicate frames: silence, sustained vowels)
+#           certify in the first pass instead of taking the collect pass (cfg1 shape, clusters of 1000 frames at noise
+#           0.2: 0.17 ms against 0.53 ms);
+#   "auto"  (default for pack_library / pack_frames of a single library) pack as bf16, probe the library with 256 of its
+#           own frames, repack as fp16 when more than an eighth of them cannot be certified.  Costs one small screen and
+#           one host synchronisation at PACK time.
+# Buffers that are filled piecewise (alloc_packed + pack_into) and query packs use the explicit format ("auto" = bf16).
+SCREEN_FORMAT = "auto"
+_FORMATS = {"bf16": _cabi.FORMAT_BF16, "fp16": _cabi.FORMAT_FP16, "auto": _cabi.FORMAT_BF16,
+            _cabi.FORMAT_BF16: _cabi.FORMAT_BF16, _cabi.FORMAT_FP16: _cabi.FORMAT_FP16}
 _PLANE_DTYPE = {_cabi.FORMAT_BF16: torch.bfloat16, _cabi.FORMAT_FP16: torch.float16}
+AUTO_PROBE_MIN_FRAMES = 4096
+AUTO_PROBE_QUERIES = 256
 
 
 def _format_of(fmt) -> int:
     return _FORMATS[SCREEN_FORMAT if fmt is None else fmt]
+
+
+def probe_uncertified_fraction(lib: "PackedFrames", samples: int = AUTO_PROBE_QUERIES) -> float:
+    """Fraction of `samples` evenly spaced LIBRARY frames, matched against the library itself (k = 4: the frame and its
+    three nearest neighbours), that the first-pass certificate cannot clear - the signature of a clustered library.
+    Synchronises the host (a pack-time decision)."""
+    global last_info
+    if lib.items != 1:
+        raise RuntimeError("probe_uncertified_fraction expects a single library")
+    m = min(samples, lib.n)
+    idx = torch.linspace(0, lib.n - 1, m, device=lib.device).long()
+    q = PackedFrames(n=m, d=lib.d, raw=lib.raw[idx], norms=lib.norms[idx], packed=lib.packed[idx], err=lib.err[idx],
+                     stats=lib.stats, lo=lib.lo[idx] if lib.lo is not None else None,
+                     err2=lib.err2[idx] if lib.err2 is not None else None, format=lib.format)
+    saved = last_info
+    match_packed_queries(q, lib, min(4, lib.n), 0.0, mode="screen", want_out=False)
+    frac = last_info.fallback_queries() / float(m)
+    last_info = saved
+    return frac
 
 
 def _want_refine(refine, n: int, d: int, device, items: int = 1) -> bool:
@@ -183,13 +213,21 @@ def pack_frames(frames_dn: torch.Tensor, refine=None, fmt=None) -> PackedFrames:
     """Normalise-and-pack a [D, N] float32 CUDA view (the reference's channel-major
     layout, any strides).  Done ONCE per library (generate_voice_library.py / load time)
     instead of once per call as common.py:101-104 does.  `refine`: also store the second bf16 plane
-    (True / False / None = REFINE_DEFAULT, see there); `fmt`: "fp16" / "bf16" (None = SCREEN_FORMAT)."""
+    (True / False / None = REFINE_DEFAULT, see there); `fmt`: "bf16" / "fp16" / "auto" (None = SCREEN_FORMAT)."""
     _require_cuda(frames_dn, "frames")
     if frames_dn.dtype != torch.float32:
         frames_dn = frames_dn.float()
     d, n = frames_dn.shape
-    out = alloc_packed(n, d, frames_dn.device, refine, fmt=fmt)
+    choice = SCREEN_FORMAT if fmt is None else fmt
+    out = alloc_packed(n, d, frames_dn.device, refine, fmt=choice)
     pack_into(out, 0, frames_dn)
+    if choice == "auto" and n >= AUTO_PROBE_MIN_FRAMES and d % 64 == 0:
+        bad_rows = int(out.stats[1].item())
+        if bad_rows == 0 and probe_uncertified_fraction(out) > 0.125:
+            keep_lo = out.lo is not None
+            del out                                   # clustered: the 8x finer rounding of fp16 pays for itself
+            out = alloc_packed(n, d, frames_dn.device, keep_lo, fmt="fp16")
+            pack_into(out, 0, frames_dn)
     return out
 
 

@@ -406,7 +406,7 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         lo, hi = shard_bounds(N, world, rank)
         if clustered is not None:
             src_dev, ref = build_clustered(T, N, clustered["clusters"], clustered["noise"], args.seed, dev)
-            lib = M.pack_library(ref)
+            lib = M.pack_library(ref, fmt=clustered.get("fmt", "auto"))       # "auto": the pack-time probe chooses
             del ref
         else:
             lib = build_library(lo, hi, args.seed, dev)
@@ -588,7 +588,9 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
                        "l2": "library (bf16 %.1f GB per GPU) is far larger than L2, no flush needed"
                              % (n_local * D * 2 / 1e9) if n_local * D * 2 > 256e6 else
                              "library smaller than 2x L2: numbers are warm-L2 steady state of a resident library",
-                       "variant": variant, "planes": f"{args.format} ({'two planes' if lib_two_planes else 'one plane'})",
+                       "variant": variant,
+                       "planes": f"{'fp16' if lib.format == 1 else 'bf16'} ({'two planes' if lib_two_planes else 'one plane'})"
+                                 + (f", requested {clustered.get('fmt', 'auto')}" if clustered is not None else ""),
                        "fallback_queries_last_step": fallback, "exact_scan_queries_last_step": exact_scan,
                        "api": "StreamingMatcher (one CUDA graph per chunk)" if streaming else
                               ("match_packed on pack_libraries (one launch for all speakers)" if batched else "ShardedLibrary.match")},
@@ -752,7 +754,7 @@ def summary_of(res):
     r = res["roofline"]
     out["roofline"] = {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "avg_kernel_ms",
                                            "frac_of_sustained", "kernel_share_of_step") if k in r}
-    out["config"] = {k: res["config"][k] for k in ("workload", "B", "T", "N", "api", "fallback_queries_last_step",
+    out["config"] = {k: res["config"][k] for k in ("workload", "B", "T", "N", "api", "planes", "fallback_queries_last_step",
                                                     "exact_scan_queries_last_step")}
     out["clocks"] = res["clocks"]
     return out
@@ -823,16 +825,17 @@ def gpu_arm(args):
             if not args.no_cpu:
                 extras[w]["cpu_baseline"] = run_cpu_arm(w, 2, 1)
         # clustered libraries: cfg1's shape, 100 clusters of ~1000 near-identical frames
-        for noise in (0.2, 0.5):
+        for noise, fmt in ((0.2, "auto"), (0.5, "auto"), (0.2, "bf16")):
+            name = f"clustered_noise{noise}" + ("" if fmt == "auto" else f"_{fmt}")
             try:
-                r = measure(env, "cfg1", 20, 3, headline=False, clustered={"clusters": 100, "noise": noise})
+                r = measure(env, "cfg1", 20, 3, headline=False, clustered={"clusters": 100, "noise": noise, "fmt": fmt})
                 ent = summary_of(r)
                 ent["slowdown_vs_random_cfg1"] = (r["ms_per_step"] / extras["cfg1"]["ms_per_step"]
                                                   if "ms_per_step" in extras.get("cfg1", {}) else None)
-                extras[f"clustered_noise{noise}"] = ent
+                extras[name] = ent
                 ok = ok and r["parity"]["ok"]
             except Exception as e:       # noqa: BLE001
-                extras[f"clustered_noise{noise}"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
         line["workloads"] = extras
     if rank == 0:
@@ -861,9 +864,10 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="multi-GPU row exchange: one fused merge+gather kernel over CUDA-IPC peer memory (falls back "
                          "to NCCL when the mapping fails), or always the NCCL reduce-scatter/all-gather")
-    ap.add_argument("--format", default="fp16", choices=["fp16", "bf16"],
-                    help="16-bit format of the packed planes (tensor-core operands): IEEE fp16 (default: same tensor-core rate, "
-                         "8x finer rounding of the normalised frames) or the bf16 the brief names")
+    ap.add_argument("--format", default="bf16", choices=["fp16", "bf16"],
+                    help="16-bit format of the packed planes (tensor-core operands) of the synthetic BASELINE libraries: bf16 "
+                         "(the brief's format and the faster one under the power cap) or IEEE fp16 (8x finer rounding; what "
+                         "pack_library's probe picks for clustered libraries - the `clustered` entries use that probe)")
     ap.add_argument("--torch-eager", action="store_true",
                     help="also time the reference's torch ops on the GPU (secondary line, where it fits)")
     args = ap.parse_args()

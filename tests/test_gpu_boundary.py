@@ -195,3 +195,38 @@ def test_two_devices_in_one_process():
     for o, i in outs[1:]:
         assert torch.equal(o, outs[0][0]) and torch.equal(i, outs[0][1])
     _oracle_check(outs[0][0], outs[0][1], src, ref, 4, 0.0)
+
+
+def test_auto_format_probe_picks_fp16_for_clustered_libraries():
+    """pack_library's default ("auto"): bf16 planes unless a probe with 256 of the library's own frames finds it
+    clustered, then IEEE fp16 (8x finer rounding -> the certificate clears in the first pass).  Results are the
+    exhaustive scan's either way."""
+    assert M.SCREEN_FORMAT == "auto"
+    g = torch.Generator(device="cuda").manual_seed(12)
+    spread = torch.randn(1, 768, 50_000, device="cuda", generator=g)
+    lib = A.pack_library(spread)
+    assert lib.format == 0 and lib.packed.dtype == torch.bfloat16 and lib.lo is not None
+    assert M.probe_uncertified_fraction(lib) == 0.0
+    cent = torch.randn(768, 50, device="cuda", generator=g)
+    clustered = (cent[:, torch.randint(0, 50, (50_000,), device="cuda", generator=g)] +
+                 0.2 * torch.randn(768, 50_000, device="cuda", generator=g))[None]
+    src = (cent[:, torch.randint(0, 50, (500,), device="cuda", generator=g)] + 0.2 * torch.randn(768, 500, device="cuda", generator=g))[None]
+    forced = A.pack_library(clustered, fmt="bf16")
+    assert M.probe_uncertified_fraction(forced) > 0.5
+    lib = A.pack_library(clustered)
+    assert lib.format == 1 and lib.packed.dtype == torch.float16
+    out, idx, sc = A.match_packed(src, lib, 4, 0.0)
+    assert M.last_info.mode == "screen" and M.last_info.fallback_queries() < 50      # certified in the first pass
+    out_b, idx_b, sc_b = A.match_packed(src, forced, 4, 0.0)
+    assert M.last_info.fallback_queries() > 250 and M.last_info.exact_scan_queries() == 0
+    out_e, idx_e, sc_e = M.run_match(src, lib, 4, 0.0, mode="exact")
+    for o, i, s_ in ((out, idx, sc), (out_b, idx_b, sc_b)):
+        assert torch.equal(i, idx_e) and torch.equal(o, out_e) and torch.equal(s_, sc_e)
+    # the functional API inherits the choice through its pack cache
+    want = A.match_features(src, clustered, 4, 0.0)
+    assert torch.equal(want, out_e.transpose(1, 2))
+    # small libraries are never probed; libraries with non-finite rows keep bf16
+    assert A.pack_library(clustered[:, :, :4000]).format == 0
+    broken = clustered.clone()
+    broken[0, :, 5] = 0.0
+    assert A.pack_library(broken).format == 0

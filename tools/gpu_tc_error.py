@@ -15,7 +15,7 @@ from alive_vc_b200 import _cabi, matching as M        # noqa: E402
 
 
 def lists(q, lib, variant):
-    plan = M.make_plan(q.n, lib.n, lib.d, q.device, variant)
+    plan = M.make_plan(q.n, lib.n, lib.d, q.device, variant, lib.format)
     cs = torch.empty((q.n, plan.lists, 8), device="cuda")
     ci = torch.empty((q.n, plan.lists, 8), dtype=torch.int32, device="cuda")
     rc = _cabi.load().alive_knn_search(q.packed.data_ptr(), lib.packed.data_ptr(), ctypes.byref(plan), cs.data_ptr(),
@@ -47,6 +47,8 @@ def report(name, q, lib, variant):
 
 def main():
     g = torch.Generator(device="cuda").manual_seed(1)
+    M.SCREEN_FORMAT = os.environ.get("PLANES", "bf16")        # explicit: no pack-time probe, both operands alike
+    print("planes:", M.SCREEN_FORMAT)
     for D in (768, 1536):
         T, N = 512, 60_000
         q = M.pack_frames(torch.randn(D, T, device="cuda", generator=g))
