@@ -310,9 +310,11 @@ __device__ __forceinline__ void list_insert(float (&s)[kListLen], uint32_t (&id)
 // the columns that beat it, the chunk parked in this thread's shared-memory scratch column,
 // and a loop over the set bits with ONE copy of the ordered insert - the code stays small
 // enough to live in the instruction cache (the fully unrolled variant was fetch-bound).
+template <int kPark = 32>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_base, int n_valid,
                                            float (&s)[kListLen], uint32_t (&id)[kListLen],
-                                           float* __restrict__ scratch /* [32][256], this thread's column */) {
+                                           float* __restrict__ scratch /* [kPark][256], this thread's column */) {
+  static_assert(kPark == 32 || kPark == 16, "park 32 or 16 columns at a time");
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -328,15 +330,36 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&raw)[32], int col_ba
     const float thr = s[kListLen - 1];
     uint32_t mask = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      scratch[j * (kNumEpiWarps * 32)] = v[j];
-      mask |= (v[j] > thr) ? (1u << j) : 0u;
-    }
-    while (mask) {
-      const int j = __ffs(static_cast<int>(mask)) - 1;
-      mask &= mask - 1;
-      const float x = scratch[j * (kNumEpiWarps * 32)];
-      if (x > s[kListLen - 1]) list_insert(s, id, x, static_cast<uint32_t>(col_base + j));
+    for (int j = 0; j < 32; ++j) mask |= (v[j] > thr) ? (1u << j) : 0u;
+    if constexpr (kPark == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) scratch[j * (kNumEpiWarps * 32)] = v[j];
+      while (mask) {
+        const int j = __ffs(static_cast<int>(mask)) - 1;
+        mask &= mask - 1;
+        const float x = scratch[j * (kNumEpiWarps * 32)];
+        if (x > s[kListLen - 1]) list_insert(s, id, x, static_cast<uint32_t>(col_base + j));
+      }
+    } else {
+      // half the scratch: the two 16-column halves are parked one after the other, ONE copy of the insert loop
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t mh = (mask >> (16 * h)) & 0xFFFFu;
+        if (mh == 0) continue;
+        if (h == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) scratch[j * (kNumEpiWarps * 32)] = v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) scratch[j * (kNumEpiWarps * 32)] = v[16 + j];
+        }
+        while (mh) {
+          const int j = __ffs(static_cast<int>(mh)) - 1;
+          mh &= mh - 1;
+          const float x = scratch[j * (kNumEpiWarps * 32)];
+          if (x > s[kListLen - 1]) list_insert(s, id, x, static_cast<uint32_t>(col_base + 16 * h + j));
+        }
+      }
     }
   }
 }
@@ -631,6 +654,294 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // ------------------------------------------ teardown ------------------------------------------
   tcgen05_fence_before();
   if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<kCtas>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel with a (partly) RESIDENT query block, specialised for a compile-time number of channel blocks
+// (kKB = d/64; 12 for the 768-channel features of the reference).
+//
+// Why: under ncu the kernel above keeps the tensor pipe 98 % busy - what bounds it is the SM clock the 1 kW power cap
+// allows, and a good part of the power moves operands: 1.23 TB per cfg4 launch cross the L2->SM crossbar, half of
+// them the SAME 128 x 768 query block fetched again for every library tile (an experiment that skipped those reloads
+// ran 8 % faster at higher clocks).  Here the first kRes channel blocks of the unit's query rows are loaded ONCE per
+// unit and stay in shared memory; the ring carries 16 KB slots: one (library) per resident channel block, two (query,
+// library) per streamed one - kUses = kRes + 2 (kKB - kRes) slot loads per tile instead of 2 kKB.
+//
+// How (measured at cfg4, ms per step, kernel above = 105.9): what decides is the look-ahead of the ring in CHANNEL
+// BLOCKS.  Six slots behind six leading resident blocks cover 6 blocks in the resident half of a tile but only 3 in
+// the streamed half: 109.1 ms with run-time slot arithmetic, 107.8 ms fully static - slower than no residency, at
+// HIGHER clocks (the tensor pipe idles).  Eight resident + four slots: 117.8 ms.  Making every OTHER channel block
+// resident (kInterleave) gives a uniform demand of 3 slots per 2 blocks = 4 blocks of look-ahead everywhere:
+// 102.5 ms, +4.3 % over the kernel above.  Everything is static: kUses is a multiple of kSlots, every use of every
+// tile therefore hits the same slot, the loops over channel blocks are fully unrolled with constant addresses, and
+// the only run-time state is one parity bit per tile.
+//   smem: A_res [kRes][16 KB] | slots [kSlots][16 KB] | epilogue scratch 32 KB | barriers
+//   barriers: full/empty per slot, tfull/tempty per accumulator, ares_full (the resident block has landed),
+//             ares_free (every MMA of the unit that read it has retired: the next unit's block may overwrite it)
+// Same MMA sequence, same accumulators, same epilogue as above: bit-identical lists.
+// ---------------------------------------------------------------------------------------------
+template <int kKB, int kRes, int kSlots, bool kInterleave = false> struct ResCfg {
+  static constexpr int kUses = kRes + 2 * (kKB - kRes);           // slot loads per library tile
+  static constexpr int kRounds = kUses / kSlots;                   // trips around the ring per tile
+  static_assert(kRes <= kKB && kUses % kSlots == 0, "resident kernel: the slot pattern must repeat every tile");
+  static_assert(!kInterleave || kKB == 2 * kRes, "interleaved pattern: every other channel block is resident");
+  static constexpr uint32_t kSmemData = (kRes + kSlots) * kABytes;
+  static constexpr uint32_t kScratch = 32 * kNumEpiWarps * 32 * 4;
+  static constexpr uint32_t kSmemBytes = kSmemData + kScratch + 1024 + 256;
+  static_assert(kSmemBytes <= 227 * 1024, "resident kernel: shared memory");
+  // which channel blocks are resident: the first kRes, or (kInterleave) the even ones - a uniform slot demand
+  __host__ __device__ static constexpr bool is_res(int kb) { return kInterleave ? (kb & 1) == 0 : kb < kRes; }
+  __host__ __device__ static constexpr int res_idx(int kb) { return kInterleave ? kb / 2 : kb; }
+  // use index (position in the per-tile load sequence) of the library (B) load of channel block kb, and of its
+  // query (A) load when that block streams
+  __host__ __device__ static constexpr int use_b(int kb) {
+    return kInterleave ? 3 * (kb / 2) + ((kb & 1) ? 2 : 0) : (kb < kRes ? kb : kRes + 2 * (kb - kRes) + 1);
+  }
+  __host__ __device__ static constexpr int use_a(int kb) { return kInterleave ? 3 * (kb / 2) + 1 : kRes + 2 * (kb - kRes); }
+  // the inverse: channel block and operand of use u
+  __host__ __device__ static constexpr int use_kb(int u) {
+    return kInterleave ? 2 * (u / 3) + (u % 3 != 0 ? 1 : 0) : (u < kRes ? u : kRes + (u - kRes) / 2);
+  }
+  __host__ __device__ static constexpr bool use_is_a(int u) {
+    return kInterleave ? u % 3 == 1 : (u >= kRes && ((u - kRes) & 1) == 0);
+  }
+};
+
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {   // small at the (unrolled) call site
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+template <int kKB, int kRes, int kSlots, bool kInterleave>
+__global__ void __launch_bounds__(kThreads, 1)
+knn_search_resident_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_lib,
+                           const SearchParams p) {
+  constexpr int kCtas = 2;
+  using RC = ResCfg<kKB, kRes, kSlots, kInterleave>;
+  constexpr uint32_t kSlotBytes = kABytes;                        // 16 KB: 128 rows x 64 channels of either operand
+  constexpr int kBRows = kBlockN / kCtas;                         // library rows this CTA loads per tile
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_res = smem_base;
+  const uint32_t smem_slot = smem_base + kRes * kSlotBytes;
+  const uint32_t scratch_off = RC::kSmemData;
+  const uint32_t bars = smem_base + RC::kSmemData + RC::kScratch;
+  const uint32_t bar_full = bars;                                // kSlots x 8 B
+  const uint32_t bar_empty = bars + 8 * kSlots;                  // kSlots x 8 B
+  const uint32_t bar_tfull = bars + 16 * kSlots;                 // 2 x 8 B
+  const uint32_t bar_tempty = bars + 16 * kSlots + 16;           // 2 x 8 B
+  const uint32_t bar_ares_full = bars + 16 * kSlots + 32;        // 8 B
+  const uint32_t bar_ares_free = bars + 16 * kSlots + 40;        // 8 B
+  const uint32_t tmem_slot = bars + 16 * kSlots + 48;            // 4 B
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int unit_stride = gridDim.x / kCtas;
+  const int first_unit = blockIdx.x / kCtas;
+  const int units_per_item = p.m_units * p.segments;
+  const int total_units = units_per_item * p.items;
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_lib);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, kNumEpiWarps * kCtas);
+    }
+    mbar_init(bar_ares_full, 1);
+    mbar_init(bar_ares_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kCtas>(tmem_slot, kTmemCols);
+    tmem_relinquish<kCtas>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    pdl_wait();
+    const uint32_t full0 = map_to_cta(bar_full, 0);              // the full barriers live in the leader
+    const uint32_t ares_full0 = map_to_cta(bar_ares_full, 0);
+    int my_tiles = 0, epoch = 0, my_units = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride, ++my_units) {
+      const int item = unit / units_per_item;
+      const int rem = unit - item * units_per_item;
+      const int m_unit = rem % p.m_units;
+      const int seg = rem / p.m_units;
+      const int tile0 = seg * p.tiles_per_segment;
+      const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
+      const int q_row = item * p.t + (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+      const int lib_row0 = item * p.n;
+      // the resident block of this unit: the previous unit's MMAs must have retired before it is overwritten
+      if (my_units > 0) mbar_wait(bar_ares_free, (static_cast<uint32_t>(my_units) - 1u) & 1u);
+      if (elect_one_sync()) {
+        if (leader) mbar_expect_tx(bar_ares_full, kRes * kSlotBytes * kCtas);
+#pragma unroll
+        for (int kb = 0; kb < kKB; ++kb)
+          if (RC::is_res(kb))
+            tma_load_2d<kCtas>(smem_res + RC::res_idx(kb) * kSlotBytes, &tmap_q, ares_full0, kb * kBlockK, q_row, p.hint_q);
+      }
+      __syncwarp();
+      for (int tile = tile0; tile < tile1; ++tile, ++my_tiles) {
+        if (p.sync_ctr != nullptr && epoch < p.sync_rounds && my_tiles == (epoch + 1) * p.sync_every) {
+          // pacing, not correctness (see knn_search_kernel)
+          if (elect_one_sync()) {
+            atomicAdd(p.sync_ctr, 1u);
+            const unsigned int target = static_cast<unsigned int>(epoch + 1) * gridDim.x;
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned int*>(p.sync_ctr) < target && clock64() - t0 < 40000) {
+            }
+          }
+          __syncwarp();
+          ++epoch;
+        }
+        const int lib_row = lib_row0 + tile * kBlockN + static_cast<int>(cta_rank) * kBRows;
+        // parity of use u of this CTA's n-th tile: ring round n * kRounds + u / kSlots
+        const uint32_t tile_par = (static_cast<uint32_t>(my_tiles) * RC::kRounds) & 1u;
+#pragma unroll
+        for (int u = 0; u < RC::kUses; ++u) {
+          const int slot = u % kSlots;
+          const uint32_t par = (tile_par + static_cast<uint32_t>(u / kSlots)) & 1u;
+          const bool is_a = RC::use_is_a(u);
+          const int kb = RC::use_kb(u);
+          mbar_wait_lean(bar_empty + 8 * slot, par ^ 1u);
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(bar_full + 8 * slot, kSlotBytes * kCtas);
+            if (is_a) tma_load_2d<kCtas>(smem_slot + slot * kSlotBytes, &tmap_q, full0 + 8 * slot, kb * kBlockK, q_row, p.hint_q);
+            else tma_load_2d<kCtas>(smem_slot + slot * kSlotBytes, &tmap_lib, full0 + 8 * slot, kb * kBlockK, lib_row, p.hint_lib);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (leader) {
+      const uint32_t idesc = make_idesc(kBlockM * kCtas, kBlockN, p.half != 0);
+      const uint64_t desc_res = make_smem_desc(smem_res);        // +1024 per 16 KB (the address field counts 16 B)
+      const uint64_t desc_slot = make_smem_desc(smem_slot);
+      uint32_t tile_count = 0;
+      int my_units = 0;
+      for (int unit = first_unit; unit < total_units; unit += unit_stride, ++my_units) {
+        const int seg = (unit % units_per_item) / p.m_units;
+        const int tile0 = seg * p.tiles_per_segment;
+        const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
+        mbar_wait(bar_ares_full, static_cast<uint32_t>(my_units) & 1u);       // the unit's resident query block
+        tcgen05_fence_after();
+        for (int tile = tile0; tile < tile1; ++tile, ++tile_count) {
+          const uint32_t acc = tile_count & 1u;
+          const uint32_t acc_phase = (tile_count >> 1) & 1u;
+          const uint32_t tile_par = (tile_count * RC::kRounds) & 1u;
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kBlockN;
+#pragma unroll
+          for (int kb = 0; kb < kKB; ++kb) {
+            constexpr uint32_t kDescStep = kSlotBytes >> 4;
+            const bool streamed = !RC::is_res(kb);
+            const int ub = RC::use_b(kb);
+            const int ua = RC::use_a(kb);
+            if (streamed) mbar_wait_lean(bar_full + 8 * (ua % kSlots), (tile_par + static_cast<uint32_t>(ua / kSlots)) & 1u);
+            mbar_wait_lean(bar_full + 8 * (ub % kSlots), (tile_par + static_cast<uint32_t>(ub / kSlots)) & 1u);
+            tcgen05_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t adesc = streamed ? desc_slot + static_cast<uint64_t>((ua % kSlots) * kDescStep)
+                                              : desc_res + static_cast<uint64_t>(RC::res_idx(kb) * kDescStep);
+              const uint64_t bdesc = desc_slot + static_cast<uint64_t>((ub % kSlots) * kDescStep);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16<kCtas>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (streamed) umma_commit<kCtas>(bar_empty + 8 * (ua % kSlots));
+              umma_commit<kCtas>(bar_empty + 8 * (ub % kSlots));
+              if (kb == kKB - 1) {
+                umma_commit<kCtas>(bar_tfull + 8 * acc);
+                if (tile == tile1 - 1) umma_commit<kCtas>(bar_ares_free);      // the resident block may be replaced
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ======================================= epilogue (as in knn_search_kernel) =======================================
+    const int quarter = warp & 3;
+    const int half = (warp - kFirstEpiWarp) >> 2;
+    const uint32_t tempty0 = map_to_cta(bar_tempty, 0);
+    const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+    float* scratch = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + scratch_off) +
+                     (threadIdx.x - kFirstEpiWarp * 32);
+    uint32_t tile_count = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+      const int item = unit / units_per_item;
+      const int rem = unit - item * units_per_item;
+      const int m_unit = rem % p.m_units;
+      const int seg = rem / p.m_units;
+      const int tile0 = seg * p.tiles_per_segment;
+      const int tile1 = min(tile0 + p.tiles_per_segment, p.n_tiles);
+      const int row_in_item = (m_unit * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
+      const bool row_valid = row_in_item < p.t;
+      const int row = item * p.t + row_in_item;
+      const int col_item0 = item * p.n;
+      const int n_valid = col_item0 + p.n;
+      float s[kListLen];
+      uint32_t id[kListLen];
+#pragma unroll
+      for (int i = 0; i < kListLen; ++i) {
+        s[i] = row_valid ? -INFINITY : INFINITY;
+        id[i] = 0xFFFFFFFFu;
+      }
+      for (int tile = tile0; tile < tile1; ++tile, ++tile_count) {
+        const uint32_t acc = tile_count & 1u;
+        const uint32_t acc_phase = (tile_count >> 1) & 1u;
+        mbar_wait(bar_tfull + 8 * acc, acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = taddr_base + acc * kBlockN;
+        const int col0 = col_item0 + tile * kBlockN + half * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + 32 * c, v);
+          tmem_ld_wait(v);
+          if (c == 3) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);
+          }
+          scan_chunk(v, col0 + 32 * c, n_valid, s, id, scratch);
+        }
+      }
+      if (row_valid) {
+        const size_t o = (static_cast<size_t>(row) * p.lists + static_cast<size_t>(seg * 2 + half)) * kListLen;
+        float4* ps = reinterpret_cast<float4*>(p.cand_score + o);
+        int4* pi = reinterpret_cast<int4*>(p.cand_idx + o);
+        ps[0] = make_float4(s[0], s[1], s[2], s[3]);
+        ps[1] = make_float4(s[4], s[5], s[6], s[7]);
+        pi[0] = make_int4(static_cast<int>(id[0]), static_cast<int>(id[1]), static_cast<int>(id[2]), static_cast<int>(id[3]));
+        pi[1] = make_int4(static_cast<int>(id[4]), static_cast<int>(id[5]), static_cast<int>(id[6]), static_cast<int>(id[7]));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc<kCtas>(tmem_base, kTmemCols);
 }
@@ -1001,6 +1312,45 @@ int launch_search(const uint16_t* q, const uint16_t* lib, const alive_knn_plan_t
       p.sync_rounds = static_cast<int>(min_tiles / p.sync_every);
       if ((static_cast<long long>(p.sync_rounds) + 1) * plan.grid >= (1ll << 32)) p.sync_ctr = nullptr;
     }
+  }
+
+  // CTA pairs that visit several library tiles per unit keep (part of) their query block resident
+  bool resident = false;
+  if constexpr (kCtas == 2 && !kCollect && !kRefine) {
+    const char* rs = getenv("ALIVE_KNN_RESIDENT");
+    resident = (rs ? atoi(rs) != 0 : true) && p.debug == 0 && plan.tiles_per_segment >= 2 && plan.d == 768;
+  }
+  if (resident) {
+    const char* rs = getenv("ALIVE_KNN_RESIDENT");
+    const int rv = rs ? atoi(rs) : 1;
+    auto go = [&](auto kern, uint32_t smem, PerDeviceOnce& once) -> int {
+      const int rc_attr = once.run([&]() -> int {
+        ALIVE_CHECK_CUDA((cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))));
+        return 0;
+      });
+      if (rc_attr) return rc_attr;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = after_query_pack ? 2 : 1;
+      ALIVE_CHECK_CUDA((cudaLaunchKernelEx(&cfg, kern, mq, ml, p)));
+      return 0;
+    };
+    static PerDeviceOnce o1, o2;
+    // ALIVE_KNN_RESIDENT=2: the first six channel blocks resident instead of every other one (kept for the A/B in
+    // 3 channel blocks of look-ahead in the streamed half of each tile, 1.8 % SLOWER than no residency)
+    if (rv == 2) return go(knn_search_resident_kernel<12, 6, 6, false>, ResCfg<12, 6, 6, false>::kSmemBytes, o2);
+    return go(knn_search_resident_kernel<12, 6, 6, true>, ResCfg<12, 6, 6, true>::kSmemBytes, o1);
   }
 
   static PerDeviceOnce attr_once;
