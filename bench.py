@@ -361,9 +361,10 @@ def parity_block(env, sharded, lib, src_dev, batched: bool):
 
 def measure(env, workload: str, steps: int, warmup: int, headline: bool, clustered=None):
     """One workload on env.world GPUs -> the dict of its numbers (rank 0; None elsewhere)."""
+    import ctypes
     import torch
     import torch.distributed as dist
-    from alive_vc_b200 import matching as M
+    from alive_vc_b200 import _cabi, matching as M
     from alive_vc_b200.sharded import CudaShardBackend, ShardedLibrary, shard_bounds
 
     world, rank, dev, args, peaks, variant = env.world, env.rank, env.dev, env.args, env.peaks, env.variant
@@ -557,10 +558,14 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         flops_per_launch = 2.0 * (lib.items if batched else B) * T * n_local * D
         avg_search_ms = sum(search_ms) / max(1, len(search_ms))
         if batched:
-            search_kernel = "knn_search_kernel"
+            _plan = _cabi.Plan()
+            _cabi.check(_cabi.load().alive_knn_plan_batched(lib.items, T, n_local, D, M._num_sms(dev), variant,
+                                                            ctypes.byref(_plan)), "alive_knn_plan_batched")
+            search_kernel = "knn_search_resident_kernel" if resident_kernel(_plan) else "knn_search_kernel"
         else:
             _plan = M.make_plan(B * T, n_local, D, dev, variant)
-            search_kernel = "knn_search_skinny_kernel" if _plan.kernel == 1 else "knn_search_kernel"
+            search_kernel = ("knn_search_skinny_kernel" if _plan.kernel == 1 else
+                             "knn_search_resident_kernel" if resident_kernel(_plan) else "knn_search_kernel")
         if latency_workload:
             bytes_per_launch = float(n_local) * D * 2
             achieved = bytes_per_launch / (avg_search_ms * 1e-3) / 1e9
@@ -629,6 +634,22 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
     return res
 
 
+def resident_kernel(plan) -> bool:
+    """Which K2 instance alive_knn_search launches for this plan (mirrors launch_search in search_sm100.cu): CTA pairs at
+    d = 768 that visit at least two library tiles per unit keep half of their query block resident."""
+    return (plan.kernel == 0 and plan.ctas_per_unit == 2 and plan.d == 768 and plan.tiles_per_segment >= 2
+            and os.environ.get("ALIVE_KNN_RESIDENT", "1") != "0")
+
+
+def _settle(seconds: float = 2.0):
+    """The standalone K1/K4 measurements ("a kernel timed alone", burst HBM peak) follow a loop that holds the GPU at its
+    power cap; the SM clock stays low for a while after it (1.3 instead of 1.9 GHz) and these latency-sensitive
+    kernels then measure 20-25 % lower.  Let the clocks come back before timing them."""
+    import torch
+    torch.cuda.synchronize()
+    time.sleep(seconds)
+
+
 def gather_roofline(env, lib, src_dev, B, T):
     """K4 alone (north_star: "fraction of HBM bandwidth for the gather"): the standalone gather-mean kernel on this
     step's own neighbour indices; in the pipeline the same arithmetic is fused into finish_kernel.  Algorithmic
@@ -643,7 +664,8 @@ def gather_roofline(env, lib, src_dev, B, T):
     q_view = M.PackedFrames(n=rows, d=D, raw=ws[off[0]: off[0] + rows * D * 4].view(torch.float32).view(rows, D),
                             norms=ws[off[1]: off[1] + rows * 4].view(torch.float32), packed=None, err=None, stats=None)
     g_out = torch.empty((rows, D), dtype=torch.float32, device=dev)
-    for _ in range(3):
+    _settle()
+    for _ in range(10):
         M.gather_mean(lib, g_idx.view(rows, K), q_view, 0.0, g_out)
     torch.cuda.synchronize()
     ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -694,8 +716,10 @@ def pack_roofline(env):
     px_rows = px.t().contiguous()
     reps = 10
 
+    _settle()
+
     def timed(dst, view):
-        for _ in range(2):
+        for _ in range(4):
             M.pack_into(dst, 0, view)
         torch.cuda.synchronize()
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
