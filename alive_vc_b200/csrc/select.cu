@@ -542,24 +542,19 @@ finish_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand
 // Also moves the query's second plane into the compact matrix.
 constexpr int kPrepThreads = 256;
 constexpr int kPrepR = 64;                 // screened entries rescored for the bound (<= 2x with ties)
-__global__ void __launch_bounds__(kPrepThreads)
-refine_prep_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int lists, int k,
-                   const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
-                   const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
-                   const float* __restrict__ q_err2, const uint16_t* __restrict__ q_lo, uint16_t* __restrict__ qc_lo,
-                   const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
-                   const unsigned int* __restrict__ lib_stats, int d, float* __restrict__ c_cut) {
+__device__ __forceinline__ void
+refine_prep_slot(int item, int slot, const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int lists, int k,
+                 const int* __restrict__ fb_list, int t_item, int rows_c,
+                 const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
+                 const float* __restrict__ q_err2, const uint16_t* __restrict__ q_lo, uint16_t* __restrict__ qc_lo,
+                 const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
+                 const unsigned int* __restrict__ lib_stats, int d, float* __restrict__ c_cut) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qh = reinterpret_cast<float*>(smem_raw);            // [d] normalised query
   int* sel = reinterpret_cast<int*>(qh + d);                 // [2 * kPrepR] frame indices
   float* csc = reinterpret_cast<float*>(sel + 2 * kPrepR);   // [2 * kPrepR] exact scores
   __shared__ int s_cnt[kPrepThreads / 32];
   __shared__ int s_total;
-  pdl_wait();
-  pdl_launch_dependents();
-  const int item = blockIdx.y, slot = blockIdx.x;
-  const int n_fb = min(fb_count[item], rows_c);
-  if (slot >= n_fb) return;
   const int q = fb_list[static_cast<size_t>(item) * t_item + slot];
   const size_t cslot = static_cast<size_t>(item) * rows_c + slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -651,33 +646,42 @@ refine_prep_kernel(const float* __restrict__ cand_score, const int* __restrict__
   }
 }
 
+// grid = (min(rows_c, a few CTAs per SM), items): the CTAs stride over the item's live slots, so the usual case - no
+// uncertified query at all - costs a launch of ~1k CTAs that exit at once instead of rows_c = 8192 of them (35 us).
+__global__ void __launch_bounds__(kPrepThreads)
+refine_prep_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int lists, int k,
+                   const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
+                   const float* __restrict__ q_raw, const float* __restrict__ q_norm, const float* __restrict__ q_err,
+                   const float* __restrict__ q_err2, const uint16_t* __restrict__ q_lo, uint16_t* __restrict__ qc_lo,
+                   const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
+                   const unsigned int* __restrict__ lib_stats, int d, float* __restrict__ c_cut) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int item = blockIdx.y;
+  const int n_fb = min(fb_count[item], rows_c);
+  for (int slot = blockIdx.x; slot < n_fb; slot += gridDim.x) {
+    refine_prep_slot(item, slot, cand_score, cand_idx, lists, k, fb_list, t_item, rows_c, q_raw, q_norm, q_err, q_err2, q_lo,
+                     qc_lo, lib_raw, lib_norm, lib_stats, d, c_cut);
+    __syncthreads();                       // the next slot reuses the shared-memory buffers
+  }
+}
+
 // One CTA per fallback slot: exact rescoring of the collected candidates, top-k, gather.  blockIdx.y = item.
 constexpr int kCollectThreads = 512;
-__global__ void __launch_bounds__(kCollectThreads, 2)
-collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
-                       const int* __restrict__ c_cnt, const int* __restrict__ c_idx, int c_cap, int k,
-                       const float* __restrict__ q_raw, const float* __restrict__ q_norm,
-                       const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n_total, int d,
-                       float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
-                       long long* __restrict__ top_idx, long long idx_base, int* __restrict__ fb2_list,
-                       int* __restrict__ fb2_count) {
+__device__ __forceinline__ void
+collect_rescore_slot(int item, int slot, const int* __restrict__ fb_list, int rows_c,
+                     const int* __restrict__ c_cnt, const int* __restrict__ c_idx, int c_cap, int k,
+                     const float* __restrict__ q_raw, const float* __restrict__ q_norm,
+                     const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n_total, int d,
+                     float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
+                     long long* __restrict__ top_idx, long long idx_base, int* __restrict__ fb2_list,
+                     int* __restrict__ fb2_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qh = reinterpret_cast<float*>(smem_raw);          // [d]
   float* csc = qh + d;                                      // [c_cap]
   __shared__ long long s_top[kMaxK];
   constexpr int kWarps = kCollectThreads / 32;
-  pdl_wait();
-  pdl_launch_dependents();
-  const int item = blockIdx.y;
-  fb_list += static_cast<size_t>(item) * t_item;
-  fb2_list += static_cast<size_t>(item) * t_item;
-  const int n_fb = fb_count[item];
-  const int slot = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // uncertified queries beyond the compact matrix go straight to the exhaustive scan
-  if (threadIdx.x == 0)
-    for (int sl = rows_c + slot; sl < n_fb; sl += gridDim.x) fb2_list[atomicAdd(&fb2_count[item], 1)] = fb_list[sl];
-  if (slot >= n_fb || slot >= rows_c) return;
   const int q = fb_list[slot];
   const size_t cslot = static_cast<size_t>(item) * rows_c + slot;
   const int cnt = c_cnt[cslot];
@@ -728,6 +732,32 @@ collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ 
   __syncthreads();
   gather_mean_row(lib_raw, n_total, d, s_top, 0, k, q_raw + static_cast<size_t>(q) * d, a0 != 0.f || !isfinite(qn), a1, a0,
                   out + static_cast<size_t>(q) * d, threadIdx.x, kCollectThreads);
+}
+
+// grid = (min(rows_c, a few CTAs per SM), items); the CTAs stride over the item's live slots (see refine_prep_kernel)
+__global__ void __launch_bounds__(kCollectThreads, 2)
+collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
+                       const int* __restrict__ c_cnt, const int* __restrict__ c_idx, int c_cap, int k,
+                       const float* __restrict__ q_raw, const float* __restrict__ q_norm,
+                       const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n_total, int d,
+                       float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
+                       long long* __restrict__ top_idx, long long idx_base, int* __restrict__ fb2_list,
+                       int* __restrict__ fb2_count) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int item = blockIdx.y;
+  fb_list += static_cast<size_t>(item) * t_item;
+  fb2_list += static_cast<size_t>(item) * t_item;
+  const int n_fb = fb_count[item];
+  // uncertified queries beyond the compact matrix go straight to the exhaustive scan
+  if (threadIdx.x == 0)
+    for (int sl = rows_c + blockIdx.x; sl < n_fb; sl += gridDim.x) fb2_list[atomicAdd(&fb2_count[item], 1)] = fb_list[sl];
+  const int live = min(n_fb, rows_c);
+  for (int slot = blockIdx.x; slot < live; slot += gridDim.x) {
+    collect_rescore_slot(item, slot, fb_list, rows_c, c_cnt, c_idx, c_cap, k, q_raw, q_norm, lib_raw, lib_norm, n_total, d, a1,
+                         a0, out, top_score, top_idx, idx_base, fb2_list, fb2_count);
+    __syncthreads();                       // the next slot reuses the shared-memory buffers
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1402,7 +1432,7 @@ int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_
   }
   ALIVE_REQUIRE(smem <= 64 * 1024, "collect pass: candidate buffer too large for shared memory");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c, items), dim3(kCollectThreads), smem, as_stream(stream),
+  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c < 1024 ? rows_c : 1024, items), dim3(kCollectThreads), smem, as_stream(stream),
                                   fb_list, fb_count, t_item, rows_c, c_cnt, c_idx, c_cap, k, q_raw, q_norm, lib_raw, lib_norm,
                                   static_cast<long long>(n_total), d, a1, alpha, out, top_score,
                                   reinterpret_cast<long long*>(top_idx), static_cast<long long>(idx_base), fb2_list,
@@ -1420,7 +1450,7 @@ int refine_prep_impl(const float* cand_score, const int32_t* cand_idx, int32_t l
                 "collect pass (refine): NULL argument");
   ALIVE_REQUIRE(d % 8 == 0 && k >= 1 && k <= kListLen, "collect pass (refine): bad sizes");
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(2 * kPrepR) * 8;
-  ALIVE_CHECK_CUDA(launch_chained(refine_prep_kernel, dim3(rows_c, items), dim3(kPrepThreads), smem, as_stream(stream),
+  ALIVE_CHECK_CUDA(launch_chained(refine_prep_kernel, dim3(rows_c < 1024 ? rows_c : 1024, items), dim3(kPrepThreads), smem, as_stream(stream),
                                   cand_score, cand_idx, lists, k, fb_list, fb_count, t_item, rows_c, q_raw, q_norm, q_err,
                                   q_err2, q_lo, qc_lo, lib_raw, lib_norm, lib_stats, d, c_cut));
   return 0;
