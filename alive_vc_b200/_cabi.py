@@ -31,7 +31,7 @@ EXPORTS = [
     "alive_knn_mean_blend", "alive_knn_scatter_grad", "alive_knn_match_layout", "alive_knn_match",
     "alive_knn_finish", "alive_knn_gather_mean_peers", "alive_knn_ipc_export", "alive_knn_ipc_open",
     "alive_knn_ipc_close", "alive_knn_merge_records", "alive_knn_merge_gather", "alive_knn_match_packed",
-    "alive_knn_graph_launch", "alive_knn_event_wait",
+    "alive_knn_graph_launch", "alive_knn_event_wait", "alive_knn_arm_notify", "alive_knn_flag_wait",
 ]
 
 
@@ -182,6 +182,10 @@ def _declare(lib):
     lib.alive_knn_graph_launch.argtypes = [_vp, _vp, _vp]
     lib.alive_knn_event_wait.restype = ctypes.c_int
     lib.alive_knn_event_wait.argtypes = [_vp]
+    lib.alive_knn_arm_notify.restype = ctypes.c_int
+    lib.alive_knn_arm_notify.argtypes = [_vp, _vp]
+    lib.alive_knn_flag_wait.restype = ctypes.c_int
+    lib.alive_knn_flag_wait.argtypes = [_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), _i64]
     lib.alive_knn_match_packed.restype = ctypes.c_int
     lib.alive_knn_match_packed.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(Library), _i32, _f32,
                                            _i32, _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]
@@ -204,7 +208,7 @@ def load():
             # ALIVE_KNN_LIB: an instrumented build of the same sources (tests/gpu_tools/finish_phases.py)
             lib = ctypes.CDLL(os.environ.get("ALIVE_KNN_LIB") or LIB_PATH)
             _declare(lib)
-            if lib.alive_knn_abi_version() != 6:
+            if lib.alive_knn_abi_version() != 7:
                 raise RuntimeError("libalive_knn.so ABI version mismatch")
             _lib = lib
     return _lib

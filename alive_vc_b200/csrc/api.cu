@@ -3,6 +3,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
+
 #include "common.cuh"
 
 namespace alive {
@@ -32,6 +35,37 @@ constexpr int kOffQRaw = 0, kOffQNorm = 1, kOffQPacked = 2, kOffQErr = 3, kOffCa
               kOffQLo = 12, kOffQErr2 = 13, kOffSlots = 14;
 
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// Early result notification (alive_knn_arm_notify): a one-thread kernel right behind finish_kernel tells the HOST that
+// the certified results are complete - and whether any query was left to the fallback chain - so a latency-critical
+// caller whose results land in mapped host memory need not wait for the (normally idle) fallback launches behind it.
+struct NotifyArm {
+  unsigned long long* host_flag = nullptr;
+  unsigned long long* dev_counter = nullptr;
+};
+thread_local NotifyArm g_notify;
+
+__global__ void notify_kernel(const int32_t* __restrict__ fb_count, int items, unsigned long long* dev_counter,
+                              volatile unsigned long long* host_flag) {
+  pdl_wait();                              // finish_kernel (or the exact scan) has completed, its writes are performed
+  pdl_launch_dependents();
+  int any = 0;
+  if (fb_count != nullptr)
+    for (int i = 0; i < items; ++i) any |= fb_count[i];
+  const unsigned long long c = *dev_counter + 1ull;
+  *dev_counter = c;
+  __threadfence_system();                  // results (mapped host memory) before the flag, system-wide
+  *host_flag = (c << 1) | (any != 0 ? 1ull : 0ull);
+}
+
+int launch_notify(const int32_t* fb_count, int items, alive_stream_t stream) {
+  if (g_notify.host_flag == nullptr) return 0;
+  const NotifyArm arm = g_notify;
+  g_notify = NotifyArm{};                  // one shot
+  ALIVE_CHECK_CUDA(launch_chained(notify_kernel, dim3(1), dim3(1), 0, as_stream(stream), fb_count, items, arm.dev_counter,
+                                  static_cast<volatile unsigned long long*>(arm.host_flag)));
+  return 0;
+}
 
 int resolve_mode(int mode, int64_t n, int d, int k) {
   (void)n;   // the screen handles any library size; the exact scan is for k > 8 or odd feature dims
@@ -263,6 +297,8 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
                      lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
                      fb_count, items, 0, q_packed, qc, c_cut, c_cnt, cl.on ? cl.rows_c : 0, stream);
     if (rc) return rc;
+    rc = launch_notify(fb_count, items, stream);
+    if (rc) return rc;
     const int32_t* x_list = fb_list;
     const int32_t* x_count = fb_count;
     if (cl.on) {
@@ -298,6 +334,8 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);
+    if (rc) return rc;
+    rc = launch_notify(nullptr, items, stream);          // exact mode: everything is final here
     if (rc) return rc;
   }
   return 0;
@@ -363,6 +401,36 @@ extern "C" int alive_knn_graph_launch(void* graph_exec, alive_stream_t stream, v
   ALIVE_CHECK_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
   if (event) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), as_stream(stream)));
   return 0;
+}
+
+extern "C" int alive_knn_arm_notify(void* host_flag, void* dev_counter) {
+  using namespace alive;
+  ALIVE_REQUIRE((host_flag == nullptr) == (dev_counter == nullptr), "alive_knn_arm_notify: both pointers or none");
+  ALIVE_REQUIRE((reinterpret_cast<uintptr_t>(host_flag) & 7) == 0 && (reinterpret_cast<uintptr_t>(dev_counter) & 7) == 0,
+                "alive_knn_arm_notify: 8-byte aligned words");
+  g_notify.host_flag = static_cast<unsigned long long*>(host_flag);
+  g_notify.dev_counter = static_cast<unsigned long long*>(dev_counter);
+  return 0;
+}
+
+extern "C" int alive_knn_flag_wait(const void* host_flag, uint64_t last, uint64_t* value_out, int64_t timeout_us) {
+  using namespace alive;
+  ALIVE_REQUIRE(host_flag != nullptr && value_out != nullptr, "alive_knn_flag_wait: NULL argument");
+  const volatile uint64_t* f = static_cast<const volatile uint64_t*>(host_flag);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spin = 0;; ++spin) {
+    const uint64_t v = *f;
+    if (v != last) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      *value_out = v;
+      return 0;
+    }
+    if ((spin & 0x3ff) == 0x3ff && timeout_us > 0 &&
+        std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > timeout_us) {
+      set_error("alive_knn_flag_wait: no notification within %lld us", static_cast<long long>(timeout_us));
+      return -3;
+    }
+  }
 }
 
 extern "C" int alive_knn_event_wait(void* event) {

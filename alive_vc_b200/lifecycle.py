@@ -11,6 +11,8 @@ All device work goes through the C ABI (include/alive_knn.h); torch is used for 
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import matching as M
@@ -255,8 +257,12 @@ class HostStreamingMatcher:
     Match only (no `pre` / `post`): the graph is one H2D copy node and the match pipeline; the last kernel of the
     pipeline writes the matched frames (contiguous 3 KB rows) straight into the pinned result over PCIe (unified
     addressing: zero_copy="out", the default) - no D2H copy node; a call is a memcpy into the pinned buffer, one
-    graph launch and one event wait.  zero_copy="both" also lets K1 read the chunk in place (no H2D node either),
+    graph launch and one wait.  zero_copy="both" also lets K1 read the chunk in place (no H2D node either),
     zero_copy=False keeps both copy nodes.  `hm.src_host` may be filled in place (`hm.run()`).
+    With zero_copy="out"/"both" the wait is an EARLY one (`early=True`, alive_knn_arm_notify): a one-thread kernel
+    right behind the finish kernel raises a flag in pinned host memory once the certified rows have landed there, and
+    `result()` returns on that flag instead of waiting for the six (normally idle) fallback launches queued behind it;
+    if the flag says some query was uncertified, `result()` waits for the whole graph as before.
 
     With caller modules - `pre` (e.g. the content encoder, realtime_inference.py:150: spectrogram chunk -> [B, D, T]
     features) and/or `post` (e.g. the decoder, :166) - the SAME graph holds  H2D copy -> pre -> match -> post -> D2H copy
@@ -267,7 +273,7 @@ class HostStreamingMatcher:
 
     def __init__(self, lib: M.PackedFrames, T: int, k: int = 4, alpha: float = 0.0, batch: int = 1,
                  mode: str = "auto", variant: int = 0, r_max: int = M.DEFAULT_R_MAX, pre=None, post=None,
-                 in_shape=None, in_dtype=torch.float32, zero_copy="out"):
+                 in_shape=None, in_dtype=torch.float32, zero_copy="out", early=True):
         dev = lib.device
         self.lib, self.pre, self.post = lib, pre, post
         if zero_copy not in (False, "out", "both"):
@@ -275,6 +281,11 @@ class HostStreamingMatcher:
         # zero-copy needs the match to be the first / last thing in the graph
         self.zc_in = zero_copy == "both" and pre is None
         self.zc_out = zero_copy in ("out", "both") and post is None
+        self.early = bool(early) and self.zc_out
+        self._c = M._cabi.load()
+        self.flag_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._flag_ptr = self.flag_host.data_ptr()
+        self._flag_last = ctypes.c_uint64(0)
         self.inner = M.StreamingMatcher(lib, T, k, alpha, batch, mode, variant, r_max, use_graph=False)
         in_shape = tuple(in_shape) if in_shape is not None else (batch, lib.d, T)
         self.src_host = torch.zeros(in_shape, dtype=in_dtype).pin_memory()
@@ -282,6 +293,7 @@ class HostStreamingMatcher:
         self.done = torch.cuda.Event()
         with torch.cuda.device(dev):
             self.in_dev = None if self.zc_in else torch.zeros(in_shape, dtype=in_dtype, device=dev)
+            self.flag_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
             if post is None:
                 self.out_host = torch.zeros((batch, T, lib.d), dtype=torch.float32).pin_memory()
             else:
@@ -299,7 +311,8 @@ class HostStreamingMatcher:
             # per-chunk host work = two C calls (alive_knn_graph_launch: cudaGraphLaunch + cudaEventRecord;
             # alive_knn_event_wait: poll) on raw handles
             self.done.record(self.stream)
-            self._c = M._cabi.load()
+            self.stream.synchronize()
+            self._flag_last.value = int(self.flag_host[0].item()) & 0xFFFFFFFFFFFFFFFF      # after the warm-up run
             self._exec = self.graph.raw_cuda_graph_exec()
             self._stream_h, self._event_h, self._dev_index = self.stream.cuda_stream, self.done.cuda_event, dev.index
 
@@ -314,6 +327,8 @@ class HostStreamingMatcher:
             if feat.dtype != torch.float32:
                 feat = feat.float()                             # (fp16 encoder output under autocast)
             src = feat
+        if self.early:
+            M._cabi.check(self._c.alive_knn_arm_notify(self._flag_ptr, self.flag_ctr.data_ptr()), "alive_knn_arm_notify")
         M.run_match(src, self.lib, i.k, i.alpha, i.mode, i.variant, i.r_max, workspace=i.workspace,
                     out=out if out is not None else i.out, top_idx=i.top_idx, top_score=i.top_score, host_buffers=True)
         if self.post is not None:
@@ -344,6 +359,12 @@ class HostStreamingMatcher:
         self.run()
 
     def result(self) -> torch.Tensor:
+        if self.early:
+            rc = self._c.alive_knn_flag_wait(self._flag_ptr, self._flag_last, ctypes.byref(self._flag_last), 10_000_000)
+            if rc:
+                M._cabi.check(rc, "alive_knn_flag_wait")
+            if not (self._flag_last.value & 1):
+                return self.out_host.transpose(1, 2)            # every row certified: the result is complete
         rc = self._c.alive_knn_event_wait(self._event_h)
         if rc:
             M._cabi.check(rc, "alive_knn_event_wait")

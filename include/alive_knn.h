@@ -33,7 +33,7 @@ extern "C" {
 
 typedef void* alive_stream_t; /* cudaStream_t */
 
-#define ALIVE_KNN_ABI_VERSION 6
+#define ALIVE_KNN_ABI_VERSION 7
 #define ALIVE_KNN_LIST_LEN 8      /* entries kept per running top list in the fused kernel */
 #define ALIVE_KNN_TILE_M 128      /* query frames per tensor-core tile   */
 #define ALIVE_KNN_TILE_N 256      /* library frames per tensor-core tile */
@@ -307,6 +307,18 @@ int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16
  * an event by polling (a blocking wait's wake-up costs more than a ~100 us chunk can spare). */
 int alive_knn_graph_launch(void* graph_exec, alive_stream_t stream, void* event);
 int alive_knn_event_wait(void* event);
+
+/* Early result notification for the same loop.  alive_knn_arm_notify(host_flag, dev_counter): the NEXT
+ * alive_knn_match / alive_knn_match_packed call of this thread (one shot; typically made once, under graph capture)
+ * launches a one-thread kernel right behind its finish kernel that increments *dev_counter (8-byte device word) and
+ * stores (counter << 1) | any_uncertified to *host_flag (8-byte word in MAPPED pinned host memory), after a
+ * system-scope fence.  When the match writes its result rows into mapped host memory too, a host that sees the flag
+ * change with bit 0 clear has the complete result of the chunk and need not wait for the (idle) fallback launches
+ * still queued behind the finish kernel; bit 0 set = some query went to the fallback chain: wait for the stream.
+ * alive_knn_flag_wait spins on the host word until it differs from `last` (returns the new value; -3 on timeout,
+ * timeout_us <= 0 = no timeout).  NULL, NULL disarms. */
+int alive_knn_arm_notify(void* host_flag, void* dev_counter);
+int alive_knn_flag_wait(const void* host_flag, uint64_t last, uint64_t* value_out, int64_t timeout_us);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     assert sorted(_cabi.EXPORTS) == declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in alive_knn.h but not exported"
-    assert lib.alive_knn_abi_version() == 6
+    assert lib.alive_knn_abi_version() == 7
 
 
 def test_sass_is_blackwell_native():

@@ -290,6 +290,38 @@ def test_host_streaming_matcher_copy_modes(zero_copy):
     assert torch.equal(hm.result(), want.transpose(1, 2).cpu())
 
 
+@pytest.mark.parametrize("early", [True, False])
+def test_host_streaming_matcher_early_wait_and_fallback_chunks(early):
+    """zero_copy="out": `result()` returns on the flag the notify kernel raises behind finish_kernel (early=True) -
+    also when a chunk holds queries the screen cannot certify (duplicated library frames, a zero query): the flag then
+    carries the "uncertified" bit and result() waits for the whole graph, so the fallback chain's rows are there."""
+    rng = np.random.default_rng(28)
+    D, T, N = 768, 32, 30_000
+    ref = rng.standard_normal((1, D, N), dtype=np.float32)
+    ref[0, :, 1000:1040] = ref[0, :, 999:1000]            # 41 identical frames: the top-k of their query ties exactly
+    lib = A.pack_library(_cuda(ref))
+    hm = HostStreamingMatcher(lib, T, 4, 0.0, early=early)
+    assert hm.early == early
+    for it in range(6):
+        chunk = torch.from_numpy(rng.standard_normal((1, D, T), dtype=np.float32))
+        if it % 2 == 1:
+            chunk[0, :, 5] = torch.from_numpy(ref[0, :, 1010])      # uncertifiable: 41 exact ties
+            chunk[0, :, 9] = 0.0                                    # zero query: NaN similarities, exhaustive scan
+        out = hm(chunk)
+        want, w_idx, _ = A.match_packed(chunk.cuda(), lib, 4, 0.0)
+        if it % 2 == 1:
+            assert M.last_info.fallback_queries() >= 2
+            assert w_idx[0, 5].tolist() == [999, 1000, 1001, 1002]  # ties -> lowest indices (torch.topk on CPU, common.py:105)
+        got, ref_out = out.contiguous(), want.transpose(1, 2).cpu()
+        assert torch.equal(torch.nan_to_num(got, nan=123.0), torch.nan_to_num(ref_out, nan=123.0))
+    # many chunks back to back: every flag value is consumed exactly once
+    for it in range(50):
+        chunk = torch.from_numpy(rng.standard_normal((1, D, T), dtype=np.float32))
+        hm.submit(chunk)
+        want, _, _ = A.match_packed(chunk.cuda(), lib, 4, 0.0)
+        assert torch.equal(hm.result(), want.transpose(1, 2).cpu())
+
+
 def test_chunk_graph_with_encoder_and_decoder_modules():
     """realtime_inference.py:143-167 as ONE graph: H2D -> encoder (pre) -> match -> decoder (post) -> D2H, under
     fp16 autocast like the reference's `-fp16`; equals the same modules run eagerly around match_features."""
