@@ -226,7 +226,7 @@ def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
         "    x[128:192, 12] *= 1e-20\n"
         "    x[:, 13] *= torch.logspace(-30, 8, 768, device='cuda')\n"
         "    for tag, v in (('cm', x), ('rm', x.t().contiguous().t())):\n"
-        "        p = M.pack_frames(v)\n"
+        "        p = M.pack_frames(v, fmt='bf16')\n"
         "        h = hashlib.sha256()\n"
         "        for f in ('raw', 'norms', 'packed', 'lo'):\n"
         "            h.update(getattr(p, f).view(torch.uint8).cpu().numpy().tobytes())\n"
@@ -234,6 +234,11 @@ def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
         "        res[f'{tag}{n}_err'] = p.err.cpu().numpy()\n"
         "        res[f'{tag}{n}_err2_err'] = p.err2.cpu().numpy()\n"
         "        res[f'{tag}{n}_stats'] = p.stats.cpu().numpy()\n"
+        "        p1 = M.pack_frames(v, refine=False, fmt='bf16')       # one plane: the pipelined row-major kernel\n"
+        "        assert p1.lo is None\n"
+        "        for f in ('raw', 'norms', 'packed'):\n"
+        "            assert torch.equal(getattr(p1, f), getattr(p, f)), (tag, n, f)\n"
+        "        assert torch.equal(p1.err, p.err) and torch.equal(p1.stats[:2], p.stats[:2]), (tag, n)\n"
         "np.savez(sys.argv[1], **res)\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
