@@ -103,3 +103,41 @@ def _free_port():
 ])
 def test_sharded_match_equals_single_library(world, n_total, T, k, alpha, B):
     mp.spawn(_worker, args=(world, _free_port(), n_total, T, k, alpha, B), nprocs=world, join=True)
+
+
+def _worker_scattered(rank, world, port, n_total, T, k, alpha):
+    """scattered form: every rank passes its slice of the query frames and gets its slice of the result"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from alive_vc_b200.sharded import ShardedLibrary, shard_bounds
+        from oracle import knn_oracle as O
+        rng = np.random.default_rng(78)
+        src = rng.standard_normal((1, 768, T), dtype=np.float32)
+        ref = rng.standard_normal((1, 768, n_total), dtype=np.float32)
+        lo, hi = shard_bounds(n_total, world, rank)
+        q_lo, q_hi = shard_bounds(T, world, rank)
+        lib = ShardedLibrary(OracleBackend(ref[0][:, lo:hi], lo), hi - lo, lo, n_total)
+        mine = torch.from_numpy(np.ascontiguousarray(src[:, :, q_lo:q_hi]))
+        out, idx = lib.match(mine, k=k, alpha=alpha, return_indices=True, scattered=True, t_total=T)
+        want_out, want_idx, _ = O.match_features_np(src, ref, k, alpha, True)
+        assert tuple(out.shape) == (1, 768, q_hi - q_lo) and tuple(idx.shape) == (1, q_hi - q_lo, k)
+        assert np.array_equal(idx.numpy(), want_idx[:, q_lo:q_hi]), "scattered indices differ from the oracle"
+        assert np.array_equal(out.numpy(), want_out[:, :, q_lo:q_hi]), "scattered features are not bit-identical"
+        # a slice of the wrong length is refused before anything is exchanged
+        if q_hi - q_lo > 1:
+            with pytest.raises(RuntimeError, match="must pass its"):
+                lib.match(mine[:, :, 1:], k=k, alpha=alpha, scattered=True, t_total=T)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total,T,k,alpha", [
+    (2, 1001, 37, 4, 0.0),        # 19 + 18 query frames: the shorter slice is padded for the all-gather
+    (3, 300, 16, 4, 0.25),
+    (3, 10, 2, 4, 0.0),           # fewer query frames than ranks: one rank passes an empty slice
+])
+def test_sharded_scattered_match(world, n_total, T, k, alpha):
+    mp.spawn(_worker_scattered, args=(world, _free_port(), n_total, T, k, alpha), nprocs=world, join=True)
