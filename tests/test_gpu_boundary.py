@@ -125,14 +125,14 @@ def test_data_writes_and_explicit_invalidation():
         vl = A.VoiceLibrary(num_tokens=n_tok).cuda()
         assert (vl.tokens.numel() >= M.PACK_CACHE_MIN_ELEMENTS) == cached
         _, idx0 = vl.match(src, return_indices=True)
-        assert int(idx0[0, 0, 0]) != 7
-        vl.tokens.data[:, :, 7] = src[0, :, 0] * 3.0                     # frame 7 := a copy of query 0
+        j = next(i for i in range(n_tok) if i not in idx0[0, 0].tolist())   # a frame query 0 did NOT select
+        vl.tokens.data[:, :, j] = src[0, :, 0] * 3.0                     # frame j := a copy of query 0
         _, idx1 = vl.match(src, return_indices=True)
         if cached:
             assert torch.equal(idx1, idx0)                               # stale by design: the write was invisible ...
             vl.invalidate()                                              # ... until told
             _, idx1 = vl.match(src, return_indices=True)
-        assert int(idx1[0, 0, 0]) == 7
+        assert int(idx1[0, 0, 0]) == j
 
 
 def test_d_limit_is_checked_before_any_launch():
