@@ -24,3 +24,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_global_rngs(request):
+    """Every test starts from the same global RNG state (torch CPU + CUDA, numpy legacy), derived from its own id:
+    a test's random data must not depend on which tests ran before it in the process."""
+    import zlib
+    seed = zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF
+    try:
+        import numpy as np
+        np.random.seed(seed)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.manual_seed(seed)
+    except Exception:
+        pass
+    yield
