@@ -236,9 +236,9 @@ def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
         "        res[f'{tag}{n}_stats'] = p.stats.cpu().numpy()\n"
         "        p1 = M.pack_frames(v, refine=False, fmt='bf16')       # one plane: the pipelined row-major kernel\n"
         "        assert p1.lo is None\n"
-        "        for f in ('raw', 'norms', 'packed'):\n"
-        "            assert torch.equal(getattr(p1, f), getattr(p, f)), (tag, n, f)\n"
-        "        assert torch.equal(p1.err, p.err) and torch.equal(p1.stats[:2], p.stats[:2]), (tag, n)\n"
+        "        for f in ('raw', 'norms', 'packed', 'err'):              # bit patterns (the rows hold NaNs)\n"
+        "            assert torch.equal(getattr(p1, f).view(torch.uint8), getattr(p, f).view(torch.uint8)), (tag, n, f)\n"
+        "        assert torch.equal(p1.stats[:2], p.stats[:2]), (tag, n)\n"
         "np.savez(sys.argv[1], **res)\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
