@@ -58,10 +58,8 @@ __global__ void notify_kernel(const int32_t* __restrict__ fb_count, int items, u
   *host_flag = (c << 1) | (any != 0 ? 1ull : 0ull);
 }
 
-int launch_notify(const int32_t* fb_count, int items, alive_stream_t stream) {
-  if (g_notify.host_flag == nullptr) return 0;
-  const NotifyArm arm = g_notify;
-  g_notify = NotifyArm{};                  // one shot
+int launch_notify(const NotifyArm& arm, const int32_t* fb_count, int items, alive_stream_t stream) {
+  if (arm.host_flag == nullptr) return 0;
   ALIVE_CHECK_CUDA(launch_chained(notify_kernel, dim3(1), dim3(1), 0, as_stream(stream), fb_count, items, arm.dev_counter,
                                   static_cast<volatile unsigned long long*>(arm.host_flag)));
   return 0;
@@ -228,6 +226,9 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
                int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max, int32_t mode,
                int32_t num_sms, int32_t variant, void* workspace, size_t workspace_bytes, float* out, int64_t* top_idx,
                float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream) {
+  // the notification request belongs to THIS call, whether it gets as far as the launch or fails on the way
+  const NotifyArm notify = g_notify;
+  g_notify = NotifyArm{};
   ALIVE_REQUIRE((source || pq) && lib && workspace && top_idx && top_score, "alive_knn_match: NULL argument");
   ALIVE_REQUIRE(batch >= 1 && t >= 1, "alive_knn_match: empty query batch");
   ALIVE_REQUIRE(static_cast<int64_t>(batch) * t < (1ll << 31), "alive_knn_match: too many query frames");
@@ -297,7 +298,7 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
                      lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
                      fb_count, items, 0, q_packed, qc, c_cut, c_cnt, cl.on ? cl.rows_c : 0, stream);
     if (rc) return rc;
-    rc = launch_notify(fb_count, items, stream);
+    rc = launch_notify(notify, fb_count, items, stream);
     if (rc) return rc;
     const int32_t* x_list = fb_list;
     const int32_t* x_count = fb_count;
@@ -335,7 +336,7 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;
-    rc = launch_notify(nullptr, items, stream);          // exact mode: everything is final here
+    rc = launch_notify(notify, nullptr, items, stream);  // exact mode: everything is final here
     if (rc) return rc;
   }
   return 0;

@@ -329,8 +329,12 @@ class HostStreamingMatcher:
             src = feat
         if self.early:
             M._cabi.check(self._c.alive_knn_arm_notify(self._flag_ptr, self.flag_ctr.data_ptr()), "alive_knn_arm_notify")
-        M.run_match(src, self.lib, i.k, i.alpha, i.mode, i.variant, i.r_max, workspace=i.workspace,
-                    out=out if out is not None else i.out, top_idx=i.top_idx, top_score=i.top_score, host_buffers=True)
+        try:
+            M.run_match(src, self.lib, i.k, i.alpha, i.mode, i.variant, i.r_max, workspace=i.workspace,
+                        out=out if out is not None else i.out, top_idx=i.top_idx, top_score=i.top_score, host_buffers=True)
+        finally:
+            if self.early:                                      # (consumed by the call above unless it raised before it)
+                self._c.alive_knn_arm_notify(None, None)
         if self.post is not None:
             return self.post(i.out.transpose(1, 2))             # [B, D, T] view, as match_features returns it
         return None if out is not None else i.out
