@@ -81,6 +81,61 @@ def main():
     torch.cuda.synchronize()
     assert torch.equal(ib[1:2], i0) and torch.equal(ob[1:2], o0)
     print("ok pack variants", flush=True)
+    # round 2: the resident-query CTA-pair kernel (d = 768, >= 2 tiles per unit), both plane formats
+    for fmt in ("bf16", "fp16"):
+        refr = torch.randn(1, 768, 40_000, device="cuda", generator=g)
+        srcr = torch.randn(1, 768, 300, device="cuda", generator=g)
+        libr = A.pack_library(refr, fmt=fmt)
+        _, idx_s, _ = M.run_match(srcr, libr, 4, 0.0, mode="screen")
+        _, idx_e, _ = M.run_match(srcr, libr, 4, 0.0, mode="exact")
+        torch.cuda.synchronize()
+        assert torch.equal(idx_s, idx_e)
+    print("ok resident kernel", flush=True)
+    # one-plane row-major pack (the pipelined kernel), K4 warp kernel with and without the blend row
+    xr = torch.randn(9000, 768, device="cuda", generator=g)
+    p1 = M.pack_frames(xr.t(), refine=False, fmt="bf16")
+    p2 = M.pack_frames(xr.t(), refine=True, fmt="bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(p1.packed, p2.packed) and torch.equal(p1.norms, p2.norms) and p1.lo is None
+    for al in (0.0, 0.3):
+        o_a, i_a, _ = A.match_packed(srcr, p2, 4, al)
+        q_pf = M.pack_queries(srcr)
+        o_b = torch.empty((300, 768), device="cuda")
+        M.gather_mean(p2, i_a.view(300, 4), q_pf, al, o_b)
+        torch.cuda.synchronize()
+        assert torch.equal(o_b, o_a[0])
+    print("ok one-plane pack + gather", flush=True)
+    # sharded: two in-process ranks, records all-gathered through shared memory, fused merge + peer gather
+    import threading
+    from alive_vc_b200.sharded import ShardedLibrary, ThreadComm, shard_bounds
+    comms = ThreadComm.make(2)
+    refs = torch.randn(1, 768, 20_000, device="cuda", generator=g)
+    srcs = torch.randn(1, 768, 150, device="cuda", generator=g)
+    want, widx = A.match_features(srcs, refs, 4, 0.0, return_indices=True)
+    res = [None, None]
+
+    def rank_fn(r):
+        torch.cuda.set_device(0)
+        sh = ShardedLibrary.from_full(refs, comm=comms[r])
+        o, i = sh.match(srcs, 4, 0.0, return_indices=True)
+        res[r] = (o.clone(), i.clone())
+        torch.cuda.synchronize()
+        comms[r].barrier()          # a rank's shard must outlive every peer's gather
+    ths = [threading.Thread(target=rank_fn, args=(r,)) for r in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for r in range(2):
+        assert torch.equal(res[r][1], widx) and torch.equal(res[r][0], want)
+    print("ok sharded thread ranks", flush=True)
+    # realtime loop with host buffers: zero-copy result + early notification
+    from alive_vc_b200.lifecycle import HostStreamingMatcher
+    hm = HostStreamingMatcher(A.pack_library(refs), 24)
+    for _ in range(3):
+        ch = torch.randn(1, 768, 24)
+        got = hm(ch)
+        wantc, _, _ = A.match_packed(ch.cuda(), hm.lib, 4, 0.0)
+        assert torch.equal(got, wantc.transpose(1, 2).cpu())
+    print("ok host streaming (early notify)", flush=True)
     vl = A.VoiceLibrary(num_tokens=300).cuda()
     s = torch.randn(2, 768, 11, device="cuda", requires_grad=True)
     vl.match(s, alpha=0.5).sum().backward()
