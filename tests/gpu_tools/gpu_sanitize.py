@@ -52,7 +52,7 @@ def main():
             0.2 * torch.randn(768, 70_000, device="cuda", generator=g))[None]
     srcc = (cent[:, torch.randint(0, 40, (260,), device="cuda", generator=g)] +
             0.2 * torch.randn(768, 260, device="cuda", generator=g))[None]
-    libc = A.pack_library(refc)
+    libc = A.pack_library(refc, fmt="bf16")            # (the automatic format would certify it in fp16)
     _, idx_s, _ = M.run_match(srcc, libc, 4, 0.0, mode="screen")
     assert M.last_info.collect and M.last_info.fallback_queries() > 0
     torch.cuda.synchronize()
