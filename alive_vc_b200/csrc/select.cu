@@ -1365,7 +1365,8 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(r_max) * 16 + 16 +
                       (staged ? static_cast<size_t>(entries) * 8 : 0);
   // 0 = by batch size: 128 threads x 8 CTAs/SM keeps more queries in flight once the batch spans many
-  // waves (measured at T = 10k: 360 -> 286 us), 256 x 4 in between, 512 / 1024 threads when there are
+  // waves (measured at T = 10k: 360 -> 286 us; 64 x 16 from 32k queries: another 0.3 ms of 33.5 at T = 64k, nothing at
+  // 10k, slower at 1k), 256 x 4 in between, 512 / 1024 threads when there are
   // fewer queries than SMs can hold; ALIVE_KNN_FINISH_THREADS=128|256|512|1024 forces one
   static const int variant = getenv("ALIVE_KNN_FINISH_THREADS") ? atoi(getenv("ALIVE_KNN_FINISH_THREADS")) : 0;
   static PerDeviceOnce attr_once;
@@ -1373,6 +1374,7 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
     const int rc_attr = attr_once.run([]() -> int {
       ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
       ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
+      ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
       ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
       ALIVE_CHECK_CUDA((cudaFuncSetAttribute(finish_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)));
       return 0;
@@ -1391,10 +1393,11 @@ int finish_impl(const float* cand_score, const int32_t* cand_idx, int32_t t, int
                                   reinterpret_cast<long long*>(top_idx), sel_n, fb_list, fb_count, staged, t / items, cs))
   // a batch that does not fill the GPU is pure latency: give every query a whole SM's worth of warps
   // (one survivor frame per warp in flight -> the rescoring is a single DRAM round trip)
-  const int threads = variant == 128 || variant == 256 || variant == 512 || variant == 1024
+  const int threads = variant == 64 || variant == 128 || variant == 256 || variant == 512 || variant == 1024
                           ? variant
-                          : (t >= 4096 ? 128 : t > 296 ? 256 : t > 148 ? 512 : 1024);
-  if (threads == 128) ALIVE_LAUNCH_FINISH(128, 8);
+                          : (t >= 32768 ? 64 : t >= 4096 ? 128 : t > 296 ? 256 : t > 148 ? 512 : 1024);
+  if (threads == 64) ALIVE_LAUNCH_FINISH(64, 16);
+  else if (threads == 128) ALIVE_LAUNCH_FINISH(128, 8);
   else if (threads == 256) ALIVE_LAUNCH_FINISH(256, 4);
   else if (threads == 512) ALIVE_LAUNCH_FINISH(512, 2);
   else ALIVE_LAUNCH_FINISH(1024, 1);
