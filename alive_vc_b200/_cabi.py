@@ -22,6 +22,7 @@ NVCC_FLAGS = [
 ]
 
 # every symbol include/alive_knn.h declares
+MODE_DEFER_FALLBACK = 0x100      # ALIVE_KNN_MODE_DEFER_FALLBACK
 FORMAT_BF16, FORMAT_FP16 = 0, 1      # ALIVE_KNN_FORMAT_*
 
 EXPORTS = [
@@ -32,6 +33,7 @@ EXPORTS = [
     "alive_knn_finish", "alive_knn_gather_mean_peers", "alive_knn_ipc_export", "alive_knn_ipc_open",
     "alive_knn_ipc_close", "alive_knn_merge_records", "alive_knn_merge_gather", "alive_knn_match_packed",
     "alive_knn_graph_launch", "alive_knn_event_wait", "alive_knn_arm_notify", "alive_knn_flag_wait",
+    "alive_knn_match_fallback",
 ]
 
 
@@ -189,6 +191,8 @@ def _declare(lib):
     lib.alive_knn_match_packed.restype = ctypes.c_int
     lib.alive_knn_match_packed.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(Library), _i32, _f32,
                                            _i32, _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]
+    lib.alive_knn_match_fallback.restype = ctypes.c_int
+    lib.alive_knn_match_fallback.argtypes = list(lib.alive_knn_match_packed.argtypes)
     lib.alive_knn_match.restype = ctypes.c_int
     lib.alive_knn_match.argtypes = [_vp, _i32, _i32, _i64, _i64, _i64, ctypes.POINTER(Library), _i32, _f32, _i32,
                                     _i32, _i32, _i32, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]

@@ -190,7 +190,7 @@ struct PackedQueries {
 int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
                int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max, int32_t mode,
                int32_t num_sms, int32_t variant, void* workspace, size_t workspace_bytes, float* out, int64_t* top_idx,
-               float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream);
+               float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream, int phase = 0);
 }  // namespace
 }  // namespace alive
 
@@ -220,16 +220,38 @@ extern "C" int alive_knn_match_packed(const float* q_raw, const float* q_norm, c
                            workspace_bytes, out, top_idx, top_score, nullptr, nullptr, stream);
 }
 
+extern "C" int alive_knn_match_fallback(const float* q_raw, const float* q_norm, const uint16_t* q_packed,
+                                        const float* q_err, const uint16_t* q_lo, const float* q_err2, int32_t batch,
+                                        int32_t t, const alive_knn_library_t* lib, int32_t k, float alpha,
+                                        int32_t r_max, int32_t mode, int32_t num_sms, int32_t variant, void* workspace,
+                                        size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
+                                        alive_stream_t stream) {
+  if (q_raw == nullptr)   // the front half was alive_knn_match: its packed queries are in the workspace
+    return alive::match_impl(nullptr, nullptr, batch, t, 0, 0, 0, lib, k, alpha, r_max, mode, num_sms, variant, workspace,
+                             workspace_bytes, out, top_idx, top_score, nullptr, nullptr, stream, 2);
+  ALIVE_REQUIRE(q_norm && q_packed && q_err, "alive_knn_match_fallback: NULL argument");
+  ALIVE_REQUIRE((q_lo == nullptr) == (q_err2 == nullptr), "alive_knn_match_fallback: q_lo and q_err2 go together");
+  alive::PackedQueries pq{q_raw, q_norm, q_packed, q_err, q_lo, q_err2};
+  return alive::match_impl(nullptr, &pq, batch, t, 0, 0, 0, lib, k, alpha, r_max, mode, num_sms, variant, workspace,
+                           workspace_bytes, out, top_idx, top_score, nullptr, nullptr, stream, 2);
+}
+
 namespace alive {
 namespace {
 int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int32_t t, int64_t stride_b, int64_t stride_t,
                int64_t stride_d, const alive_knn_library_t* lib, int32_t k, float alpha, int32_t r_max, int32_t mode,
                int32_t num_sms, int32_t variant, void* workspace, size_t workspace_bytes, float* out, int64_t* top_idx,
-               float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream) {
+               float* top_score, void* ev_search_start, void* ev_search_stop, alive_stream_t stream, int phase) {
   // the notification request belongs to THIS call, whether it gets as far as the launch or fails on the way
   const NotifyArm notify = g_notify;
   g_notify = NotifyArm{};
-  ALIVE_REQUIRE((source || pq) && lib && workspace && top_idx && top_score, "alive_knn_match: NULL argument");
+  // phase 0: the whole chain; 1 (mode | ALIVE_KNN_MODE_DEFER_FALLBACK): pack, search, finish [, notify] only - the
+  // fallback chain for uncertified queries is left to a later alive_knn_match_fallback call on the same workspace;
+  // 2: that call (queries: the ones the front half packed into the workspace, or `pq`)
+  if (phase == 0 && (mode & ALIVE_KNN_MODE_DEFER_FALLBACK)) phase = 1;
+  mode &= ~ALIVE_KNN_MODE_DEFER_FALLBACK;
+  const bool run_front = phase != 2, run_back = phase != 1;
+  ALIVE_REQUIRE((source || pq || phase == 2) && lib && workspace && top_idx && top_score, "alive_knn_match: NULL argument");
   ALIVE_REQUIRE(batch >= 1 && t >= 1, "alive_knn_match: empty query batch");
   ALIVE_REQUIRE(static_cast<int64_t>(batch) * t < (1ll << 31), "alive_knn_match: too many query frames");
   ALIVE_REQUIRE(k >= 1 && k <= lib->n, "selected index k out of range");
@@ -271,7 +293,9 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws + off[kOffFbCount]);
   void* exact_ws = ws + off[kOffExact];
 
-  if (pq == nullptr) {
+  if (!run_front) {
+    // (the front half of an earlier call left the packed queries, the lists and the counters in the workspace)
+  } else if (pq == nullptr) {
     // all batch items in ONE pack launch, which also zeroes the fallback counters (no separate memset node)
     rc = pack_impl(source, rows, d, stride_t, stride_d, reinterpret_cast<float*>(ws + off[kOffQRaw]),
                    reinterpret_cast<float*>(ws + off[kOffQNorm]), reinterpret_cast<uint16_t*>(ws + off[kOffQPacked]),
@@ -283,23 +307,26 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
     ALIVE_CHECK_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t) * 2 * items, as_stream(stream)));
   }
   if (mode == 1) {
-    if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
-    // the search may start behind the (still running) query pack: see search_impl
-    static const bool pdl = !(getenv("ALIVE_KNN_PDL") && atoi(getenv("ALIVE_KNN_PDL")) == 0);
-    rc = search_impl(q_packed, lib->packed, &plan, cand_score, cand_idx, (pdl && !ev_search_start && pq == nullptr) ? 1 : 0, stream);
-    if (rc) return rc;
-    if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
     char* ca = ws + off[kOffCollect];
     uint16_t* qc = cl.on ? reinterpret_cast<uint16_t*>(ca + cl.qc) : nullptr;
     float* c_cut = cl.on ? reinterpret_cast<float*>(ca + cl.cut) : nullptr;
     int32_t* c_cnt = cl.on ? reinterpret_cast<int32_t*>(ca + cl.cnt) : nullptr;
-    rc = finish_impl(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
-                     lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
-                     fb_count, items, 0, q_packed, qc, c_cut, c_cnt, cl.on ? cl.rows_c : 0, stream);
-    if (rc) return rc;
-    rc = launch_notify(notify, fb_count, items, stream);
-    if (rc) return rc;
+    if (run_front) {
+      if (ev_search_start) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_start), as_stream(stream)));
+      // the search may start behind the (still running) query pack: see search_impl
+      static const bool pdl = !(getenv("ALIVE_KNN_PDL") && atoi(getenv("ALIVE_KNN_PDL")) == 0);
+      rc = search_impl(q_packed, lib->packed, &plan, cand_score, cand_idx, (pdl && !ev_search_start && pq == nullptr) ? 1 : 0, stream);
+      if (rc) return rc;
+      if (ev_search_stop) ALIVE_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_search_stop), as_stream(stream)));
+      rc = finish_impl(cand_score, cand_idx, rows, plan.lists, k, q_raw, q_norm, q_err, lib->raw, lib->norms,
+                       lib->stats, lib->n * items, d, r_max, lib->row_base, alpha, out, top_score, top_idx, sel_n, fb_list,
+                       fb_count, items, 0, q_packed, qc, c_cut, c_cnt, cl.on ? cl.rows_c : 0, stream);
+      if (rc) return rc;
+      rc = launch_notify(notify, fb_count, items, stream);
+      if (rc) return rc;
+    }
+    if (!run_back) return 0;
     const int32_t* x_list = fb_list;
     const int32_t* x_count = fb_count;
     if (cl.on) {
@@ -331,7 +358,7 @@ int match_impl(const float* source, const PackedQueries* pq, int32_t batch, int3
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, x_list, x_count, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);
     if (rc) return rc;
-  } else {
+  } else if (run_front) {       // exact mode has no fallback half: the front half is everything
     ALIVE_REQUIRE(out == nullptr || lib->row_base == 0, "alive_knn_match: gather needs an unsharded library (row_base == 0)");
     rc = alive_knn_exact(q_raw, q_norm, rows, lib->raw, lib->norms, lib->n, d, k, nullptr, nullptr, lib->row_base,
                          exact_ws, top_score, top_idx, alpha, out, items, stream);

@@ -261,8 +261,9 @@ class HostStreamingMatcher:
     zero_copy=False keeps both copy nodes.  `hm.src_host` may be filled in place (`hm.run()`).
     With zero_copy="out"/"both" the wait is an EARLY one (`early=True`, alive_knn_arm_notify): a one-thread kernel
     right behind the finish kernel raises a flag in pinned host memory once the certified rows have landed there, and
-    `result()` returns on that flag instead of waiting for the six (normally idle) fallback launches queued behind it;
-    if the flag says some query was uncertified, `result()` waits for the whole graph as before.
+    `result()` returns on that flag.  The six launches of the fallback chain (idle whenever every query certifies) are
+    not part of the graph at all (ALIVE_KNN_MODE_DEFER_FALLBACK); if the flag says some query was uncertified,
+    `result()` enqueues them (alive_knn_match_fallback) and waits for the stream.
 
     With caller modules - `pre` (e.g. the content encoder, realtime_inference.py:150: spectrogram chunk -> [B, D, T]
     features) and/or `post` (e.g. the decoder, :166) - the SAME graph holds  H2D copy -> pre -> match -> post -> D2H copy
@@ -331,7 +332,8 @@ class HostStreamingMatcher:
             M._cabi.check(self._c.alive_knn_arm_notify(self._flag_ptr, self.flag_ctr.data_ptr()), "alive_knn_arm_notify")
         try:
             M.run_match(src, self.lib, i.k, i.alpha, i.mode, i.variant, i.r_max, workspace=i.workspace,
-                        out=out if out is not None else i.out, top_idx=i.top_idx, top_score=i.top_score, host_buffers=True)
+                        out=out if out is not None else i.out, top_idx=i.top_idx, top_score=i.top_score, host_buffers=True,
+                        defer_fallback=self.early)
         finally:
             if self.early:                                      # (consumed by the call above unless it raised before it)
                 self._c.alive_knn_arm_notify(None, None)
@@ -369,6 +371,12 @@ class HostStreamingMatcher:
                 M._cabi.check(rc, "alive_knn_flag_wait")
             if not (self._flag_last.value & 1):
                 return self.out_host.transpose(1, 2)            # every row certified: the result is complete
+            # some query was left uncertified: the fallback chain was not part of the graph - enqueue it now
+            i = self.inner
+            with torch.cuda.device(self.lib.device), torch.cuda.stream(self.stream):
+                M.run_match_fallback(i.src.shape[0], i.src.shape[2], self.lib, i.k, i.alpha, i.mode, i.variant, i.r_max, i.workspace,
+                                     self.out_host, i.top_idx, i.top_score)
+                self.done.record(self.stream)
         rc = self._c.alive_knn_event_wait(self._event_h)
         if rc:
             M._cabi.check(rc, "alive_knn_event_wait")

@@ -614,13 +614,16 @@ def _layout(rows: int, lib: PackedFrames, k: int, r_max: int, mode: int, variant
 
 def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0, mode: str = "auto",
               variant: int = 0, r_max: int = DEFAULT_R_MAX, want_out: bool = True, workspace=None,
-              out=None, top_idx=None, top_score=None, info_sink: Optional[dict] = None, host_buffers: bool = False):
+              out=None, top_idx=None, top_score=None, info_sink: Optional[dict] = None, host_buffers: bool = False,
+              defer_fallback: bool = False):
     """The whole path in ONE C call (alive_knn_match): pack the B*T query frames of `source`
     [B,D,T] (any strides, float32, CUDA), search, certify, rescore, exact-scan the uncertified,
     gather+mean+blend.  Returns (out [B,T,D] or None, top_idx [B,T,k] int64, top_score [B,T,k]).
     `info_sink` (a dict) receives the workspace and its layout offsets (q_raw at offsets[0], q_norm at [1]).
     `host_buffers`: `source` (and a given `out`) may be PINNED HOST tensors - the kernels read / write them in place
-    over PCIe (unified addressing; HostStreamingMatcher's zero-copy chunk path); everything else lives on lib.device."""
+    over PCIe (unified addressing; HostStreamingMatcher's zero-copy chunk path); everything else lives on lib.device.
+    `defer_fallback`: enqueue pack -> search -> finish only (ALIVE_KNN_MODE_DEFER_FALLBACK); the caller must learn whether
+    a query was left uncertified (alive_knn_arm_notify) and then call run_match_fallback with the same arguments."""
     global last_info
     c = _cabi.load()
     B, D, T = source.shape
@@ -666,13 +669,16 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
             ev1.record()
             search_events.append((ev0, ev1))
         rc = c.alive_knn_match(source.data_ptr(), B, T, source.stride(0), source.stride(2), source.stride(1),
-                               ctypes.byref(lib.handle()), k, float(alpha), r_max, m, _num_sms(dev), variant,
+                               ctypes.byref(lib.handle()), k, float(alpha), r_max,
+                               m | (_cabi.MODE_DEFER_FALLBACK if defer_fallback else 0), _num_sms(dev), variant,
                                workspace.data_ptr(), workspace.numel(), out.data_ptr() if want_out else None,
                                top_idx.data_ptr(), top_score.data_ptr(),
                                ev0.cuda_event if ev0 is not None else None,
                                ev1.cuda_event if ev1 is not None else None, _stream_ptr(dev))
     _cabi.check(rc, "alive_knn_match")
     n_launch = 1 + ((_collect_launches(lib.lo is not None) if off[7] > off[6] else 4) if m == 1 else 2)
+    if defer_fallback and m == 1:
+        n_launch = 3                                     # pack, search, finish
     _count(n_launch)
     last_info = SearchInfo(mode="screen" if m == 1 else "exact",
                            fb_count=workspace[off[9]:off[9] + 4 * lib.items].view(torch.int32),
@@ -685,6 +691,27 @@ def run_match(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float 
     if info_sink is not None:          # callers on several threads cannot rely on the module-level last_info
         info_sink["workspace"], info_sink["offsets"] = workspace, off
     return (out if want_out else None), top_idx, top_score
+
+
+def run_match_fallback(B: int, T: int, lib: PackedFrames, k: int, alpha: float, mode: str, variant: int, r_max: int,
+                       workspace: torch.Tensor, out, top_idx: torch.Tensor, top_score: torch.Tensor):
+    """The second half of a run_match(..., defer_fallback=True) call: the fallback chain for the queries its finish
+    kernel could not certify (alive_knn_match_fallback; same sizes, same workspace, same result buffers)."""
+    c = _cabi.load()
+    m = _MODES[mode]
+    if m == 0:
+        m = 2 if (k > LIST_LEN or lib.n_item < EXACT_BELOW_N or lib.d % 64 != 0) else 1
+    if m != 1:
+        return                      # the exact mode has no second half
+    dev = lib.device
+    with _on(dev):
+        rc = c.alive_knn_match_fallback(None, None, None, None, None, None, B, T, ctypes.byref(lib.handle()), k, float(alpha),
+                                        r_max, m, _num_sms(dev), variant, workspace.data_ptr(), workspace.numel(),
+                                        out.data_ptr() if out is not None else None, top_idx.data_ptr(),
+                                        top_score.data_ptr(), _stream_ptr(dev))
+    _cabi.check(rc, "alive_knn_match_fallback")
+    off = _layout(B * T, lib, k, r_max, m, variant, dev)
+    _count((_collect_launches(lib.lo is not None) if off[7] > off[6] else 4) - 2)
 
 
 def match_packed(source: torch.Tensor, lib: PackedFrames, k: int = 4, alpha: float = 0.0,

@@ -302,6 +302,20 @@ int alive_knn_match_packed(const float* q_raw, const float* q_norm, const uint16
                            size_t workspace_bytes, float* out, int64_t* top_idx, float* top_score,
                            alive_stream_t stream);
 
+/* Deferred fallback (the realtime loop again): with ALIVE_KNN_MODE_DEFER_FALLBACK or-ed into `mode`,
+ * alive_knn_match / alive_knn_match_packed enqueue only pack -> search -> finish (-> the notify kernel, if armed):
+ * the six launches of the fallback chain, idle whenever every query certifies, are NOT enqueued.  A caller that learns
+ * (alive_knn_arm_notify's flag, bit 0) that some query was left uncertified enqueues them afterwards with
+ * alive_knn_match_fallback - same arguments and SAME workspace as the front half; q_* = NULL when the front half was
+ * alive_knn_match (its packed queries are in the workspace), else the packed queries again.  Results are identical to
+ * the one-call form.  Without a notification there is no way to know: do not defer. */
+#define ALIVE_KNN_MODE_DEFER_FALLBACK 0x100
+int alive_knn_match_fallback(const float* q_raw, const float* q_norm, const uint16_t* q_packed, const float* q_err,
+                             const uint16_t* q_lo, const float* q_err2, int32_t batch, int32_t t,
+                             const alive_knn_library_t* lib_host, int32_t k, float alpha, int32_t r_max, int32_t mode,
+                             int32_t num_sms, int32_t variant, void* workspace, size_t workspace_bytes, float* out,
+                             int64_t* top_idx, float* top_score, alive_stream_t stream);
+
 /* Chunk-loop runtime (realtime_inference.py:130-191; host-side, no kernels): launch an instantiated CUDA graph
  * (cudaGraphExec_t) on `stream` and record `event` (cudaEvent_t, nullable) behind it - one call per chunk; wait for
  * an event by polling (a blocking wait's wake-up costs more than a ~100 us chunk can spare). */

@@ -386,3 +386,28 @@ def test_producer_side_pack_is_bit_identical():
     out, idx, _ = A.match_packed_queries(q, libs, 4, 0.0, batch=2)
     w_out, w_idx, _ = M.run_match(rows.transpose(1, 2), libs, 4, 0.0)
     assert torch.equal(idx, w_idx) and torch.equal(out, w_out)
+
+
+@pytest.mark.parametrize("T,N", [(300, 70_000), (40, 9_000)])
+def test_deferred_fallback_equals_one_call(T, N):
+    """ALIVE_KNN_MODE_DEFER_FALLBACK + alive_knn_match_fallback (the two halves HostStreamingMatcher uses) give exactly
+    what the one-call pipeline gives - with the collect pass (T*N >= 2^24) and without - on a clustered library where
+    every query is uncertified, plus a zero query (no usable cut: exhaustive scan)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cent = torch.randn(768, 30, device="cuda", generator=g)
+    ref = (cent[:, torch.randint(0, 30, (N,), device="cuda", generator=g)] +
+           0.2 * torch.randn(768, N, device="cuda", generator=g))[None]
+    src = (cent[:, torch.randint(0, 30, (T,), device="cuda", generator=g)] +
+           0.2 * torch.randn(768, T, device="cuda", generator=g))[None].contiguous()
+    src[0, :, 3] = 0.0
+    lib = A.pack_library(ref, fmt="bf16")
+    out1, idx1, sc1 = M.run_match(src, lib, 4, 0.25, mode="screen")
+    n_fb = M.last_info.fallback_queries()
+    assert n_fb >= T // 2
+    info = {}
+    out2, idx2, sc2 = M.run_match(src, lib, 4, 0.25, mode="screen", defer_fallback=True, info_sink=info)
+    assert M.last_info.launches == 3 and M.last_info.fallback_queries() == n_fb
+    M.run_match_fallback(1, T, lib, 4, 0.25, "screen", 0, M.DEFAULT_R_MAX, info["workspace"], out2, idx2, sc2)
+    torch.cuda.synchronize()
+    assert torch.equal(idx1, idx2) and torch.equal(sc1.view(torch.int32), sc2.view(torch.int32))
+    assert torch.equal(out1.view(torch.int32), out2.view(torch.int32))
