@@ -502,9 +502,9 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
 
 // Row-major input (a producer's [n, D]: stride_d == 1, 16-byte aligned rows, d % 4 == 0): nothing to
 // transpose - one warp per frame, the 3 KB row lives in registers between the norm and the division.
-constexpr int kRmMaxV = 12;                         // float4 per lane: d <= 1536
-template <bool kHalf>
-__global__ void __launch_bounds__(kPackThreads)
+constexpr int kRmMaxV = 12;                         // float4 per lane: d <= 1536 (kV = 6: d <= 768, half the registers)
+template <bool kHalf, int kV>
+__global__ void __launch_bounds__(kPackThreads, kV <= 6 ? 4 : 3)
 pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, float* __restrict__ raw,
                float* __restrict__ norms, uint16_t* __restrict__ packed, float* __restrict__ err,
                unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
@@ -520,15 +520,15 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
   const int d4 = d >> 2;
   const float4* src = reinterpret_cast<const float4*>(frame_ptr(x, fm, row));
   float4* dst_raw = reinterpret_cast<float4*>(raw + row * d);
-  float4 v[kRmMaxV];
+  float4 v[kV];
 #pragma unroll
-  for (int i = 0; i < kRmMaxV; ++i) {
+  for (int i = 0; i < kV; ++i) {
     const int q = lane + 32 * i;
     v[i] = (q < d4) ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   double ss = 0.0;
 #pragma unroll
-  for (int i = 0; i < kRmMaxV; ++i) {
+  for (int i = 0; i < kV; ++i) {
     const int q = lane + 32 * i;
     if (q < d4) {
       dst_raw[q] = v[i];
@@ -546,7 +546,7 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
   uint2* dst_pk = reinterpret_cast<uint2*>(packed + row * d);
   uint2* dst_lo = rf.lo ? reinterpret_cast<uint2*>(rf.lo + row * d) : nullptr;
 #pragma unroll
-  for (int i = 0; i < kRmMaxV; ++i) {
+  for (int i = 0; i < kV; ++i) {
     const int q = lane + 32 * i;
     if (q < d4) {
       const float xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -583,103 +583,6 @@ pack_rm_kernel(const float* __restrict__ x, long long n, int d, const FrameMap f
   finite = __all_sync(0xffffffffu, finite);
   if (lane == 0) finish_frame(row, nrm, e2, e22, finite, norms, err, rf, &cta_stats);
   }  // row < n
-  __syncthreads();
-  cta_stats_publish(&cta_stats, stats);
-}
-
-// The same for d <= 768, persistent and software-pipelined: a warp requests the row of its NEXT frame before it
-// finishes the current one, so every resident warp always has 3 KB of reads in flight (the kernel above alternates
-// between a load phase and an arithmetic/store phase per warp).  Used for frames packed WITHOUT the second plane.
-// Identical arithmetic per frame, frames visited in another order (the statistics are order-independent maxima).
-constexpr int kRmStreamV = 6;                       // float4 per lane: d <= 768
-template <bool kHalf>
-__global__ void __launch_bounds__(kPackThreads, 3)
-pack_rm_stream_kernel(const float* __restrict__ x, long long n, int d, const FrameMap fm, float* __restrict__ raw,
-                      float* __restrict__ norms, uint16_t* __restrict__ packed, float* __restrict__ err,
-                      unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
-  pdl_launch_dependents();
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < n_zero; i += kPackThreads) zero_words[i] = 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ CtaStats cta_stats;
-  cta_stats_init(&cta_stats);
-  __syncthreads();
-  const int d4 = d >> 2;
-  const long long stride = static_cast<long long>(gridDim.x) * (kPackThreads / 32);
-  long long row = static_cast<long long>(blockIdx.x) * (kPackThreads / 32) + warp;
-  float4 v[kRmStreamV], nx[kRmStreamV];
-  auto load_row = [&](float4 (&dst)[kRmStreamV], long long r) {
-    const float4* src = reinterpret_cast<const float4*>(frame_ptr(x, fm, r));
-#pragma unroll
-    for (int i = 0; i < kRmStreamV; ++i) {
-      const int q = lane + 32 * i;
-      dst[i] = (q < d4) ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  if (row < n) load_row(v, row);
-  for (; row < n; row += stride) {
-    const long long next = row + stride;
-    if (next < n) load_row(nx, next);               // in flight while this frame is finished
-    float4* dst_raw = reinterpret_cast<float4*>(raw + row * d);
-    double ss = 0.0;
-#pragma unroll
-    for (int i = 0; i < kRmStreamV; ++i) {
-      const int q = lane + 32 * i;
-      if (q < d4) {
-        dst_raw[q] = v[i];
-        ss += static_cast<double>(v[i].x) * static_cast<double>(v[i].x);
-        ss += static_cast<double>(v[i].y) * static_cast<double>(v[i].y);
-        ss += static_cast<double>(v[i].z) * static_cast<double>(v[i].z);
-        ss += static_cast<double>(v[i].w) * static_cast<double>(v[i].w);
-      }
-    }
-    const float nrm = static_cast<float>(sqrt(warp_sum_f64(ss)));
-    const bool tame = norm_is_tame(nrm);
-    const float rinv = tame ? __frcp_rn(nrm) : 0.f;
-    bool finite = true;
-    float e2 = 0.f, e22 = 0.f;
-    uint2* dst_pk = reinterpret_cast<uint2*>(packed + row * d);
-    uint2* dst_lo = rf.lo ? reinterpret_cast<uint2*>(rf.lo + row * d) : nullptr;
-#pragma unroll
-    for (int i = 0; i < kRmStreamV; ++i) {
-      const int q = lane + 32 * i;
-      if (q < d4) {
-        const float xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-        unsigned short hb[4], lb[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float a;
-          if (tame) {
-            a = div_by_norm(xs[c], nrm, rinv);
-          } else {
-            a = __fdiv_rn(xs[c], nrm);
-            finite = finite && isfinite(a);
-          }
-          hb[c] = Plane<kHalf>::one(a);
-          const float fh = Plane<kHalf>::val(hb[c]);
-          const float da = fh - a;
-          e2 = fmaf(da, da, e2);
-          float r2nd;
-          lb[c] = split_lo<kHalf>(a, fh, &r2nd);
-          e22 = fmaf(r2nd, r2nd, e22);
-        }
-        dst_pk[q] = make_uint2(static_cast<unsigned>(hb[0]) | (static_cast<unsigned>(hb[1]) << 16),
-                               static_cast<unsigned>(hb[2]) | (static_cast<unsigned>(hb[3]) << 16));
-        if (dst_lo)
-          dst_lo[q] = make_uint2(static_cast<unsigned>(lb[0]) | (static_cast<unsigned>(lb[1]) << 16),
-                                 static_cast<unsigned>(lb[2]) | (static_cast<unsigned>(lb[3]) << 16));
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-      e22 += __shfl_xor_sync(0xffffffffu, e22, o);
-    }
-    finite = __all_sync(0xffffffffu, finite);
-    if (lane == 0) finish_frame(row, nrm, e2, e22, finite, norms, err, rf, &cta_stats);
-#pragma unroll
-    for (int i = 0; i < kRmStreamV; ++i) v[i] = nx[i];
-  }
   __syncthreads();
   cta_stats_publish(&cta_stats, stats);
 }
@@ -797,21 +700,17 @@ int pack_dispatch(const float* x, int64_t n, int32_t d, const FrameMap& fm, bool
   const bool x16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   const bool out16 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(pk) & 7) == 0;
   if (fast && n > 512 && stride_d == 1 && d % 4 == 0 && stride_n % 4 == 0 && (uniform || stride_b % 4 == 0) && x16 && out16) {
-    // Which row-major kernel (measured, 250k frames, fraction of the HBM peak): with the second plane the plain
-    // warp-per-frame kernel wins (0.874 vs 0.833-0.851 for the pipelined one), without it the pipelined one does
-    // (0.838 vs 0.778).  ALIVE_KNN_PACK_STREAM=0 / 1 force one or the other for A/B runs.
-    static const int stream_env = getenv("ALIVE_KNN_PACK_STREAM") ? atoi(getenv("ALIVE_KNN_PACK_STREAM")) : -1;
-    const bool stream_rm = stream_env < 0 ? rf.lo == nullptr : stream_env != 0;
-    if (stream_rm && d <= 4 * 32 * kRmStreamV && n >= 8192) {
-      int dev = 0, sms = 148;
-      ALIVE_CHECK_CUDA(cudaGetDevice(&dev));
-      ALIVE_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const long long want = (n + 7) / 8, grid = static_cast<long long>(sms) * 3;
-      pack_rm_stream_kernel<kHalf><<<static_cast<unsigned>(want < grid ? want : grid), kPackThreads, 0, stream>>>(
-          x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
-    } else {
-      pack_rm_kernel<kHalf><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, stream>>>(
-          x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
+    // d <= 768 runs the instance with half the row registers (60 instead of 80-92): four CTAs per SM instead of three
+    // took this kernel from 0.87 to 1.0 of the measured copy peak (0.78 -> 0.96 without the second plane); a persistent
+    // software-pipelined variant (next row requested before the current one is finished) was measured before that
+    // and is gone: 0.82-0.85, it needs the registers of two rows
+    {
+      if (d <= 4 * 32 * 6)
+        pack_rm_kernel<kHalf, 6><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, stream>>>(
+            x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
+      else
+        pack_rm_kernel<kHalf, kRmMaxV><<<static_cast<unsigned>((n + 7) / 8), kPackThreads, 0, stream>>>(
+            x, n, d, fm, raw, norms, pk, err, stats, zero_words, n_zero, rf);
     }
   } else if (fast && uniform && n > 8192 && stride_n == 1 && stride_d % 4 == 0 && x16) {
     const size_t smem = static_cast<size_t>(d) * kCmLd * sizeof(float);

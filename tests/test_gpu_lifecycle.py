@@ -234,7 +234,7 @@ def test_fast_pack_kernels_equal_the_generic_kernel(tmp_path):
         "        res[f'{tag}{n}_err'] = p.err.cpu().numpy()\n"
         "        res[f'{tag}{n}_err2_err'] = p.err2.cpu().numpy()\n"
         "        res[f'{tag}{n}_stats'] = p.stats.cpu().numpy()\n"
-        "        p1 = M.pack_frames(v, refine=False, fmt='bf16')       # one plane: the pipelined row-major kernel\n"
+        "        p1 = M.pack_frames(v, refine=False, fmt='bf16')       # one plane\n"
         "        assert p1.lo is None\n"
         "        for f in ('raw', 'norms', 'packed', 'err'):              # bit patterns (the rows hold NaNs)\n"
         "            assert torch.equal(getattr(p1, f).view(torch.uint8), getattr(p, f).view(torch.uint8)), (tag, n, f)\n"
