@@ -411,3 +411,29 @@ def test_deferred_fallback_equals_one_call(T, N):
     torch.cuda.synchronize()
     assert torch.equal(idx1, idx2) and torch.equal(sc1.view(torch.int32), sc2.view(torch.int32))
     assert torch.equal(out1.view(torch.int32), out2.view(torch.int32))
+
+
+def test_host_streaming_matcher_deferred_collect_pass():
+    """The deferred fallback chain of the realtime loop on a library large enough for the collect pass (T*N >= 2^24):
+    clustered bf16 planes leave every query of a chunk uncertified, result() enqueues refine-prep -> collect search ->
+    collect-rescore -> exact scan behind the graph and returns what the one-call pipeline returns."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    N, T = 600_000, 32
+    cent = torch.randn(768, 200, device="cuda", generator=g)
+    ref = (cent[:, torch.randint(0, 200, (N,), device="cuda", generator=g)] +
+           0.2 * torch.randn(768, N, device="cuda", generator=g))[None]
+    lib = A.pack_library(ref, fmt="bf16")
+    del ref
+    hm = HostStreamingMatcher(lib, T, 4, 0.0)
+    assert hm.early
+    for it in range(4):
+        if it % 2 == 0:        # a clustered chunk: nothing certifies
+            chunk = (cent[:, torch.randint(0, 200, (T,), device="cuda", generator=g)] +
+                     0.2 * torch.randn(768, T, device="cuda", generator=g))[None].cpu()
+        else:                  # an ordinary chunk: everything certifies, no fallback is enqueued
+            chunk = torch.randn(1, 768, T, generator=torch.Generator().manual_seed(it))
+        out = hm(chunk)
+        want, _, _ = A.match_packed(chunk.cuda(), lib, 4, 0.0)
+        fb = M.last_info.fallback_queries()
+        assert (fb > 0) == (it % 2 == 0) and M.last_info.collect
+        assert torch.equal(out.contiguous(), want.transpose(1, 2).cpu())
