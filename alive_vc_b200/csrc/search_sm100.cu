@@ -382,6 +382,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     return (live + kBlockM * kCtas - 1) / (kBlockM * kCtas);
   };
   if constexpr (kCollect) {
+    pdl_launch_dependents();                 // (before the wait: an idle fallback chain drains without launch gaps)
     pdl_wait();
     int any = 0;
     for (int i = 0; i < p.items; ++i) any |= p.c_active[i];

@@ -646,8 +646,8 @@ refine_prep_slot(int item, int slot, const float* __restrict__ cand_score, const
   }
 }
 
-// grid = (min(rows_c, a few CTAs per SM), items): the CTAs stride over the item's live slots, so the usual case - no
-// uncertified query at all - costs a launch of ~1k CTAs that exit at once instead of rows_c = 8192 of them (35 us).
+// grid = (min(rows_c, one wave of CTAs), items): the CTAs stride over the item's live slots, so the usual case - no
+// uncertified query at all - costs a launch of a few hundred CTAs that exit at once instead of rows_c = 8192 of them.
 __global__ void __launch_bounds__(kPrepThreads)
 refine_prep_kernel(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int lists, int k,
                    const int* __restrict__ fb_list, const int* __restrict__ fb_count, int t_item, int rows_c,
@@ -655,8 +655,8 @@ refine_prep_kernel(const float* __restrict__ cand_score, const int* __restrict__
                    const float* __restrict__ q_err2, const uint16_t* __restrict__ q_lo, uint16_t* __restrict__ qc_lo,
                    const float* __restrict__ lib_raw, const float* __restrict__ lib_norm,
                    const unsigned int* __restrict__ lib_stats, int d, float* __restrict__ c_cut) {
-  pdl_wait();
   pdl_launch_dependents();
+  pdl_wait();
   const int item = blockIdx.y;
   const int n_fb = min(fb_count[item], rows_c);
   for (int slot = blockIdx.x; slot < n_fb; slot += gridDim.x) {
@@ -743,8 +743,8 @@ collect_rescore_kernel(const int* __restrict__ fb_list, const int* __restrict__ 
                        float a1, float a0, float* __restrict__ out, float* __restrict__ top_score,
                        long long* __restrict__ top_idx, long long idx_base, int* __restrict__ fb2_list,
                        int* __restrict__ fb2_count) {
-  pdl_wait();
   pdl_launch_dependents();
+  pdl_wait();
   const int item = blockIdx.y;
   fb_list += static_cast<size_t>(item) * t_item;
   fb2_list += static_cast<size_t>(item) * t_item;
@@ -782,8 +782,8 @@ exact_partial_kernel(const float* __restrict__ q_raw, const float* __restrict__ 
                      float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item, int few) {
   // blockIdx.y = item: its queries are q_list[item][..] (or [item*t_item, (item+1)*t_item) when no
   // list is given) and its frames are rows [item*n, (item+1)*n) of lib_raw; t = queries PER ITEM
-  pdl_wait();
   pdl_launch_dependents();
+  pdl_wait();
   const int item = blockIdx.y;
   if (q_list) q_list += static_cast<size_t>(item) * t_item;
   if (q_count) q_count += item;
@@ -988,8 +988,8 @@ exact_rows_kernel(const float* __restrict__ q_raw, const float* __restrict__ q_n
                   const float* __restrict__ lib_raw, const float* __restrict__ lib_norm, long long n, int d,
                   int k, const int* __restrict__ q_list, const int* __restrict__ q_count, int splits,
                   float* __restrict__ part_score, long long* __restrict__ part_idx, int t_item, int few) {
-  pdl_wait();
   pdl_launch_dependents();
+  pdl_wait();
   const int item = blockIdx.y;
   if (q_list) q_list += static_cast<size_t>(item) * t_item;
   if (q_count) q_count += item;
@@ -1293,9 +1293,12 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
     if (rc_attr) return rc_attr;
   }
   ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
-  // at most ~4 waves of CTAs; the (group, split) items beyond that are reached grid-stride
+  // one wave of CTAs (the shared-memory tile allows one or two per SM); the (group, split) items beyond that are reached
+  // grid-stride.  One wave also lets an IDLE launch of this kernel trigger its dependents before its own wait returns
+  // (griddepcontrol.launch_dependents precedes the wait in the fallback-chain kernels), so an idle chain drains without
+  // launch gaps
   const size_t work = groups * static_cast<size_t>(splits);
-  size_t gx = (4 * 148 + items - 1) / items;
+  size_t gx = ((smem > 100 * 1024 ? 1 : 2) * 148 + items - 1) / items;
   if (gx > work) gx = work;
   if (gx < 1) gx = 1;
   dim3 pgrid(static_cast<unsigned>(gx), static_cast<unsigned>(items));
@@ -1308,7 +1311,7 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
                                   part_idx, t_item, few));
   if (few > 0) {
     const size_t rwork = static_cast<size_t>((few + kRQ - 1) / kRQ) * splits;
-    size_t rgx = (4 * 148 + items - 1) / items;
+    size_t rgx = ((rsmem > 100 * 1024 ? 1 : 2) * 148 + items - 1) / items;
     if (rgx > rwork) rgx = rwork;
     if (rgx < 1) rgx = 1;
     dim3 rgrid(static_cast<unsigned>(rgx), static_cast<unsigned>(items));
@@ -1435,7 +1438,7 @@ int collect_rescore_impl(const int32_t* fb_list, const int32_t* fb_count, int32_
   }
   ALIVE_REQUIRE(smem <= 64 * 1024, "collect pass: candidate buffer too large for shared memory");
   const float a1 = static_cast<float>(1.0 - static_cast<double>(alpha));
-  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c < 1024 ? rows_c : 1024, items), dim3(kCollectThreads), smem, as_stream(stream),
+  ALIVE_CHECK_CUDA(launch_chained(collect_rescore_kernel, dim3(rows_c < 296 ? rows_c : 296, items), dim3(kCollectThreads), smem, as_stream(stream),
                                   fb_list, fb_count, t_item, rows_c, c_cnt, c_idx, c_cap, k, q_raw, q_norm, lib_raw, lib_norm,
                                   static_cast<long long>(n_total), d, a1, alpha, out, top_score,
                                   reinterpret_cast<long long*>(top_idx), static_cast<long long>(idx_base), fb2_list,
@@ -1453,7 +1456,7 @@ int refine_prep_impl(const float* cand_score, const int32_t* cand_idx, int32_t l
                 "collect pass (refine): NULL argument");
   ALIVE_REQUIRE(d % 8 == 0 && k >= 1 && k <= kListLen, "collect pass (refine): bad sizes");
   const size_t smem = static_cast<size_t>(d) * 4 + static_cast<size_t>(2 * kPrepR) * 8;
-  ALIVE_CHECK_CUDA(launch_chained(refine_prep_kernel, dim3(rows_c < 1024 ? rows_c : 1024, items), dim3(kPrepThreads), smem, as_stream(stream),
+  ALIVE_CHECK_CUDA(launch_chained(refine_prep_kernel, dim3(rows_c < 592 ? rows_c : 592, items), dim3(kPrepThreads), smem, as_stream(stream),
                                   cand_score, cand_idx, lists, k, fb_list, fb_count, t_item, rows_c, q_raw, q_norm, q_err,
                                   q_err2, q_lo, qc_lo, lib_raw, lib_norm, lib_stats, d, c_cut));
   return 0;
