@@ -1293,12 +1293,13 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
     if (rc_attr) return rc_attr;
   }
   ALIVE_REQUIRE(smem <= 160 * 1024, "alive_knn_exact: shared memory budget exceeded");
-  // one wave of CTAs (the shared-memory tile allows one or two per SM); the (group, split) items beyond that are reached
-  // grid-stride.  One wave also lets an IDLE launch of this kernel trigger its dependents before its own wait returns
-  // (griddepcontrol.launch_dependents precedes the wait in the fallback-chain kernels), so an idle chain drains without
-  // launch gaps
+  // The (group, split) items are reached grid-stride.  Scanning EVERY query (no list: mode = exact, k > 8): ~4 waves of
+  // CTAs - one wave measured 22 % slower (13.2 instead of 10.8 ms at T = 1000 x N = 100k).  As the tail of the screened
+  // pipeline (a list of uncertified queries, normally empty): ONE wave, so that an idle launch releases its dependents
+  // before its own wait returns and the idle chain drains without launch gaps (cfg2 p50 76.4 -> 74.7 us).
   const size_t work = groups * static_cast<size_t>(splits);
-  size_t gx = ((smem > 100 * 1024 ? 1 : 2) * 148 + items - 1) / items;
+  const int waves = q_list != nullptr ? 1 : 4;
+  size_t gx = (static_cast<size_t>(waves) * 148 + items - 1) / items;
   if (gx > work) gx = work;
   if (gx < 1) gx = 1;
   dim3 pgrid(static_cast<unsigned>(gx), static_cast<unsigned>(items));
@@ -1311,7 +1312,7 @@ extern "C" int alive_knn_exact(const float* q_raw, const float* q_norm, int32_t 
                                   part_idx, t_item, few));
   if (few > 0) {
     const size_t rwork = static_cast<size_t>((few + kRQ - 1) / kRQ) * splits;
-    size_t rgx = ((rsmem > 100 * 1024 ? 1 : 2) * 148 + items - 1) / items;
+    size_t rgx = (static_cast<size_t>(waves) * 148 + items - 1) / items;
     if (rgx > rwork) rgx = rwork;
     if (rgx < 1) rgx = 1;
     dim3 rgrid(static_cast<unsigned>(rgx), static_cast<unsigned>(items));
