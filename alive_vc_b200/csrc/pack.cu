@@ -13,7 +13,8 @@
 //
 // HBM-bound: algorithmic bytes per frame = d*(4 read + 4 raw + 2 packed) + 8 = 7,688 B at d=768.
 // Kernels (dispatch in pack_impl at the end of this file; DESIGN.md §4 K1 has the measurements):
-//   pack_cm_kernel     channel-major libraries: 32-frame [d][36] tile filled by 16-byte cp.async
+//   pack_cm2_kernel    channel-major libraries: 32-frame [d][36] tile filled by 16-byte cp.async, 16 warps x 2 frames
+//   pack_cm_kernel     the same tile finished by 8 warps x 4 frames (A/B: ALIVE_KNN_PACK_CM2=0)
 //   pack_rm_kernel     row-major frames: one warp per frame, the row stays in registers
 //   pack_kernel<8/32>  any strides / alignment, batches of query items (FrameMap)
 //   pack_frame_kernel  <= 512 frames (a streaming chunk): one CTA per frame
@@ -273,22 +274,24 @@ __device__ __forceinline__ void cm_stage(float* tile, const float* __restrict__ 
                                          long long stride_d) {
   const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
   if (nf == 32) {
-    const int g4 = threadIdx.x & 7, jsub = threadIdx.x >> 3;          // 8 groups of 4 frames x 32 channel rows
+    const int g4 = threadIdx.x & 7, jsub = threadIdx.x >> 3;          // 8 groups of 4 frames x blockDim/8 channel rows
+    const int rows = static_cast<int>(blockDim.x >> 3);               // (32 with 256 threads, 64 with 512)
     const float* src = x + f0 + 4 * g4 + static_cast<long long>(jsub) * stride_d;
     unsigned dst = tile_s + 4u * (jsub * kCmLd + 4 * g4);
-    const long long src_step = 32 * stride_d;
+    const long long src_step = rows * stride_d;
+    const unsigned dst_step = 4u * rows * kCmLd;
 #pragma unroll 4
-    for (int j = jsub; j < d; j += 32) {
+    for (int j = jsub; j < d; j += rows) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       src += src_step;
-      dst += 4u * 32 * kCmLd;
+      dst += dst_step;
     }
   } else {
     // ragged last tile: element-wise, missing frames read as zeros
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool ok = lane < nf;
     const float* src = x + f0 + lane;
-    for (int j = warp; j < d; j += kPackThreads / 32) {
+    for (int j = warp; j < d; j += static_cast<int>(blockDim.x >> 5)) {
       if (ok)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + 4u * (j * kCmLd + lane)),
                      "l"(src + j * stride_d)
@@ -496,6 +499,160 @@ pack_cm_kernel(const float* __restrict__ x, long long n, int d, long long stride
     __syncthreads();                 // every warp is done with `cur` before it is refilled
     if (!kDouble && tn < n_tiles)
       cm_stage(tile, x, tn * 32, static_cast<int>(min(32ll, n - tn * 32)), d, stride_d);
+  }
+  cta_stats_publish(&cta_stats, stats);
+}
+
+// The same tile finished by SIXTEEN warps, two frames each (512-thread CTAs, two per SM, <= 64 registers): twice the
+// warps of cm_compute on the same shared-memory footprint.  The kernel above sits at 0.82 of the HBM peak with 24 % of
+// the warp slots in use (105 registers, two 8-warp CTAs per SM: its finishing pass is latency-bound) - the row-major
+// kernel showed what occupancy is worth in this family.  Identical arithmetic per element; a lane pair (2m, 2m+1)
+// exchanges its packed word so that the even lane stores frame 0 and the odd lane frame 1 as 32-bit words of two
+// adjacent channels.
+template <bool kHalf>
+__device__ __forceinline__ void cm_compute2(const float* tile, long long f0, int nf, int d, float* __restrict__ raw,
+                                            float* __restrict__ norms, uint16_t* __restrict__ packed,
+                                            float* __restrict__ err, const Refine& rf, CtaStats* cta_stats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fw = 2 * warp;
+  const long long row0 = f0 + fw;
+  const int nv = max(0, min(2, nf - fw));
+  if (nv == 0) return;
+  const float2* t2 = reinterpret_cast<const float2*>(tile) + warp;      // tile[j*36 + 2w] = t2[j*18]
+  double ss0 = 0.0, ss1 = 0.0;
+  {
+    float* r0 = raw + row0 * d;
+    const bool two = nv > 1;
+#pragma unroll 4
+    for (int j = lane; j < d; j += 32) {
+      const float2 v = t2[j * (kCmLd / 2)];
+      r0[j] = v.x;
+      if (two) r0[j + d] = v.y;
+      ss0 += static_cast<double>(v.x) * static_cast<double>(v.x);
+      ss1 += static_cast<double>(v.y) * static_cast<double>(v.y);
+    }
+  }
+  float nrm[2];
+  nrm[0] = static_cast<float>(sqrt(warp_sum_f64(ss0)));
+  nrm[1] = static_cast<float>(sqrt(warp_sum_f64(ss1)));
+  bool tame[2], finite[2];
+  float rinv[2], e2[2], e22[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    tame[c] = norm_is_tame(nrm[c]);
+    rinv[c] = tame[c] ? __frcp_rn(nrm[c]) : 0.f;
+    finite[c] = true;
+    e2[c] = 0.f;
+    e22[c] = 0.f;
+  }
+  if (tame[0] && tame[1]) {
+    const bool odd = (lane & 1) != 0;
+    const bool ok = (odd ? 1 : 0) < nv;                        // the frame this lane stores exists
+    unsigned* pk = reinterpret_cast<unsigned*>(packed + (row0 + (odd ? 1 : 0)) * d);
+    const bool want_lo = rf.lo != nullptr;
+    unsigned* lo = want_lo ? reinterpret_cast<unsigned*>(rf.lo + (row0 + (odd ? 1 : 0)) * d) : nullptr;
+    auto step = [&](int j, bool live) {
+      const float2 v = live ? t2[j * (kCmLd / 2)] : make_float2(1.f, 1.f);
+      const float xs[2] = {v.x, v.y};
+      float a[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float q0 = __fmul_rn(xs[c], rinv[c]);
+        const float e = __fmaf_rn(-q0, nrm[c], xs[c]);
+        a[c] = __fmaf_rn(e, rinv[c], q0);
+      }
+      if (!(fminf(fabsf(a[0]), fabsf(a[1])) >= 0x1p-40f)) {    // zeros / tiny quotients: rare, see cm_compute
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (xs[c] == 0.f) a[c] = __fmul_rn(xs[c], rinv[c]);
+          else if (!(fabsf(a[c]) >= 0x1p-40f)) a[c] = __fdiv_rn(xs[c], nrm[c]);
+        }
+      }
+      const unsigned w01 = Plane<kHalf>::pack2(a[0], a[1]);      // my channel: frame 0 low half, frame 1 high half
+      const float r0 = a[0] - Plane<kHalf>::lo_val(w01), r1 = a[1] - Plane<kHalf>::hi_val(w01);
+      if (live) {
+        e2[0] = fmaf(r0, r0, e2[0]);
+        e2[1] = fmaf(r1, r1, e2[1]);
+      }
+      const unsigned got = __shfl_xor_sync(0xffffffffu, w01, 1);   // the partner's channel, both frames
+      const int w = j >> 1;                                        // word index of the channel pair
+      // even lane: frame 0 of (my channel, partner's); odd lane: frame 1 of (partner's channel, mine)
+      if (ok && live) pk[w] = odd ? __byte_perm(got, w01, 0x7632) : __byte_perm(w01, got, 0x5410);
+      const unsigned l01 = Plane<kHalf>::pack2(r0, r1);
+      if (live) {
+        const float s0 = r0 - Plane<kHalf>::lo_val(l01), s1 = r1 - Plane<kHalf>::hi_val(l01);
+        e22[0] = fmaf(s0, s0, e22[0]);
+        e22[1] = fmaf(s1, s1, e22[1]);
+      }
+      if (want_lo) {                                               // (warp-uniform)
+        const unsigned lgot = __shfl_xor_sync(0xffffffffu, l01, 1);
+        if (ok && live) lo[w] = odd ? __byte_perm(lgot, l01, 0x7632) : __byte_perm(l01, lgot, 0x5410);
+      }
+    };
+    const int d_full = d & ~31;
+#pragma unroll 2
+    for (int j0 = 0; j0 < d_full; j0 += 32) step(j0 + lane, true);
+    if (d_full < d) step(d_full + lane, d_full + lane < d);
+  } else {
+    unsigned short* pk16 = reinterpret_cast<unsigned short*>(packed);
+    for (int j = lane; j < d; j += 32) {
+      const float2 v = t2[j * (kCmLd / 2)];
+      const float xs[2] = {v.x, v.y};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float a;
+        if (tame[c]) {
+          a = div_by_norm(xs[c], nrm[c], rinv[c]);
+        } else {
+          a = __fdiv_rn(xs[c], nrm[c]);
+          finite[c] = finite[c] && isfinite(a);
+        }
+        const unsigned short hb = Plane<kHalf>::one(a);
+        const float fh = Plane<kHalf>::val(hb);
+        const float da = fh - a;
+        e2[c] = fmaf(da, da, e2[c]);
+        if (c < nv) pk16[(row0 + c) * d + j] = hb;
+        float r2nd;
+        const unsigned short lb = split_lo<kHalf>(a, fh, &r2nd);
+        e22[c] = fmaf(r2nd, r2nd, e22[c]);
+        if (rf.lo && c < nv) rf.lo[(row0 + c) * d + j] = lb;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e2[c] += __shfl_xor_sync(0xffffffffu, e2[c], o);
+      e22[c] += __shfl_xor_sync(0xffffffffu, e22[c], o);
+    }
+    finite[c] = __all_sync(0xffffffffu, finite[c]);
+    if (lane == 0 && c < nv) finish_frame(row0 + c, nrm[c], e2[c], e22[c], finite[c], norms, err, rf, cta_stats);
+  }
+}
+
+constexpr int kCm2Threads = 512;
+template <bool kHalf>
+__global__ void __launch_bounds__(kCm2Threads, 2)
+pack_cm2_kernel(const float* __restrict__ x, long long n, int d, long long stride_d, float* __restrict__ raw,
+                float* __restrict__ norms, uint16_t* __restrict__ packed, float* __restrict__ err,
+                unsigned int* __restrict__ stats, int* __restrict__ zero_words, int n_zero, const Refine rf) {
+  extern __shared__ __align__(16) float tile[];   // [d][36]
+  __shared__ CtaStats cta_stats;
+  cta_stats_init(&cta_stats);
+  pdl_launch_dependents();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kCm2Threads) zero_words[i] = 0;
+  const long long n_tiles = (n + 31) / 32;
+  long long t = blockIdx.x;
+  if (t < n_tiles) cm_stage(tile, x, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, stride_d);
+  for (; t < n_tiles; t += gridDim.x) {
+    const long long tn = t + gridDim.x;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    cm_compute2<kHalf>(tile, t * 32, static_cast<int>(min(32ll, n - t * 32)), d, raw, norms, packed, err, rf, &cta_stats);
+    __syncthreads();                 // every warp is done with the tile before it is refilled
+    if (tn < n_tiles) cm_stage(tile, x, tn * 32, static_cast<int>(min(32ll, n - tn * 32)), d, stride_d);
   }
   cta_stats_publish(&cta_stats, stats);
 }
@@ -729,6 +886,19 @@ int pack_dispatch(const float* x, int64_t n, int32_t d, const FrameMap& fm, bool
       pack_cm_kernel<true, kHalf><<<static_cast<unsigned>(num_sms), kPackThreads, 2 * smem, stream>>>(
           x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
     } else {
+      // 16 warps per tile by default (0.84-0.89 of the HBM peak against 0.82-0.855 for the 8-warp kernel, same bits);
+      // ALIVE_KNN_PACK_CM2=0 runs the 8-warp kernel for A/B
+      static const int cm2 = getenv("ALIVE_KNN_PACK_CM2") ? atoi(getenv("ALIVE_KNN_PACK_CM2")) : 1;
+      if (cm2) {
+        static PerDeviceOnce cm2_once;
+        const int rc2 = cm2_once.run([]() -> int {
+          ALIVE_CHECK_CUDA((cudaFuncSetAttribute(pack_cm2_kernel<kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * kCmLd * 4)));
+          return 0;
+        });
+        if (rc2) return rc2;
+        pack_cm2_kernel<kHalf><<<static_cast<unsigned>(n_tiles), kCm2Threads, smem, stream>>>(
+            x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
+      } else
       pack_cm_kernel<false, kHalf><<<static_cast<unsigned>(n_tiles), kPackThreads, smem, stream>>>(
           x, n, d, stride_d, raw, norms, pk, err, stats, zero_words, n_zero, rf);
     }

@@ -737,7 +737,7 @@ def pack_roofline(env):
         ms_cm = timed(pdst, px)
         ms_rm = timed(pdst, px_rows.t())       # the same frames as a row-major producer hands them over (pack_rows)
         out[refine] = {"bytes_per_frame": per_frame,
-                       "channel_major": {"kernel": "pack_cm_kernel", "avg_kernel_ms": ms_cm,
+                       "channel_major": {"kernel": "pack_cm2_kernel", "avg_kernel_ms": ms_cm,
                                          "achieved": pn * per_frame / (ms_cm * 1e-3) / 1e9,
                                          "frac": pn * per_frame / (ms_cm * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                        "row_major": {"kernel": "pack_rm_kernel", "avg_kernel_ms": ms_rm,
@@ -759,7 +759,7 @@ def pack_roofline(env):
     del t_out, px, px_rows
     torch.cuda.empty_cache()
     main = out[True]
-    return {"bound": "hbm", "kernel": "pack_cm_kernel", "achieved": main["channel_major"]["achieved"],
+    return {"bound": "hbm", "kernel": "pack_cm2_kernel", "achieved": main["channel_major"]["achieved"],
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": main["channel_major"]["frac"],
             "avg_kernel_ms": main["channel_major"]["avg_kernel_ms"], "bytes_per_frame": main["bytes_per_frame"], "frames": pn,
             "row_major": main["row_major"],
