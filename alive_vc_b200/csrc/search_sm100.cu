@@ -1453,7 +1453,7 @@ extern "C" int alive_knn_plan_batched(int32_t items, int32_t t, int64_t n, int32
   ALIVE_REQUIRE(static_cast<long long>(items) * n < (1ll << 31) - 512 && static_cast<long long>(items) * t < (1ll << 31) - 512,
                 "alive_knn_plan: items * n and items * t must stay below 2^31");
   // d <= 1536: the exact scan behind every screened call (alive_knn_exact) and the certificate's accumulation
-  // slack (select.cu kAccumSlack) are both sized for at most 1536 channels - refuse here, before anything is launched
+  // slack (select.cu accum_slack) are both sized for at most 1536 channels - refuse here, before anything is launched
   ALIVE_REQUIRE(d >= 64 && d % 64 == 0 && d <= 1536, "alive_knn_plan: d must be a multiple of 64, <= 1536 (got %d)", d);
   ALIVE_REQUIRE(num_sms >= 2, "alive_knn_plan: num_sms must be >= 2");
   // default: the CTA-pair kernel (cta_group::2) once there is more than one 128-query tile - it
