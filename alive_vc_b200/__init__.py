@@ -10,11 +10,11 @@ include/alive_knn.h (alive_vc_b200/libalive_knn.so, sm_100a); there is no fallba
 from .matching import (PackedFrames, StreamingMatcher, clear_pack_cache, load_packed_library, save_packed_library, match_features, match_indices, match_packed,
                        match_packed_queries, pack_frames, pack_libraries, pack_library, pack_queries, search_topk)
 from .voice_library import VoiceLibrary
-from .lifecycle import HostStreamingMatcher, LibraryBuilder, RowsContentEncoder, match_rows, match_windows, pack_rows
+from .lifecycle import HostPipeline, HostStreamingMatcher, LibraryBuilder, RowsContentEncoder, match_rows, match_windows, pack_rows
 
 __all__ = [
     "match_features", "VoiceLibrary", "match_indices", "match_packed", "pack_library", "pack_libraries", "pack_frames",
     "search_topk", "PackedFrames", "clear_pack_cache", "StreamingMatcher",
     "save_packed_library", "load_packed_library", "LibraryBuilder", "match_windows", "HostStreamingMatcher",
-    "match_rows", "pack_rows", "match_packed_queries", "pack_queries", "RowsContentEncoder",
+    "match_rows", "pack_rows", "match_packed_queries", "pack_queries", "RowsContentEncoder", "HostPipeline",
 ]

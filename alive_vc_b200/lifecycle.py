@@ -387,6 +387,71 @@ class HostStreamingMatcher:
         return self.result()
 
 
+class HostPipeline:
+    """Throughput path with HOST buffers (offline batch conversion: features arrive from the host utterance after
+    utterance, results go back): every step is  host -> device copy, match, device -> host copy  of one [B, D, T] batch,
+    and the copies of neighbouring steps overlap the match - double-buffered device staging, the copies on two side
+    streams, the matches back to back on the caller's stream.
+
+        hp = HostPipeline(lib, B, T)
+        for src_host, out_host in batches:         # pinned [B, D, T] in, pinned [B, T, D] out
+            hp.step(src_host, out_host)            # returns at once
+        hp.drain()                                 # every out_host is complete
+
+    `out_host[b]` receives the contiguous [T, D] block the kernels write (match_features' result is its transpose).
+    Results are those of match_packed on the same frames."""
+
+    def __init__(self, lib: M.PackedFrames, B: int, T: int, k: int = 4, alpha: float = 0.0, mode: str = "auto",
+                 variant: int = 0, r_max: int = M.DEFAULT_R_MAX, depth: int = 2):
+        dev = lib.device
+        self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max, self.depth = lib, k, float(alpha), mode, variant, r_max, depth
+        with torch.cuda.device(dev):
+            self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self.src = [torch.empty((B, lib.d, T), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.out = [torch.empty((B, T, lib.d), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.top_idx = torch.empty((B, T, k), dtype=torch.int64, device=dev)
+            self.top_score = torch.empty((B, T, k), dtype=torch.float32, device=dev)
+            self.ev_in = [torch.cuda.Event() for _ in range(depth)]      # the step's input has landed in src[i]
+            self.ev_run = [torch.cuda.Event() for _ in range(depth)]     # the step's match has finished (src[i] is free, out[i] is ready)
+            self.ev_out = [torch.cuda.Event() for _ in range(depth)]     # out[i] has left for the host
+            self.workspace = None
+        self.n = 0
+
+    def step(self, src_host: torch.Tensor, out_host: torch.Tensor):
+        if not (src_host.is_pinned() and out_host.is_pinned()):
+            raise RuntimeError("alive_vc_b200: HostPipeline needs pinned (page-locked) host buffers")
+        i = self.n % self.depth
+        dev = self.lib.device
+        main = torch.cuda.current_stream(dev)
+        first = self.n < self.depth
+        if not first:
+            self.s_in.wait_event(self.ev_run[i])          # the match that last read src[i] is done
+        else:
+            self.s_in.wait_stream(main)                    # (allocation order)
+        with torch.cuda.stream(self.s_in):
+            self.src[i].copy_(src_host, non_blocking=True)
+            self.ev_in[i].record(self.s_in)
+        main.wait_event(self.ev_in[i])
+        if not first:
+            main.wait_event(self.ev_out[i])                # out[i] of the step before last has been read out
+        info = {}
+        M.run_match(self.src[i], self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max, workspace=self.workspace,
+                    out=self.out[i], top_idx=self.top_idx, top_score=self.top_score, info_sink=info)
+        self.workspace = info["workspace"]
+        self.ev_run[i].record(main)
+        self.s_out.wait_event(self.ev_run[i])
+        with torch.cuda.stream(self.s_out):
+            out_host.copy_(self.out[i], non_blocking=True)
+            self.ev_out[i].record(self.s_out)
+        self.n += 1
+
+    def drain(self):
+        """The caller's stream waits for every copy issued so far (no host synchronisation)."""
+        main = torch.cuda.current_stream(self.lib.device)
+        for i in range(min(self.n, self.depth)):
+            main.wait_event(self.ev_out[i])
+
+
 class RowsContentEncoder(torch.nn.Module):
     """The producer step around a content encoder with the reference's structure
     (module/content_encoder.py:8-25: `input_layer` -> `mid_layers` -> `output_layer`, a 1x1 Conv1d to 768 channels;

@@ -486,6 +486,10 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
     value = units_per_step / (ms_per_step * 1e-3)
 
     # ---- end-to-end: host buffers through the public API ----
+    e2e_api = None
+
+    def e2e_finish():
+        pass
     scattered = world > 1 and not batched and B == 1
     if scattered:
         # every query byte crosses PCIe once: this rank's T/world slice in, its slice of the result out
@@ -505,20 +509,33 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         # the result is a transposed view of a contiguous [B,T,D] block (like the reference's); the pinned
         # host buffer has the same strides, so the device->host read is one plain memcpy
         _b, _d, _t = src_dev.shape
-        out_host = torch.empty((_b, _t, _d), dtype=torch.float32).pin_memory().transpose(1, 2)
+        out_rows_host = torch.empty((_b, _t, _d), dtype=torch.float32).pin_memory()
+        out_host = out_rows_host.transpose(1, 2)
+        if world == 1 and not streaming:
+            # throughput workloads: lifecycle.HostPipeline - the same three operations per step, double-buffered so
+            # that the copies of neighbouring steps overlap the match (every step still moves its own bytes both ways)
+            from alive_vc_b200.lifecycle import HostPipeline
+            pipeline = HostPipeline(lib, _b, _t, K, 0.0, "screen", variant)
+            e2e_api = "lifecycle.HostPipeline.step"
 
-        def e2e_step():
-            # the streaming matcher copies the pinned host chunk straight into its static input buffer
-            s = src_host if streaming else src_host.to(dev, non_blocking=True)
-            o = step(s)
-            out_host.copy_(o, non_blocking=True)
+            def e2e_step():
+                pipeline.step(src_host, out_rows_host)
+            e2e_finish = pipeline.drain
+        else:
+            def e2e_step():
+                # the streaming matcher copies the pinned host chunk straight into its static input buffer
+                s = src_host if streaming else src_host.to(dev, non_blocking=True)
+                o = step(s)
+                out_host.copy_(o, non_blocking=True)
         io_bytes = src_host.numel() * 4 * (world if batched else 1)
     for _ in range(min(warmup, 3)):
         e2e_step()
+    e2e_finish()
     barrier()
     e0.record()
     for _ in range(steps):
         e2e_step()
+    e2e_finish()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -603,7 +620,9 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
             "e2e": {"value": e2e_value, "unit": "query_frames/s", "h2d_bytes_per_step": io_bytes,
                     "d2h_bytes_per_step": io_bytes, "ms_per_step": e2e_ms / steps,
                     "path": "per rank: H2D of its T/N query slice -> all-gather over NVLink -> match -> D2H of its T/N result slice"
-                            if scattered else "H2D of the queries -> match -> D2H of the result"},
+                            if scattered else ("H2D of the queries -> match -> D2H of the result, every step; double-buffered "
+                                               "(lifecycle.HostPipeline: the copies of neighbouring steps overlap the match)"
+                                               if e2e_api else "H2D of the queries -> match -> D2H of the result")},
             "gpu_launches": launches,
             "roofline": roof,
             "parity": parity,

@@ -437,3 +437,25 @@ def test_host_streaming_matcher_deferred_collect_pass():
         fb = M.last_info.fallback_queries()
         assert (fb > 0) == (it % 2 == 0) and M.last_info.collect
         assert torch.equal(out.contiguous(), want.transpose(1, 2).cpu())
+
+
+@pytest.mark.parametrize("B,T,N", [(1, 3000, 50_000), (3, 500, 8_000)])
+def test_host_pipeline_overlapped_copies(B, T, N):
+    """lifecycle.HostPipeline: H2D / match / D2H of successive batches overlap on three streams through double-buffered
+    device staging; every batch's rows equal match_packed on the same frames (different data per step, so a buffer
+    recycled too early would show)."""
+    from alive_vc_b200.lifecycle import HostPipeline
+    g = torch.Generator(device="cuda").manual_seed(40)
+    lib = A.pack_library(torch.randn(1, 768, N, device="cuda", generator=g))
+    hp = HostPipeline(lib, B, T, 4, 0.25)
+    srcs = [torch.randn(B, 768, T, generator=torch.Generator().manual_seed(s)).pin_memory() for s in range(5)]
+    outs = [torch.empty((B, T, 768)).pin_memory() for _ in range(5)]
+    for s_h, o_h in zip(srcs, outs):
+        hp.step(s_h, o_h)
+    hp.drain()
+    torch.cuda.synchronize()
+    for s_h, o_h in zip(srcs, outs):
+        want, _, _ = A.match_packed(s_h.cuda(), lib, 4, 0.25)
+        assert torch.equal(o_h, want.cpu())
+    with pytest.raises(RuntimeError, match="pinned"):
+        hp.step(torch.randn(B, 768, T), outs[0])
