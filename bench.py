@@ -511,7 +511,7 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         _b, _d, _t = src_dev.shape
         out_rows_host = torch.empty((_b, _t, _d), dtype=torch.float32).pin_memory()
         out_host = out_rows_host.transpose(1, 2)
-        if world == 1 and not streaming:
+        if world == 1 and not latency_workload:
             # throughput workloads: lifecycle.HostPipeline - the same three operations per step, double-buffered so
             # that the copies of neighbouring steps overlap the match (every step still moves its own bytes both ways)
             from alive_vc_b200.lifecycle import HostPipeline
