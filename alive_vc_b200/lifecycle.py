@@ -402,13 +402,17 @@ class HostPipeline:
     Results are those of match_packed on the same frames."""
 
     def __init__(self, lib: M.PackedFrames, B: int, T: int, k: int = 4, alpha: float = 0.0, mode: str = "auto",
-                 variant: int = 0, r_max: int = M.DEFAULT_R_MAX, depth: int = 2):
+                 variant: int = 0, r_max: int = M.DEFAULT_R_MAX, depth: int = 2, match_fn=None):
+        """`match_fn(src_dev [B, D, T]) -> rows [B, T, D]` (a device tensor, any strides) replaces the local match - e.g.
+        a ShardedLibrary's scattered match, whose collectives then run on the caller's stream between the copies."""
         dev = lib.device
         self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max, self.depth = lib, k, float(alpha), mode, variant, r_max, depth
+        self.match_fn = match_fn
         with torch.cuda.device(dev):
             self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
             self.src = [torch.empty((B, lib.d, T), dtype=torch.float32, device=dev) for _ in range(depth)]
-            self.out = [torch.empty((B, T, lib.d), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.out = [None if match_fn is not None else torch.empty((B, T, lib.d), dtype=torch.float32, device=dev)
+                        for _ in range(depth)]
             self.top_idx = torch.empty((B, T, k), dtype=torch.int64, device=dev)
             self.top_score = torch.empty((B, T, k), dtype=torch.float32, device=dev)
             self.ev_in = [torch.cuda.Event() for _ in range(depth)]      # the step's input has landed in src[i]
@@ -434,10 +438,13 @@ class HostPipeline:
         main.wait_event(self.ev_in[i])
         if not first:
             main.wait_event(self.ev_out[i])                # out[i] of the step before last has been read out
-        info = {}
-        M.run_match(self.src[i], self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max, workspace=self.workspace,
-                    out=self.out[i], top_idx=self.top_idx, top_score=self.top_score, info_sink=info)
-        self.workspace = info["workspace"]
+        if self.match_fn is not None:
+            self.out[i] = self.match_fn(self.src[i])       # (kept referenced until its copy has been issued AND the slot recycled)
+        else:
+            info = {}
+            M.run_match(self.src[i], self.lib, self.k, self.alpha, self.mode, self.variant, self.r_max, workspace=self.workspace,
+                        out=self.out[i], top_idx=self.top_idx, top_score=self.top_score, info_sink=info)
+            self.workspace = info["workspace"]
         self.ev_run[i].record(main)
         self.s_out.wait_event(self.ev_run[i])
         with torch.cuda.stream(self.s_out):

@@ -496,12 +496,16 @@ def measure(env, workload: str, steps: int, warmup: int, headline: bool, cluster
         q_lo, q_hi = shard_bounds(T, world, rank)
         src_host = torch.empty((1, D, q_hi - q_lo), dtype=torch.float32).pin_memory()
         src_host.copy_(src_dev[:, :, q_lo:q_hi])
-        out_host = torch.empty((1, q_hi - q_lo, D), dtype=torch.float32).pin_memory().transpose(1, 2)
+        out_rows_host = torch.empty((1, q_hi - q_lo, D), dtype=torch.float32).pin_memory()
+        from alive_vc_b200.lifecycle import HostPipeline
+        # the same double-buffered host feeding as on one GPU; the collectives of the scattered match run on the
+        # main stream between the copies
+        pipeline = HostPipeline(lib, 1, q_hi - q_lo, K, 0.0, match_fn=lambda s: sharded.match(
+            s, K, 0.0, scattered=True, t_total=T).transpose(1, 2))
 
         def e2e_step():
-            s = src_host.to(dev, non_blocking=True)
-            o = sharded.match(s, K, 0.0, scattered=True, t_total=T)
-            out_host.copy_(o, non_blocking=True)
+            pipeline.step(src_host, out_rows_host)
+        e2e_finish = pipeline.drain
         io_bytes = T * D * 4                       # whole job, all ranks together
     else:
         src_host = torch.empty(src_dev.shape, dtype=torch.float32).pin_memory()

@@ -459,3 +459,12 @@ def test_host_pipeline_overlapped_copies(B, T, N):
         assert torch.equal(o_h, want.cpu())
     with pytest.raises(RuntimeError, match="pinned"):
         hp.step(torch.randn(B, 768, T), outs[0])
+    # a caller-supplied match (what the sharded e2e path passes: its scattered match) in the same pipeline
+    hp2 = HostPipeline(lib, B, T, match_fn=lambda sd: A.match_packed(sd, lib, 4, 0.25)[0])
+    outs2 = [torch.empty((B, T, 768)).pin_memory() for _ in range(5)]
+    for s_h, o_h in zip(srcs, outs2):
+        hp2.step(s_h, o_h)
+    hp2.drain()
+    torch.cuda.synchronize()
+    for a, b_ in zip(outs, outs2):
+        assert torch.equal(a, b_)
