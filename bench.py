@@ -11,9 +11,12 @@ A "step" = one pass of the hot path over one batch of T synthetic query frames:
   value : inputs resident in HBM, CUDA-event timed, barrier + synchronize on both sides, max over ranks,
           value = T / time
   e2e   : the same call through the public API with HOST buffers: pinned-host queries -> H2D -> match -> D2H of
-          the matched features, every step.  At N > 1 every query byte crosses PCIe ONCE: rank r copies its T/N
-          slice of the frames, the slices are all-gathered over NVLink, and rank r reads back its T/N slice of
-          the result (ShardedLibrary.match(scattered=True)); the byte counts are the whole job's.
+          the matched features, every step.  Throughput workloads go through lifecycle.HostPipeline (double-buffered
+          device staging: the copies of neighbouring steps overlap the match; the timed region ends when the last
+          result has reached the host), latency workloads through HostStreamingMatcher (one blocking chunk at a
+          time).  At N > 1 every query byte crosses PCIe ONCE: rank r copies its T/N slice of the frames, the slices
+          are all-gathered over NVLink, and rank r reads back its T/N slice of the result
+          (ShardedLibrary.match(scattered=True) inside the same pipeline); the byte counts are the whole job's.
   roofline        : the fused tcgen05 similarity+top-list kernel (alive_knn_search), its own CUDA-event duration
                     inside the timed region vs MEASURED_PEAKS.json
   roofline_gather : the standalone gather-mean kernel (K4) on the step's own indices vs the HBM peak (algorithmic
